@@ -1,0 +1,388 @@
+"""ORACLE — test infrastructure, not product code.
+
+CPU fp32 restatement (functional PyTorch over a plain ``state_dict``) of the
+reference's data-parallel hot path, every function citing the reference lines
+it follows (paths relative to /root/reference/AGQA/src).  The path is floating
+point, so the restatement is a torch fp32 one; the integer part (the Hungarian
+matching) is restated in C in ``oracle/lsap.c``.
+
+Parity pinning: the reference ships NO tests / golden vectors for this path
+("parity unpinned" by its own tests).  This oracle is therefore
+pinned against outputs of the UNMODIFIED reference run in the build container:
+``tools/gen_golden.py`` imports the reference (tools/ref_harness.py), loads the
+deterministic weights of ``make_state_dict`` with ``load_state_dict(strict=True)``,
+runs config 1 (B=2, fwd + matcher + loss + bwd) and commits the outputs to
+``tests/golden/hgqa_b2.npz`` / ``vqa_b2.npz``.  ``tests/test_oracle_golden.py``
+checks this file against those vectors (fp32, 2e-4 abs / rel), and
+``tests/test_oracle_vs_reference.py`` re-runs the reference live when
+/root/reference is present.
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` /
+``--impl reference`` legs may import this module.
+"""
+import ctypes
+import math
+import os
+import zlib
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HID = 768
+HEADS = 12
+LN_EPS_BERT = 1e-12   # modeling_capsbert.py:310,338,428,482 ; agqa_model.py:108
+LN_EPS_DETR = 1e-5    # transformer.py:199-201 (nn.LayerNorm default)
+
+# --------------------------------------------------------------------------- #
+# Deterministic weights for a reference-shaped state_dict
+# --------------------------------------------------------------------------- #
+
+def canonical_key(key):
+    """Aliased state_dict entries (one module registered under several names,
+    modeling_capsbert.py:1122-1124, 1247-1249, 1144, 1811) → one canonical name."""
+    for n in ("0", "1"):
+        key = key.replace(".x_layers.%s." % n, ".cross_attn_layer.cross.")
+    if ".pooler.dense2." in key:
+        key = key.replace(".pooler.dense2.", ".pooler_dict.cross.dense2.")
+    return key
+
+
+def make_state_dict(key_shapes, seed=0):
+    """key_shapes: {key: [shape, dtype_str]} (tests/golden/state_dict_keys.json).
+    Values depend only on (canonical key, seed): N(0,0.04) for matrices and
+    embeddings, 1+N(0,0.1) for LayerNorm gains, N(0,0.02) biases (non-zero on
+    purpose — a zero bias would hide bias-path bugs), N(0,1) for the hypergraph
+    query embeddings as in the reference's default nn.Embedding init, and Conv3d
+    weights scaled so the visual tokens enter the relation layers at O(1) rms."""
+    out, cache = {}, {}
+    for key, (shape, dtype) in key_shapes.items():
+        ck = canonical_key(key)
+        if ck in cache:
+            out[key] = cache[ck]
+            continue
+        if key.endswith("position_ids"):
+            t = torch.arange(shape[-1]).expand(shape).clone()
+        else:
+            g = torch.Generator().manual_seed((zlib.crc32(ck.encode()) + seed) & 0x7FFFFFFF)
+            t = torch.randn(shape, generator=g, dtype=torch.float32)
+            is_ln_gain = ("LayerNorm.weight" in ck or ".norm1.weight" in ck or ".norm2.weight" in ck
+                          or ".norm3.weight" in ck or "layer_norm.weight" in ck
+                          or ck in ("class_embed.2.weight", "action_embed.2.weight", "logit_fc.2.weight"))
+            if is_ln_gain:
+                t = 1.0 + 0.1 * t
+            elif ck.startswith(("relation_query_embed.", "action_query_embed.")) and ck.endswith("embeddings.weight"):
+                t[0].zero_()           # padding_idx=0 row (modeling_capsbert.py:305-306)
+            elif ck.endswith("conv.1.weight"):
+                t = 0.005 * t          # keeps visual tokens at O(1) rms (K = 2048*45)
+            elif ck.endswith("conv.4.weight"):
+                t = 0.0067 * t
+            elif t.dim() >= 2:
+                t = 0.04 * t           # scores std ~1: a softmax that is neither flat nor one-hot
+            else:
+                t = 0.02 * t
+        cache[ck] = t
+        out[key] = t
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# Small pieces
+# --------------------------------------------------------------------------- #
+
+def _lin(sd, p, x):
+    return F.linear(x, sd[p + ".weight"], sd[p + ".bias"])
+
+
+def _ln(sd, p, x, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def gelu_erf(x):
+    """modeling_capsbert.py:127-133 — exact erf form."""
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def _split_heads(x):
+    b, l, _ = x.shape
+    return x.view(b, l, HEADS, HID // HEADS).transpose(1, 2)
+
+
+def bert_attention(sd, p, x, ctx, add_mask):
+    """modeling_capsbert.py:384-421: three separate projections, scores/sqrt(64)
+    AFTER QK^T, additive mask, softmax over keys (dropout off: eval)."""
+    q = _split_heads(_lin(sd, p + ".query", x))
+    k = _split_heads(_lin(sd, p + ".key", ctx))
+    v = _split_heads(_lin(sd, p + ".value", ctx))
+    s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(HID // HEADS)
+    if add_mask is not None:
+        s = s + add_mask
+    o = torch.matmul(torch.softmax(s, dim=-1), v)
+    return o.transpose(1, 2).reshape(x.shape[0], x.shape[1], HID)
+
+
+def dense_residual_ln(sd, p, h, residual):
+    """BertAttOutput / BertOutput, modeling_capsbert.py:431-435, 485-489."""
+    return _ln(sd, p + ".LayerNorm", _lin(sd, p + ".dense", h) + residual, LN_EPS_BERT)
+
+
+def bert_layer(sd, p, x, add_mask):
+    """BertLayer, modeling_capsbert.py:499-503 (self-attn :456-460, FFN :472-489)."""
+    a = bert_attention(sd, p + ".attention.self", x, x, add_mask)
+    a = dense_residual_ln(sd, p + ".attention.output", a, x)
+    h = gelu_erf(_lin(sd, p + ".intermediate.dense", a))
+    return dense_residual_ln(sd, p + ".output", h, a)
+
+
+def cross_layer(sd, p, lang, lang_mask, visn, visn_mask):
+    """CrossLayer, modeling_capsbert.py:658-677: ONE attention block used in both
+    directions (:643-644), no self-attention, then separate FFNs (:647-655)."""
+    att = p + ".visual_attention"
+    l_att = dense_residual_ln(sd, att + ".output", bert_attention(sd, att + ".att", lang, visn, visn_mask), lang)
+    v_att = dense_residual_ln(sd, att + ".output", bert_attention(sd, att + ".att", visn, lang, lang_mask), visn)
+    l_out = dense_residual_ln(sd, p + ".lang_output", gelu_erf(_lin(sd, p + ".lang_inter.dense", l_att)), l_att)
+    v_out = dense_residual_ln(sd, p + ".visn_output", gelu_erf(_lin(sd, p + ".visn_inter.dense", v_att)), v_att)
+    return l_out, v_out
+
+
+def pooler2(sd, p, first, second):
+    """BertPooler2, modeling_capsbert.py:1525-1533: tanh(W [first_cls ; second_cls])."""
+    return torch.tanh(_lin(sd, p + ".dense2", torch.cat([first[:, 0], second[:, 0]], dim=-1)))
+
+
+def visual_front_end(sd, p, feat):
+    """VisualFeatEncoder (no_caps), modeling_capsbert.py:989-996, 1037-1073:
+    pad H,W by 1 → Conv3d(2048→768,(5,3,3)) → GELU → pad → Conv3d(768→768) → GELU →
+    tokens (t,h,w) → prepend cls → + learned position rows 0..392."""
+    x = feat.float()
+    x = gelu_erf(F.conv3d(F.pad(x, (1, 1, 1, 1)), sd[p + ".conv.1.weight"], sd[p + ".conv.1.bias"]))
+    x = gelu_erf(F.conv3d(F.pad(x, (1, 1, 1, 1)), sd[p + ".conv.4.weight"], sd[p + ".conv.4.bias"]))
+    b, c = x.shape[:2]
+    tok = x.permute(0, 2, 3, 4, 1).reshape(b, -1, c)
+    tok = torch.cat([sd[p + ".cls_token"].expand(b, -1, -1), tok], dim=1)
+    return tok + sd[p + ".position_encoding.pe.weight"][: tok.shape[1]].unsqueeze(0)
+
+
+def bert_embeddings(sd, p, ids, seg):
+    """BertEmbeddings, modeling_capsbert.py:341-355."""
+    # all three tables are nn.Embedding(padding_idx=0) (:331-333): row 0 never receives gradient
+    pos = torch.arange(ids.shape[1]).unsqueeze(0).expand_as(ids)
+    e = (F.embedding(ids, sd[p + ".word_embeddings.weight"], padding_idx=0)
+         + F.embedding(pos, sd[p + ".position_embeddings.weight"], padding_idx=0)
+         + F.embedding(seg, sd[p + ".token_type_embeddings.weight"], padding_idx=0))
+    return _ln(sd, p + ".LayerNorm", e, LN_EPS_BERT)
+
+
+def additive_key_mask(mask01):
+    """NoCapsModel.forward, modeling_capsbert.py:1826-1844: (1-mask)*-10000 → [B,1,1,L]."""
+    return ((1.0 - mask01.float()) * -10000.0)[:, None, None, :]
+
+
+def lxrt_encoder(sd, ids, mask, seg, feat, boxes, visn_tokens=None, p="lxrt_encoder.model.bert"):
+    """NoCapsModel.forward :1814-1857 + NoCapsEncoder.forward :1254-1302.
+    ``visn_tokens`` (B,393,768) bypasses the Conv3d front-end (hot-path-only runs)."""
+    lmask = additive_key_mask(mask)
+    vmask = additive_key_mask(boxes)          # boxes doubles as visual mask (:1836); ones → zeros
+    lang = bert_embeddings(sd, p + ".embeddings", ids, seg)
+    visn = visual_front_end(sd, p + ".encoder.visn_fc", feat) if visn_tokens is None else visn_tokens.float()
+    for i in range(5):
+        lang = bert_layer(sd, "%s.encoder.layer.%d" % (p, i), lang, lmask)
+    lang_l = lang
+    for i in range(5):
+        visn = bert_layer(sd, "%s.encoder.r_layers.%d" % (p, i), visn, vmask)
+    visn_r = visn
+    for _ in range(2):                        # the SAME module twice (:1247-1249)
+        lang, visn = cross_layer(sd, p + ".encoder.cross_attn_layer.cross", lang, lmask, visn, vmask)
+    pooled = pooler2(sd, p + ".pooler_dict.cross", visn, lang)   # pooler(visn, lang) :1855
+    return dict(lang=lang, visn=visn, pooled=pooled, lang_l=lang_l, visn_r=visn_r, lang_mask=lmask)
+
+
+def hg_embeddings(sd, p, seg_ids):
+    """HGEmbeddings, modeling_capsbert.py:313-325: ALL word rows (no lookup) + frame-id rows."""
+    e = (sd[p + ".word_embeddings.weight"].unsqueeze(0)
+         + F.embedding(seg_ids, sd[p + ".token_type_embeddings.weight"], padding_idx=0))
+    return _ln(sd, p + ".LayerNorm", e, LN_EPS_BERT)
+
+
+def block_causal_mask(n_frames, per_frame):
+    """entry.py:114-121: -inf where key frame > query frame, else 0."""
+    f = torch.arange(n_frames).repeat_interleave(per_frame)
+    m = torch.zeros(f.numel(), f.numel())
+    m[f[None, :] > f[:, None]] = float("-inf")
+    return m
+
+
+def mha(sd, p, q_in, k_in, v_in, add_mask):
+    """nn.MultiheadAttention (transformer.py:192-193), batch-first restatement:
+    packed in_proj rows [0:768]=q [768:1536]=k [1536:2304]=v; q scaled by 1/8 BEFORE QK^T."""
+    w, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
+    q = _split_heads(F.linear(q_in, w[:HID], b[:HID])) * (1.0 / math.sqrt(HID // HEADS))
+    k = _split_heads(F.linear(k_in, w[HID:2 * HID], b[HID:2 * HID]))
+    v = _split_heads(F.linear(v_in, w[2 * HID:], b[2 * HID:]))
+    s = torch.matmul(q, k.transpose(-1, -2))
+    if add_mask is not None:
+        s = s + add_mask
+    o = torch.matmul(torch.softmax(s, dim=-1), v).transpose(1, 2).reshape(q_in.shape[0], q_in.shape[1], HID)
+    return _lin(sd, p + ".out_proj", o)
+
+
+def decoder_layer(sd, p, tgt, memory, tgt_mask, query_pos):
+    """TransformerDecoderLayer.forward_post, transformer.py:212-233."""
+    qk = tgt + query_pos
+    tgt = _ln(sd, p + ".norm1", tgt + mha(sd, p + ".self_attn", qk, qk, tgt, tgt_mask), LN_EPS_DETR)
+    tgt = _ln(sd, p + ".norm2", tgt + mha(sd, p + ".multihead_attn", tgt + query_pos, memory, memory, None), LN_EPS_DETR)
+    ff = _lin(sd, p + ".linear2", F.relu(_lin(sd, p + ".linear1", tgt)))
+    return _ln(sd, p + ".norm3", tgt + ff, LN_EPS_DETR)
+
+
+def decoder(sd, p, memory, tgt_mask, query_pos, n_layers=5):
+    """TransformerDecoder.forward, transformer.py:95-124; tgt starts at zero (agqa_model.py:235,245)."""
+    tgt = torch.zeros_like(query_pos)
+    for i in range(n_layers):
+        tgt = decoder_layer(sd, "%s.layers.%d" % (p, i), tgt, memory, tgt_mask, query_pos)
+    return tgt
+
+
+def mlp_head(sd, p, x):
+    """class_embed / action_embed / logit_fc, agqa_model.py:105-110,121-126,135-140."""
+    h = _ln(sd, p + ".2", gelu_erf(_lin(sd, p + ".0", x)), LN_EPS_BERT)
+    return _lin(sd, p + ".3", h)
+
+
+def cross_encoder(sd, p, lang, lang_mask, hg, hg_mask01, n_act=3, n_rel=8):
+    """CrossEncoder.forward, modeling_capsbert.py:1152-1215."""
+    b, n, d = hg.shape
+    t = n // (n_act + n_rel)
+    typ = torch.cat([sd[p + ".act_token"].expand(1, n_act, d), sd[p + ".rel_token"].expand(1, n_rel, d)], dim=1)
+    hg = (hg.view(b, t, -1, d) + typ.unsqueeze(1)).view(b, -1, d)
+    hg = torch.cat([sd[p + ".cls_token"].expand(b, -1, -1), hg], dim=1)
+    hmask = None
+    if hg_mask01 is not None:
+        hmask = additive_key_mask(torch.cat([torch.ones(b, 1), hg_mask01.view(b, -1).float()], dim=1))
+    for _ in range(2):
+        lang, hg = cross_layer(sd, p + ".cross_attn_layer.cross", lang, lang_mask, hg, hmask)
+    return pooler2(sd, p + ".pooler_dict.cross", hg, lang)
+
+
+# --------------------------------------------------------------------------- #
+# Whole-model forward (AGQAModel.forward, agqa_model.py:166-269)
+# --------------------------------------------------------------------------- #
+
+def agqa_forward(sd, inp, task="hgqa", use_hg_mask=False, n_frames=16, n_rel=8, n_act=3):
+    """inp: dict(feat | visn_tokens, boxes, input_ids, input_mask, segment_ids,
+    rel_segment_ids, act_segment_ids, hg_mask).  Returns dict of every graded tensor."""
+    enc = lxrt_encoder(sd, inp["input_ids"], inp["input_mask"], inp["segment_ids"],
+                       inp.get("feat"), inp["boxes"], visn_tokens=inp.get("visn_tokens"))
+    out = dict(enc)
+    out["logit"] = mlp_head(sd, "logit_fc", enc["pooled"])                       # :205 / :191
+    if task == "vqa":
+        return out
+    memory = enc["visn_r"]                                                       # :218 (pre-cross features)
+    rel_q = hg_embeddings(sd, "relation_query_embed", inp["rel_segment_ids"])    # :234
+    rel_out = decoder(sd, "rel_decoder", memory, block_causal_mask(n_frames, n_rel), rel_q)
+    out["rel_logits"] = mlp_head(sd, "class_embed", rel_out)                     # :238
+    act_q = hg_embeddings(sd, "action_query_embed", inp["act_segment_ids"])      # :244
+    act_out = decoder(sd, "action_decoder", memory, block_causal_mask(n_frames, n_act), act_q)
+    out["act_logits"] = mlp_head(sd, "action_embed", act_out)                    # :249
+    b = rel_out.shape[0]
+    hg_in = torch.cat([act_out.view(b, n_frames, n_act, HID), rel_out.view(b, n_frames, n_rel, HID)], dim=2)  # :255-258
+    hg_mask = inp["hg_mask"] if use_hg_mask else None                            # :261-264
+    out["rel_out"], out["act_out"] = rel_out, act_out
+    out["hg_pooled"] = cross_encoder(sd, "hgq_encoder", enc["lang_l"], enc["lang_mask"],
+                                     hg_in.view(b, -1, HID), hg_mask, n_act, n_rel)   # :265
+    out["hg_logit"] = mlp_head(sd, "logit_fc", out["hg_pooled"])                 # :266
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# Hungarian matching (matcher.py:59-80) and set loss (agqaHGQA.py:166-229, 344-378)
+# --------------------------------------------------------------------------- #
+
+_LIB = None
+
+
+def lsap_lib():
+    """ctypes handle on oracle/_build/liblsap_oracle.so (built by __graft_entry__.build())."""
+    global _LIB
+    if _LIB is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(here, "_build", "liblsap_oracle.so")
+        if not os.path.exists(so):
+            os.makedirs(os.path.dirname(so), exist_ok=True)
+            import subprocess
+            subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(here, "lsap.c"), "-lm"])
+        _LIB = ctypes.CDLL(so)
+    return _LIB
+
+
+def lsap(cost):
+    """cost: 2-D numpy float array. Returns (row_ind, col_ind) int64 arrays like scipy."""
+    c = np.ascontiguousarray(cost, dtype=np.float64)
+    nr, nc = c.shape
+    k = min(nr, nc)
+    rows = np.zeros(max(k, 1), dtype=np.int64)
+    cols = np.zeros(max(k, 1), dtype=np.int64)
+    rc = lsap_lib().shg_oracle_lsap_f64(
+        ctypes.c_int(nr), ctypes.c_int(nc), c.ctypes.data_as(ctypes.c_void_p),
+        rows.ctypes.data_as(ctypes.c_void_p), cols.ctypes.data_as(ctypes.c_void_p))
+    if rc == -2:
+        raise ValueError("matrix contains invalid numeric entries")
+    if rc == -1:
+        raise ValueError("cost matrix is infeasible")
+    if rc < 0:
+        raise ValueError("lsap oracle: dimension too large")
+    return rows[:rc], cols[:rc]
+
+
+def frame_costs(logits, frame_labels, n_frames=16):
+    """matcher.py:62-76: C = -softmax(logits)[:, labels] per (sample, frame) block.
+    frame_labels: list over B*n_frames of 1-D int64 tensors. Returns list of [q_f, n_i] fp32."""
+    b, q, _ = logits.shape
+    q_f = q // n_frames
+    prob = logits.flatten(0, 1).softmax(-1).view(b * n_frames, q_f, -1)
+    return [-prob[i][:, lab] for i, lab in enumerate(frame_labels)]
+
+
+def hungarian_match(logits, frame_labels, n_frames=16):
+    """HungarianMatcher.forward per-frame branch, matcher.py:59-80."""
+    res = []
+    for c in frame_costs(logits, frame_labels, n_frames):
+        r, cc = lsap(c.detach().numpy())
+        res.append((torch.as_tensor(r.copy(), dtype=torch.int64), torch.as_tensor(cc.copy(), dtype=torch.int64)))
+    return res
+
+
+def set_loss(logits, frame_labels, indices, eos_coef=0.1, n_frames=16):
+    """AGQA.loss_labels (loss_hg_per_frame branch), agqaHGQA.py:203-229:
+    background class 0 everywhere, matched slots ← labels, weighted CE
+    (weight[0]=eos_coef, agqaHGQA.py:103-112) = Σ w·nll / Σ w; class_error = 100 − top-1
+    accuracy on matched slots (vis_utils.py:388-403; 0 matched → accuracy 0 → error 100)."""
+    b, q, c = logits.shape
+    q_f = q // n_frames
+    lg = logits.reshape(b * n_frames, q_f, c)
+    tgt = torch.zeros(b * n_frames, q_f, dtype=torch.int64)
+    for f, (rows, cols) in enumerate(indices):
+        tgt[f, rows] = frame_labels[f][cols]
+    w = torch.ones(c)
+    w[0] = eos_coef
+    loss = F.cross_entropy(lg.transpose(1, 2), tgt, w)
+    fi = torch.cat([torch.full_like(r, f) for f, (r, _) in enumerate(indices)]) if indices else torch.zeros(0, dtype=torch.int64)
+    ri = torch.cat([r for r, _ in indices]) if indices else torch.zeros(0, dtype=torch.int64)
+    if ri.numel() == 0:
+        err = torch.tensor(100.0)
+    else:
+        pred = lg[fi, ri].argmax(-1)
+        err = 100.0 - (pred == tgt[fi, ri]).float().mean() * 100.0
+    return loss, err, tgt
+
+
+def hgqa_total_loss(out, inp, n_frames=16):
+    """agqaHGQA.py:344-378: BCEWithLogits(hg_logit, target)·N_ans + rel CE + act CE."""
+    n_ans = out["hg_logit"].shape[1]
+    qa = F.binary_cross_entropy_with_logits(out["hg_logit"], inp["target"]) * n_ans
+    rel_idx = hungarian_match(out["rel_logits"], inp["rel_labels"], n_frames)
+    act_idx = hungarian_match(out["act_logits"], inp["act_labels"], n_frames)
+    rel_ce, rel_err, _ = set_loss(out["rel_logits"], inp["rel_labels"], rel_idx, 0.1, n_frames)
+    act_ce, act_err, _ = set_loss(out["act_logits"], inp["act_labels"], act_idx, 0.1, n_frames)
+    return dict(total=qa + rel_ce + act_ce, qa=qa, rel_ce=rel_ce, act_ce=act_ce,
+                rel_err=rel_err, act_err=act_err, rel_idx=rel_idx, act_idx=act_idx)
