@@ -1,0 +1,152 @@
+/*
+ * libshgvqa — C ABI of the B200-native (sm_100a) hot path of SHG-VQA.
+ *
+ * The reference (aurooj/SHG-VQA) has no FFI layer: its hot path is reached through
+ * Python nn.Module symbols.  Each entry point below names the
+ * reference computation it replaces (paths relative to AGQA/src/).  Conventions:
+ *   - plain pointers and sizes; all pointers are DEVICE pointers unless named host_*;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does not
+ *     allocate, and is CUDA-graph capturable;
+ *   - returns 0 on success or a negative SHG_E* code; shg_last_error() gives the text;
+ *   - matrices are row-major; activations bf16 (uint16_t storage), master weights and
+ *     gradients fp32, statistics fp32, LSAP arithmetic fp64 (as scipy's).
+ */
+#ifndef SHGVQA_H
+#define SHGVQA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHG_OK 0
+#define SHG_EINVAL (-1)      /* bad argument                                  */
+#define SHG_ESHAPE (-2)      /* unsupported shape / alignment                 */
+#define SHG_ECUDA (-3)       /* CUDA runtime / driver error                   */
+#define SHG_EDEVICE (-4)     /* not an sm_100 device                          */
+
+const char* shg_last_error(void);
+int shg_version(void);
+/* Refuses anything that is not compute capability 10.x (there is no fallback path). */
+int shg_device_check(int device);
+
+/* ------------------------------------------------------------------ Hungarian matching
+ * Replaces the CPU loop `[linear_sum_assignment(c[i]) for i, c in enumerate(C.split(sizes, -1))]`
+ * (lxrt/matcher.py:76-80; scipy's rectangular_lsap, tie-break included).  One CTA per frame.
+ *
+ * cost      fp32 [n_frames, q_f, ld]: frame f owns rows [f*q_f,(f+1)*q_f) and the column range
+ *           [col_off[f], col_off[f+1]) — the layout of `C.view(bs*clip_len, q, -1)` (matcher.py:76).
+ * rows/cols int32 [n_frames, q_f]: matched (query, target) pairs, query ascending, -1 padded.
+ * n_match   int32 [n_frames]; status int32 [n_frames]: 0 ok, -1 infeasible, -2 NaN/-inf entry
+ *           (scipy raises ValueError for both).
+ * q_f <= 32 and every frame's target count <= 32.
+ */
+int shg_lsap_batched(const float* cost, int n_frames, int q_f, int ld, const int32_t* col_off,
+                     int32_t* rows, int32_t* cols, int32_t* n_match, int32_t* status, void* stream);
+
+/* Fused matcher front half + solver: softmax over classes, gather of the target columns, cost = -p,
+ * LSAP (lxrt/matcher.py:59-80) and, optionally, the scatter of matched labels into `target_classes`
+ * (tasks/agqaHGQA.py:216-221; background class 0 elsewhere).  logits fp32 or bf16 [n_frames*q_f, n_cls]
+ * (ld_logits elements per row); labels int32, CSR by frame through label_off[n_frames+1].
+ * row_max / row_lse fp32 and row_argmax int32 [n_frames*q_f]: softmax statistics reused by the set loss
+ * (row_argmax may be NULL).  target_classes int32 [n_frames*q_f] or NULL. */
+int shg_match_from_logits(const void* logits, int logits_bf16, int n_frames, int q_f, int n_cls, int ld_logits,
+                          const int32_t* labels, const int32_t* label_off, int32_t* rows, int32_t* cols,
+                          int32_t* n_match, int32_t* status, float* row_max, float* row_lse, int32_t* row_argmax,
+                          int32_t* target_classes, void* stream);
+
+/* Weighted cross-entropy over the matched targets and its gradient (tasks/agqaHGQA.py:223:
+ * F.cross_entropy(weight=empty_weight) = sum w_t nll / sum w_t with w[0] = eos_coef, else 1) plus the
+ * counts behind class_error (tasks/agqaHGQA.py:228).  fwd ADDS into out[0]=sum w*nll, out[1]=sum w,
+ * out[2]=#matched, out[3]=#matched whose argmax is the label (caller zeroes `out`); bwd writes
+ * dlogits = grad_scale * w_t (softmax - onehot) / out[1] as bf16 or fp32. */
+int shg_set_loss_fwd(const void* logits, int logits_bf16, int n_rows, int n_cls, int ld_logits,
+                     const int32_t* target_classes, const float* row_lse, const int32_t* row_argmax, float eos_coef,
+                     float* out, void* stream);
+int shg_set_loss_bwd(const void* logits, int logits_bf16, int n_rows, int n_cls, int ld_logits,
+                     const int32_t* target_classes, const float* row_lse, float eos_coef, const float* out,
+                     float grad_scale, void* dlogits, int dlogits_bf16, int ld_dlogits, void* stream);
+
+/* ------------------------------------------------------------------ dense projections (tcgen05 + TMA)
+ * D[M,N] = epilogue( A . B^T ) with bf16 operands staged by TMA (128B swizzle) and fp32 accumulation in TMEM.
+ * Replaces every nn.Linear on the path (lxrt/modeling_capsbert.py:373-375,427,466,481;
+ * lxrt/transformer.py:189-193 incl. packed in_proj; tasks/agqa_model.py:105-140) and their backward.
+ *
+ *   a_mn_major = 0: A is [M,K] row-major (lda elements per row).  1: A is stored [K,M] row-major (A^T view).
+ *   b_mn_major = 0: B is [N,K] row-major (nn.Linear weight).      1: B is stored [K,N] row-major.
+ *   forward        : A = x [M,K],  B = W [N,K]                      (0,0)
+ *   dgrad          : A = dy [M,N'], B = W stored [N',K'] as [K,N]    (0,1)  -> dx = dy . W
+ *   wgrad          : A = dy stored [M',N] as [K,M], B = x stored [M',K'] as [K,N]  (1,1) -> dW = dy^T . x
+ *
+ * Epilogue, in this order: + bias[N] (fp32, may be NULL) ; optional store of the pre-activation (bf16, `preact`,
+ * same ld as d) ; activation ; x act'(mul_aux) (backward of GELU / ReLU) ; + residual (bf16 [M,N], ldr) ; store as bf16 or fp32 — or, with
+ * SHG_GEMM_ACCUMULATE, atomically add fp32 into d (split-K wgrad: `splits` CTAs share one output tile).
+ */
+#define SHG_ACT_NONE 0
+#define SHG_ACT_GELU_ERF 1   /* lxrt/modeling_capsbert.py:127-133 */
+#define SHG_ACT_RELU 2       /* lxrt/transformer.py:229 */
+#define SHG_ACT_TANH 3       /* BertPooler2, lxrt/modeling_capsbert.py:1531 */
+#define SHG_MUL_GELU_GRAD 1
+#define SHG_MUL_RELU_MASK 2
+#define SHG_GEMM_OUT_F32 1
+#define SHG_GEMM_ACCUMULATE 2
+typedef struct {
+    const void* a; int64_t lda; int a_mn_major;
+    const void* b; int64_t ldb; int b_mn_major;
+    void* d; int64_t ldd;
+    int m, n, k;
+    const float* bias;
+    const void* residual; int64_t ldr;
+    void* preact;
+    int act;
+    const void* mul_aux;   /* bf16 [M,N], ld = ldd: backward through an activation, applied after act/bias */
+    int mul_mode;          /* SHG_MUL_GELU_GRAD: d *= gelu'(mul_aux) ; SHG_MUL_RELU_MASK: d = mul_aux > 0 ? d : 0 */
+    int flags;
+    int splits;        /* >= 1; > 1 requires SHG_GEMM_ACCUMULATE */
+    int block_n;       /* 0 = choose; else one of 64,128,192,256 */
+} shg_gemm_args;
+int shg_gemm(const shg_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm family (HBM-bound)
+ * y = LN(x (+ residual)) * gamma + beta, rows of width n (768 / 1536), statistics fp32.  Replaces
+ * BertLayerNorm after BertAttOutput/BertOutput (lxrt/modeling_capsbert.py:431-435,485-489; eps 1e-12),
+ * the DETR norms (lxrt/transformer.py:199-201; eps 1e-5) and the head norm (tasks/agqa_model.py:108).
+ * Optional second output y2 = y + addend (the decoder's `tgt + query_pos`, lxrt/transformer.py:220,224);
+ * addend rows repeat with period addend_rows (0 = same shape as x).  mean/rstd (fp32 [rows]) may be NULL. */
+int shg_layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta, float eps,
+                      void* y, void* y2, const void* addend, int addend_rows, float* mean, float* rstd,
+                      int rows, int n, void* stream);
+
+/* Backward of the above.  g = dy (+ dy2, the gradient arriving over the residual branch); x (+ residual) is the
+ * forward input; dx bf16; dgamma/dbeta fp32 [n] are ACCUMULATED; dxsum (fp32 [n], may be NULL) accumulates the
+ * column sums of dx = the bias gradient of the Linear that produced x. */
+int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* residual, const float* gamma,
+                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
+                      int rows, int n, void* stream);
+
+/* out[n] += column sums of the bf16 matrix x [rows, n] (ld elements per row): bias gradients. */
+int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, void* stream);
+
+/* Embedding gathers fused with LayerNorm: BertEmbeddings (lxrt/modeling_capsbert.py:341-355; word[ids] +
+ * pos[t] + type[seg]) and HGEmbeddings (:313-325; word_ids == NULL: row t of the table, pos == NULL).
+ * Tables fp32 [*, n]; ids int64 [rows]; t = row % seq_len.  y bf16; pre (bf16 pre-LN sum), mean, rstd are
+ * the saved tensors for the backward (may be NULL). */
+int shg_embed_ln_fwd(const float* word, const int64_t* word_ids, const float* pos, const float* type,
+                     const int64_t* type_ids, const float* gamma, const float* beta, float eps, void* y, void* pre,
+                     float* mean, float* rstd, int rows, int seq_len, int n, void* stream);
+/* Scatter-add of the gradient wrt the pre-LN sum (bf16 [rows,n]) into the fp32 table gradients;
+ * *_pad = padding_idx whose row receives no gradient (nn.Embedding(padding_idx=0)), or -1. */
+int shg_embed_scatter_bwd(const void* de, const int64_t* word_ids, const int64_t* type_ids, float* dword,
+                          int word_pad, float* dpos, int pos_pad, float* dtype, int type_pad, int rows, int seq_len,
+                          int n, void* stream);
+
+/* y[r,:] = x[r,:] + add[r % add_rows,:] (bf16): type tokens of CrossEncoder (lxrt/modeling_capsbert.py:1168-1181),
+ * learned visual position rows (:1019-1024). */
+int shg_add_rows(const void* x, const void* add, int add_rows, void* y, int rows, int n, void* stream);
+/* fp32 -> bf16 shadow copy of parameters / inputs. */
+int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

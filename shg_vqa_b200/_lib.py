@@ -1,0 +1,99 @@
+"""ctypes binding of libshgvqa.so (the C ABI declared in include/shgvqa.h).
+
+There is no fallback: if the shared library is missing or the device is not sm_100
+every entry point raises.  Host code hands raw device pointers and the current
+torch CUDA stream to the library; torch only owns memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshgvqa.so")
+
+c_int, c_i64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class ShgError(RuntimeError):
+    pass
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [("a", c_vp), ("lda", c_i64), ("a_mn_major", c_int),
+                ("b", c_vp), ("ldb", c_i64), ("b_mn_major", c_int),
+                ("d", c_vp), ("ldd", c_i64),
+                ("m", c_int), ("n", c_int), ("k", c_int),
+                ("bias", c_vp), ("residual", c_vp), ("ldr", c_i64),
+                ("preact", c_vp), ("act", c_int),
+                ("mul_aux", c_vp), ("mul_mode", c_int),
+                ("flags", c_int), ("splits", c_int), ("block_n", c_int)]
+
+
+# name -> argtypes (all return int).  Must list every symbol include/shgvqa.h declares.
+SIGNATURES = {
+    "shg_version": [],
+    "shg_device_check": [c_int],
+    "shg_lsap_batched": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "shg_match_from_logits": [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                              c_vp, c_vp, c_vp, c_vp, c_vp],
+    "shg_set_loss_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp],
+    "shg_set_loss_bwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_int, c_int, c_vp],
+    "shg_gemm": [ctypes.POINTER(GemmArgs), c_vp],
+    "shg_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp],
+    "shg_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp],
+    "shg_colsum_accum": [c_vp, c_i64, c_int, c_int, c_vp, c_vp],
+    "shg_embed_ln_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_int, c_int,
+                         c_int, c_vp],
+    "shg_embed_scatter_bwd": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "shg_add_rows": [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp],
+    "shg_f32_to_bf16": [c_vp, c_vp, c_i64, c_vp],
+}
+
+_lib = None
+_checked_devices = set()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ShgError("libshgvqa.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "— there is no CPU or PyTorch fallback for the hot path" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.shg_last_error.restype = ctypes.c_char_p
+        _lib.shg_last_error.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+    return _lib
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device(t):
+    """All product entry points go through here: CUDA tensor on an sm_100 device or raise."""
+    if not t.is_cuda:
+        raise ShgError("shg_vqa_b200 ops need CUDA tensors on a B200 (got %s); there is no CPU path" % t.device)
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        check(lib().shg_device_check(idx))
+        _checked_devices.add(idx)
+
+
+def check(rc):
+    if rc != 0:
+        raise ShgError("libshgvqa error %d: %s" % (rc, lib().shg_last_error().decode()))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args))

@@ -1,0 +1,406 @@
+// Persistent, warp-specialised tcgen05 GEMM for every dense projection on the path.
+//
+//   warp 0      : TMA producer (one elected lane) — bf16 operand tiles, 128B swizzle, mbarrier ring
+//   warp 1      : TMEM allocation (whole warp) + MMA issuer (one lane): tcgen05.mma 128 x block_n x 16,
+//                 fp32 accumulators in TMEM, two accumulator stages so the epilogue of tile t overlaps
+//                 the main loop of tile t+1
+//   warps 2..5  : epilogue — tcgen05.ld (thread = one output row), bias / pre-activation store /
+//                 GELU|ReLU|tanh / residual / bf16|fp32 store or fp32 atomic accumulate (split-K wgrad)
+//
+// Operand majors are runtime-selectable so the forward (x.W^T), dgrad (dy.W) and wgrad (dy^T.x) products
+// all read the tensors where they already lie in HBM — no transposed copies.
+#include "shg_common.cuh"
+
+namespace shg {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct GemmParams {
+    void* d;
+    int64_t ldd;
+    int m, n, k;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    int64_t ldr;
+    __nv_bfloat16* preact;
+    const __nv_bfloat16* mul_aux;
+    int mul_mode;
+    int act, out_f32, accumulate;
+    int splits, block_n, n_stages;
+    int m_tiles, n_tiles, kb_total, kb_per_split;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    switch (act) {
+        case SHG_ACT_GELU_ERF: return gelu_erf(x);
+        case SHG_ACT_RELU: return fmaxf(x, 0.0f);
+        case SHG_ACT_TANH: return tanhf(x);
+        default: return x;
+    }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = BM * BK * 2;
+    const uint32_t b_bytes = p.block_n * BK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.n_stages; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full + s, 1);
+            mbar_init(tmem_empty + s, 4);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int rem = tile - split * (p.m_tiles * p.n_tiles);
+                const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + a_bytes;
+                    mbar_expect_tx(full_bar + stage, stage_bytes);
+                    const int k0 = kb * BK;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tma_a, full_bar + stage, k0, m0);
+                    } else {
+                        tma_load_2d(sa, &tma_a, full_bar + stage, m0, k0);
+                        tma_load_2d(sa + 8192, &tma_a, full_bar + stage, m0 + 64, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tma_b, full_bar + stage, k0, n0);
+                    } else {
+                        for (int h = 0; h * 64 < p.block_n; ++h)
+                            tma_load_2d(sb + h * 8192, &tma_b, full_bar + stage, n0 + h * 64, k0);
+                    }
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BM, p.block_n, A_MN, B_MN);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                mbar_wait(tmem_empty + as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        const uint64_t adesc = A_MN ? make_smem_desc(sa + ks * 2048, 8192, 1024)
+                                                    : make_smem_desc(sa + ks * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? make_smem_desc(sb + ks * 2048, 8192, 1024)
+                                                    : make_smem_desc(sb + ks * 32, 16, 1024);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar + stage);  // frees the smem slot once these MMAs retire
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(tmem_full + as);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (warps 2..5)
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+        int as = 0;
+        uint32_t aphase = 0;
+        const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
+        const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
+        const bool vec_ok_aux = p.mul_aux && (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mul_aux) & 15) == 0);
+        const bool bias_vec_ok = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+        const bool vec_ok_res = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int rem = tile % (p.m_tiles * p.n_tiles);
+            const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
+            const int row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < p.m;
+            mbar_wait(tmem_full + as, aphase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
+            for (int c = 0; c < p.block_n; c += 32) {
+                const int col0 = n0 + c;
+                if (col0 >= p.n) break;  // warp-uniform
+                uint32_t raw[32];
+                __syncwarp();
+                tmem_ld32(t_row + c, raw);
+                tmem_ld_wait();
+                float acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(raw[i]);
+                const bool full_chunk = col0 + 32 <= p.n;
+                if (p.bias) {
+                    if (full_chunk && bias_vec_ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                            acc[i] += b4.x, acc[i + 1] += b4.y, acc[i + 2] += b4.z, acc[i + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.n) acc[i] += __ldg(p.bias + col0 + i);
+                    }
+                }
+                if (row_ok) {
+                if (p.preact) {
+                    __nv_bfloat16* pr = p.preact + (size_t)row * p.ldd + col0;
+                    if (full_chunk && vec_ok_bf16) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 u;
+                            u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
+                            u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
+                            *reinterpret_cast<uint4*>(pr + i) = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.n) pr[i] = __float2bfloat16(acc[i]);
+                    }
+                }
+                if (p.act != SHG_ACT_NONE) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = apply_act(acc[i], p.act);
+                }
+                if (p.mul_mode) {
+                    // backward through an activation: acc *= act'(aux) (aux = saved pre-activation for GELU,
+                    // saved output for ReLU)
+                    const __nv_bfloat16* ax = p.mul_aux + (size_t)row * p.ldd + col0;
+                    float av[32];
+                    if (full_chunk && vec_ok_aux) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(ax + i));
+                            float2 f;
+                            f = unpack_bf16x2(u.x), av[i] = f.x, av[i + 1] = f.y;
+                            f = unpack_bf16x2(u.y), av[i + 2] = f.x, av[i + 3] = f.y;
+                            f = unpack_bf16x2(u.z), av[i + 4] = f.x, av[i + 5] = f.y;
+                            f = unpack_bf16x2(u.w), av[i + 6] = f.x, av[i + 7] = f.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) av[i] = col0 + i < p.n ? __bfloat162float(ax[i]) : 0.f;
+                    }
+                    if (p.mul_mode == SHG_MUL_GELU_GRAD) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[i] *= gelu_erf_grad(av[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[i] = av[i] > 0.f ? acc[i] : 0.f;
+                    }
+                }
+                if (p.residual) {
+                    const __nv_bfloat16* rs = p.residual + (size_t)row * p.ldr + col0;
+                    if (full_chunk && vec_ok_res) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rs + i));
+                            float2 f;
+                            f = unpack_bf16x2(u.x), acc[i] += f.x, acc[i + 1] += f.y;
+                            f = unpack_bf16x2(u.y), acc[i + 2] += f.x, acc[i + 3] += f.y;
+                            f = unpack_bf16x2(u.z), acc[i + 4] += f.x, acc[i + 5] += f.y;
+                            f = unpack_bf16x2(u.w), acc[i + 6] += f.x, acc[i + 7] += f.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.n) acc[i] += __bfloat162float(rs[i]);
+                    }
+                }
+                if (p.accumulate) {
+                    float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
+                    if (full_chunk && vec_ok_f32) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            atomicAdd(reinterpret_cast<float4*>(o + i),
+                                      make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.n) atomicAdd(o + i, acc[i]);
+                    }
+                } else if (p.out_f32) {
+                    float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
+                    if (full_chunk && vec_ok_f32) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(o + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.n) o[i] = acc[i];
+                    }
+                } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)row * p.ldd + col0;
+                    if (full_chunk && vec_ok_bf16) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 u;
+                            u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
+                            u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
+                            *reinterpret_cast<uint4*>(o + i) = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.n) o[i] = __float2bfloat16(acc[i]);
+                    }
+                }
+                }  // row_ok
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + as);
+            if (++as == 2) {
+                as = 0;
+                aphase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int pick_block_n(int m_tiles, int n) {
+    // minimise (waves x per-tile cost) over the legal UMMA N values; prefers wider tiles on ties
+    const int cands[4] = {256, 192, 128, 64};
+    int best = 128;
+    double best_cost = 1e30;
+    for (int bn : cands) {
+        const int n_tiles = (n + bn - 1) / bn;
+        const long tiles = (long)m_tiles * n_tiles;
+        const long waves = (tiles + kNumSMs - 1) / kNumSMs;
+        // per-tile time ~ bn (MMA) + fixed overhead; narrow tiles also halve operand reuse
+        const double cost = (double)waves * (bn + 24.0 + (bn <= 64 ? 24.0 : 0.0));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+}  // namespace shg
+
+extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(a && a->a && a->b && a->d, SHG_EINVAL, "shg_gemm: null operand");
+    SHG_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, SHG_EINVAL, "shg_gemm: empty problem %dx%dx%d", a->m, a->n, a->k);
+    const int splits = a->splits < 1 ? 1 : a->splits;
+    const bool accumulate = (a->flags & SHG_GEMM_ACCUMULATE) != 0;
+    SHG_REQUIRE(splits == 1 || accumulate, SHG_EINVAL, "shg_gemm: splits>1 needs SHG_GEMM_ACCUMULATE");
+    SHG_REQUIRE(!accumulate || !(a->preact || a->residual || a->act || a->mul_aux), SHG_EINVAL,
+                "shg_gemm: accumulate mode takes no activation/residual/preact");
+    GemmParams p;
+    p.d = a->d, p.ldd = a->ldd, p.m = a->m, p.n = a->n, p.k = a->k;
+    p.bias = a->bias, p.residual = (const __nv_bfloat16*)a->residual, p.ldr = a->ldr;
+    p.preact = (__nv_bfloat16*)a->preact, p.act = a->act;
+    p.mul_aux = (const __nv_bfloat16*)a->mul_aux, p.mul_mode = a->mul_aux ? a->mul_mode : 0;
+    p.out_f32 = (a->flags & SHG_GEMM_OUT_F32) || accumulate, p.accumulate = accumulate;
+    p.m_tiles = (a->m + BM - 1) / BM;
+    int bn = a->block_n ? a->block_n : pick_block_n(p.m_tiles * splits, a->n);
+    SHG_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, SHG_ESHAPE, "shg_gemm: block_n=%d", bn);
+    p.block_n = bn;
+    p.n_tiles = (a->n + bn - 1) / bn;
+    p.kb_total = (a->k + BK - 1) / BK;
+    p.splits = splits > p.kb_total ? p.kb_total : splits;
+    p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+    const int stage_bytes = BM * BK * 2 + bn * BK * 2;
+    const int bar_bytes = 1024;
+    int n_stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
+    if (n_stages > kMaxStages) n_stages = kMaxStages;
+    p.n_stages = n_stages;
+    const size_t smem = (size_t)n_stages * stage_bytes + bar_bytes + 1024;
+
+    // TMA descriptors over the operands as they lie in HBM
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    const CUtensorMap *ta, *tb;
+    if (!a->a_mn_major) { dims[0] = a->k, dims[1] = a->m, box[0] = BK, box[1] = BM; }
+    else { dims[0] = a->m, dims[1] = a->k, box[0] = 64, box[1] = BK; }
+    strides[0] = (uint64_t)a->lda * 2;
+    ta = get_tmap_bf16(a->a, 2, dims, strides, box);
+    if (!ta) return SHG_ECUDA;
+    if (!a->b_mn_major) { dims[0] = a->k, dims[1] = a->n, box[0] = BK, box[1] = (uint32_t)bn; }
+    else { dims[0] = a->n, dims[1] = a->k, box[0] = 64, box[1] = BK; }
+    strides[0] = (uint64_t)a->ldb * 2;
+    tb = get_tmap_bf16(a->b, 2, dims, strides, box);
+    if (!tb) return SHG_ECUDA;
+
+    const int total = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    cudaStream_t s = (cudaStream_t)stream;
+#define SHG_GEMM_LAUNCH(AM, BMJ)                                                                              \
+    do {                                                                                                      \
+        static bool attr_set = false;                                                                         \
+        if (!attr_set) {                                                                                      \
+            cudaFuncSetAttribute(gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            attr_set = true;                                                                                  \
+        }                                                                                                     \
+        gemm_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, p);                                   \
+    } while (0)
+    if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM_LAUNCH(false, false);
+    else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM_LAUNCH(false, true);
+    else if (a->a_mn_major && a->b_mn_major) SHG_GEMM_LAUNCH(true, true);
+    else SHG_GEMM_LAUNCH(true, false);
+#undef SHG_GEMM_LAUNCH
+    return check_launch("shg_gemm");
+}

@@ -1,0 +1,444 @@
+// HBM-bound row kernels: LayerNorm(+residual) forward/backward, embedding gathers fused with LayerNorm,
+// column sums (bias gradients), row-broadcast adds and small dtype helpers.  One warp per row, 128-bit loads
+// and stores, fp32 statistics via warp shuffles; nothing here is reshaped into a GEMM.
+#include "shg_common.cuh"
+
+namespace shg {
+
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 f;
+    f = unpack_bf16x2(u.x), v[0] = f.x, v[1] = f.y;
+    f = unpack_bf16x2(u.y), v[2] = f.x, v[3] = f.y;
+    f = unpack_bf16x2(u.z), v[4] = f.x, v[5] = f.y;
+    f = unpack_bf16x2(u.w), v[6] = f.x, v[7] = f.y;
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]), u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]), u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// CH = 16-byte chunks of 8 elements per lane: n = 256 * CH  (768 -> 3, 1536 -> 6)
+template <int CH>
+__device__ __forceinline__ void row_stats(const float (&v)[CH][8], float inv_n, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[j][i];
+    mean = warp_sum(s) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float d = v[j][i] - mean;
+            q += d * d;
+        }
+    rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
+                     const __nv_bfloat16* __restrict__ addend, int addend_rows, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows) {
+    constexpr int N = 256 * CH;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[CH][8];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        load8(x + (size_t)row * N + c, v[j]);
+        if (residual) {
+            float r[8];
+            load8(residual + (size_t)row * N + c, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] += r[i];
+        }
+    }
+    float mean, rstd;
+    row_stats<CH>(v, 1.0f / N, eps, mean, rstd);
+    if (mean_out && lane == 0) mean_out[row] = mean, rstd_out[row] = rstd;
+    const int arow = addend ? (addend_rows > 0 ? row % addend_rows : row) : 0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        float g[8], b[8], o[8];
+        load8(gamma + c, g);
+        load8(beta + c, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+        store8(y + (size_t)row * N + c, o);
+        if (y2) {
+            float a[8];
+            load8(addend + (size_t)arow * N + c, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += a[i];
+            store8(y2 + (size_t)row * N + c, o);
+        }
+    }
+}
+
+// dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)),  g = dy (+ dy2)
+// dgamma += sum_rows g*xhat ; dbeta += sum_rows g ; dxsum += sum_rows dx (bias gradient of the Linear that fed x)
+template <int CH>
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
+                     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
+                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dxsum, int rows) {
+    constexpr int N = 256 * CH;
+    __shared__ float red[kRowWarps][256 + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float ag[CH][8], ab[CH][8], ax[CH][8];
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ag[j][i] = ab[j][i] = ax[j][i] = 0.f;
+    float gm[CH][8];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) load8(gamma + (j * 32 + lane) * 8, gm[j]);
+
+    for (int row = blockIdx.x * kRowWarps + warp; row < rows; row += gridDim.x * kRowWarps) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float g[CH][8], xh[CH][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int c = (j * 32 + lane) * 8;
+            load8(dy + (size_t)row * N + c, g[j]);
+            if (dy2) {
+                float t[8];
+                load8(dy2 + (size_t)row * N + c, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[j][i] += t[i];
+            }
+            load8(x + (size_t)row * N + c, xh[j]);
+            if (residual) {
+                float t[8];
+                load8(residual + (size_t)row * N + c, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xh[j][i] += t[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                xh[j][i] = (xh[j][i] - mean) * rstd;
+                const float gg = g[j][i] * gm[j][i];
+                s1 += gg;
+                s2 += gg * xh[j][i];
+                ag[j][i] += g[j][i] * xh[j][i];
+                ab[j][i] += g[j][i];
+            }
+        }
+        s1 = warp_sum(s1) * (1.0f / N);
+        s2 = warp_sum(s2) * (1.0f / N);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o[i] = rstd * (g[j][i] * gm[j][i] - s1 - xh[j][i] * s2);
+                ax[j][i] += o[i];
+            }
+            store8(dx + (size_t)row * N + (j * 32 + lane) * 8, o);
+        }
+    }
+    // block reduction of the three column accumulators (one 256-column chunk at a time), then one atomic per
+    // column per block
+    for (int pass = 0; pass < 3; ++pass) {
+        float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
+        if (!dst) continue;  // uniform
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                red[warp][lane * 8 + i] = pass == 0 ? ag[j][i] : (pass == 1 ? ab[j][i] : ax[j][i]);
+            __syncthreads();
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < kRowWarps; ++w) sum += red[w][threadIdx.x];
+            atomicAdd(dst + j * 256 + threadIdx.x, sum);
+            __syncthreads();
+        }
+    }
+}
+
+// out[c] += sum_rows x[row, c]  (bias gradients).  Block = 256 threads over 8-column groups x row slices.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, int n,
+                                                    float* __restrict__ out, int rows_per_block) {
+    // thread t owns column group (blockIdx.x*32 + t%32) of 8 columns, row phase t/32
+    const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = cg * 8;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, rows);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < n) {
+        for (int r = r0 + (threadIdx.x >> 5); r < r1; r += 8) {
+            float v[8];
+            load8(x + (size_t)r * ld + c, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+    }
+    __shared__ float red[8][32][9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x >> 5][threadIdx.x & 31][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 32 && c < n) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x][i];
+            atomicAdd(out + c + i, s);
+        }
+    }
+}
+
+// Embedding gathers fused with LayerNorm (BertEmbeddings, lxrt/modeling_capsbert.py:341-355, and
+// HGEmbeddings, :313-325).  word_ids == NULL means "row r of the table" (HGEmbeddings uses every row).
+template <int CH>
+__global__ void __launch_bounds__(kRowThreads)
+embed_ln_fwd_kernel(const float* __restrict__ word, const int64_t* __restrict__ word_ids,
+                    const float* __restrict__ pos, const float* __restrict__ type,
+                    const int64_t* __restrict__ type_ids, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
+                    __nv_bfloat16* __restrict__ pre_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                    int rows, int seq_len) {
+    constexpr int N = 256 * CH;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int t = row % seq_len;
+    const int64_t wid = word_ids ? word_ids[row] : t;
+    const int64_t tid = type_ids ? type_ids[row] : 0;
+    float v[CH][8];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        load8(word + (size_t)wid * N + c, v[j]);
+        float a[8];
+        if (pos) {
+            load8(pos + (size_t)t * N + c, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] += a[i];
+        }
+        if (type) {
+            load8(type + (size_t)tid * N + c, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] += a[i];
+        }
+    }
+    if (pre_out) {
+        // the backward re-reads the pre-LN sum in bf16, so the statistics are taken on the rounded values
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            store8(pre_out + (size_t)row * N + (j * 32 + lane) * 8, v[j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] = __bfloat162float(__float2bfloat16(v[j][i]));
+        }
+    }
+    float mean, rstd;
+    row_stats<CH>(v, 1.0f / N, eps, mean, rstd);
+    if (rstd_out && lane == 0) mean_out[row] = mean, rstd_out[row] = rstd;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        float g[8], b[8], o[8];
+        load8(gamma + c, g);
+        load8(beta + c, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+        store8(y + (size_t)row * N + c, o);
+    }
+}
+
+// Backward of the gathers: scatter-add of the (already LayerNorm-back-propagated) row gradient into the
+// tables with fp32 atomics.  padding_idx rows (< 0 = none) receive no gradient, as nn.Embedding's do.
+template <int CH>
+__global__ void __launch_bounds__(kRowThreads)
+embed_scatter_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int64_t* __restrict__ word_ids,
+                         const int64_t* __restrict__ type_ids, float* __restrict__ dword, int word_pad,
+                         float* __restrict__ dpos, int pos_pad, float* __restrict__ dtype, int type_pad, int rows,
+                         int seq_len) {
+    constexpr int N = 256 * CH;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int t = row % seq_len;
+    const int64_t wid = word_ids ? word_ids[row] : t;
+    const int64_t tid = type_ids ? type_ids[row] : 0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        float d[8];
+        load8(de + (size_t)row * N + c, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (dword && wid != word_pad) atomicAdd(dword + (size_t)wid * N + c + i, d[i]);
+            if (dpos && t != pos_pad) atomicAdd(dpos + (size_t)t * N + c + i, d[i]);
+            if (dtype && tid != type_pad) atomicAdd(dtype + (size_t)tid * N + c + i, d[i]);
+        }
+    }
+}
+
+// y[r, :] = x[r, :] + add[r % add_rows, :]   (type tokens / position rows; bf16 in, bf16 out)
+__global__ void __launch_bounds__(256) add_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                      const __nv_bfloat16* __restrict__ add, int add_rows,
+                                                      __nv_bfloat16* __restrict__ y, int64_t total8, int n8) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n8;
+        const int c8 = (int)(i - r * n8);
+        float a[8], b[8];
+        load8(x + i * 8, a);
+        load8(add + ((r % add_rows) * n8 + c8) * 8, b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += b[k];
+        store8(y + i * 8, a);
+    }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                         int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n8 = n / 8;
+    for (; i < n8; i += stride) {
+        float v[8];
+        load8(x + i * 8, v);
+        store8(y + i * 8, v);
+    }
+    for (int64_t t = n8 * 8 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += stride)
+        y[t] = __float2bfloat16(x[t]);
+}
+
+}  // namespace shg
+
+extern "C" {
+
+int shg_layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta, float eps, void* y,
+                      void* y2, const void* addend, int addend_rows, float* mean, float* rstd, int rows, int n,
+                      void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(n == 768 || n == 1536, SHG_ESHAPE, "shg_layernorm_fwd: width %d (768 or 1536 supported)", n);
+    SHG_REQUIRE((y2 == nullptr) == (addend == nullptr), SHG_EINVAL, "shg_layernorm_fwd: y2 and addend go together");
+    SHG_REQUIRE((mean == nullptr) == (rstd == nullptr), SHG_EINVAL, "shg_layernorm_fwd: mean and rstd go together");
+    if (rows <= 0) return SHG_OK;
+    const int blocks = (rows + kRowWarps - 1) / kRowWarps;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 768)
+        layernorm_fwd_kernel<3><<<blocks, kRowThreads, 0, s>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, eps, (__nv_bfloat16*)y,
+            (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows);
+    else
+        layernorm_fwd_kernel<6><<<blocks, kRowThreads, 0, s>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, eps, (__nv_bfloat16*)y,
+            (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows);
+    return check_launch("shg_layernorm_fwd");
+}
+
+int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* residual, const float* gamma,
+                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
+                      int rows, int n, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(n == 768 || n == 1536, SHG_ESHAPE, "shg_layernorm_bwd: width %d (768 or 1536 supported)", n);
+    if (rows <= 0) return SHG_OK;
+    int blocks = (rows + kRowWarps - 1) / kRowWarps;
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 768)
+        layernorm_bwd_kernel<3><<<blocks, kRowThreads, 0, s>>>(
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
+            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows);
+    else
+        layernorm_bwd_kernel<6><<<blocks, kRowThreads, 0, s>>>(
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
+            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows);
+    return check_launch("shg_layernorm_bwd");
+}
+
+int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(n % 8 == 0 && ld % 8 == 0, SHG_ESHAPE, "shg_colsum_accum: n=%d ld=%lld must be multiples of 8", n,
+                (long long)ld);
+    if (rows <= 0) return SHG_OK;
+    const int col_blocks = (n / 8 + 31) / 32;
+    int row_blocks = (2 * kNumSMs + col_blocks - 1) / col_blocks;
+    int rpb = (rows + row_blocks - 1) / row_blocks;
+    if (rpb < 64) rpb = 64;
+    row_blocks = (rows + rpb - 1) / rpb;
+    colsum_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, rows,
+                                                                                  n, out, rpb);
+    return check_launch("shg_colsum_accum");
+}
+
+int shg_embed_ln_fwd(const float* word, const int64_t* word_ids, const float* pos, const float* type,
+                     const int64_t* type_ids, const float* gamma, const float* beta, float eps, void* y, void* pre,
+                     float* mean, float* rstd, int rows, int seq_len, int n, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(n == 768, SHG_ESHAPE, "shg_embed_ln_fwd: width %d (768 supported)", n);
+    SHG_REQUIRE((mean == nullptr) == (rstd == nullptr), SHG_EINVAL, "shg_embed_ln_fwd: mean and rstd go together");
+    if (rows <= 0) return SHG_OK;
+    const int blocks = (rows + kRowWarps - 1) / kRowWarps;
+    embed_ln_fwd_kernel<3><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
+        word, word_ids, pos, type, type_ids, gamma, beta, eps, (__nv_bfloat16*)y, (__nv_bfloat16*)pre, mean, rstd,
+        rows, seq_len);
+    return check_launch("shg_embed_ln_fwd");
+}
+
+int shg_embed_scatter_bwd(const void* de, const int64_t* word_ids, const int64_t* type_ids, float* dword,
+                          int word_pad, float* dpos, int pos_pad, float* dtype, int type_pad, int rows, int seq_len,
+                          int n, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(n == 768, SHG_ESHAPE, "shg_embed_scatter_bwd: width %d (768 supported)", n);
+    if (rows <= 0) return SHG_OK;
+    const int blocks = (rows + kRowWarps - 1) / kRowWarps;
+    embed_scatter_bwd_kernel<3><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)de, word_ids, type_ids, dword, word_pad, dpos, pos_pad, dtype, type_pad, rows, seq_len);
+    return check_launch("shg_embed_scatter_bwd");
+}
+
+int shg_add_rows(const void* x, const void* add, int add_rows, void* y, int rows, int n, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(n % 8 == 0 && add_rows > 0, SHG_ESHAPE, "shg_add_rows: n=%d add_rows=%d", n, add_rows);
+    if (rows <= 0) return SHG_OK;
+    const int64_t total8 = (int64_t)rows * (n / 8);
+    int blocks = (int)((total8 + 255) / 256);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    add_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add,
+                                                              add_rows, (__nv_bfloat16*)y, total8, n / 8);
+    return check_launch("shg_add_rows");
+}
+
+int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+    using namespace shg;
+    if (n <= 0) return SHG_OK;
+    SHG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, SHG_ESHAPE,
+                "shg_f32_to_bf16: pointers must be 16-byte aligned");
+    int64_t blocks = (n / 8 + 255) / 256;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    f32_to_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+    return check_launch("shg_f32_to_bf16");
+}
+}

@@ -1,0 +1,163 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see autograd.py).
+
+Every function takes CUDA tensors, launches on the current torch stream and
+returns torch tensors it allocated; none falls back to PyTorch math.
+"""
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, call, ptr, require_device, stream
+
+ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "tanh": 3}
+MUL = {None: 0, "gelu_grad": 1, "relu_mask": 2}
+GEMM_OUT_F32 = 1
+GEMM_ACCUMULATE = 2
+BF16 = torch.bfloat16
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "row-major 2-D tensor (any leading dimension) expected"
+    return t.stride(0)
+
+
+def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, preact=None, mul_aux=None,
+         mul_mode=None, out=None, out_f32=False, accumulate=False, splits=1, block_n=0):
+    """D = epilogue(A . B^T).  a: [M,K] (or stored [K,M] with a_t), b: [N,K] (or stored [K,N] with b_t); bf16."""
+    require_device(a)
+    assert a.dtype == BF16 and b.dtype == BF16
+    if a_t:
+        k, m = a.shape
+    else:
+        m, k = a.shape
+    if b_t:
+        kb, n = b.shape
+    else:
+        n, kb = b.shape
+    assert k == kb, (a.shape, b.shape, a_t, b_t)
+    if out is None:
+        out = torch.empty(m, n, device=a.device, dtype=torch.float32 if (out_f32 or accumulate) else BF16)
+    assert out.shape == (m, n)
+    args = GemmArgs()
+    args.a, args.lda, args.a_mn_major = ptr(a), _ld(a), int(a_t)
+    args.b, args.ldb, args.b_mn_major = ptr(b), _ld(b), int(b_t)
+    args.d, args.ldd = ptr(out), _ld(out)
+    args.m, args.n, args.k = m, n, k
+    args.bias = ptr(bias)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == n and bias.is_contiguous()
+    args.residual = ptr(residual)
+    args.ldr = _ld(residual) if residual is not None else 0
+    if preact is not None:
+        assert preact.dtype == BF16 and _ld(preact) == _ld(out) and preact.shape == out.shape
+    args.preact = ptr(preact)
+    args.act = ACT[act]
+    if mul_aux is not None:
+        assert mul_aux.dtype == BF16 and _ld(mul_aux) == _ld(out) and mul_aux.shape == out.shape
+    args.mul_aux, args.mul_mode = ptr(mul_aux), MUL[mul_mode]
+    args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
+    args.splits, args.block_n = splits, block_n
+    call("shg_gemm", args, stream())
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False):
+    require_device(x)
+    rows, n = x.shape
+    assert x.dtype == BF16 and x.is_contiguous() and gamma.dtype == torch.float32
+    y = torch.empty_like(x)
+    y2 = torch.empty_like(x) if addend is not None else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty_like(mean) if save_stats else None
+    call("shg_layernorm_fwd", ptr(x), ptr(residual), ptr(gamma), ptr(beta), eps, ptr(y), ptr(y2), ptr(addend),
+         addend_rows, ptr(mean), ptr(rstd), rows, n, stream())
+    return y, y2, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dy2=None, residual=None, dxsum=None):
+    require_device(dy)
+    rows, n = x.shape
+    dx = torch.empty_like(x)
+    call("shg_layernorm_bwd", ptr(dy), ptr(dy2), ptr(x), ptr(residual), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx),
+         ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, stream())
+    return dx
+
+
+def colsum_accum(x, out):
+    require_device(x)
+    rows, n = x.shape
+    call("shg_colsum_accum", ptr(x), _ld(x), rows, n, ptr(out), stream())
+
+
+def add_rows(x, add):
+    require_device(x)
+    rows, n = x.shape
+    y = torch.empty_like(x)
+    call("shg_add_rows", ptr(x), ptr(add), add.shape[0], ptr(y), rows, n, stream())
+    return y
+
+
+def to_bf16(x, out=None):
+    require_device(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    call("shg_f32_to_bf16", ptr(x), ptr(out), x.numel(), stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- matching
+
+def lsap_batched(cost, col_off, q_f):
+    """cost fp32 [n_frames, q_f, ld] device; col_off int32 [n_frames+1] device."""
+    require_device(cost)
+    n_frames = cost.shape[0]
+    assert cost.dtype == torch.float32 and cost.is_contiguous() and cost.shape[1] == q_f
+    dev = cost.device
+    rows = torch.empty(n_frames, q_f, device=dev, dtype=torch.int32)
+    cols = torch.empty_like(rows)
+    n_match = torch.empty(n_frames, device=dev, dtype=torch.int32)
+    status = torch.empty_like(n_match)
+    call("shg_lsap_batched", ptr(cost), n_frames, q_f, cost.shape[2], ptr(col_off), ptr(rows), ptr(cols),
+         ptr(n_match), ptr(status), stream())
+    return rows, cols, n_match, status
+
+
+def match_from_logits(logits, labels, label_off, q_f, want_targets=True):
+    """logits [n_frames*q_f, n_cls] fp32|bf16 (row stride = ld); labels int32 CSR."""
+    require_device(logits)
+    n_rows, n_cls = logits.shape
+    n_frames = n_rows // q_f
+    dev = logits.device
+    rows = torch.empty(n_frames, q_f, device=dev, dtype=torch.int32)
+    cols = torch.empty_like(rows)
+    n_match = torch.empty(n_frames, device=dev, dtype=torch.int32)
+    status = torch.empty_like(n_match)
+    row_max = torch.empty(n_rows, device=dev, dtype=torch.float32)
+    row_lse = torch.empty_like(row_max)
+    row_arg = torch.empty(n_rows, device=dev, dtype=torch.int32)
+    tgt = torch.empty(n_rows, device=dev, dtype=torch.int32) if want_targets else None
+    call("shg_match_from_logits", ptr(logits), int(logits.dtype == BF16), n_frames, q_f, n_cls, _ld(logits),
+         ptr(labels), ptr(label_off), ptr(rows), ptr(cols), ptr(n_match), ptr(status), ptr(row_max), ptr(row_lse),
+         ptr(row_arg), ptr(tgt), stream())
+    return dict(rows=rows, cols=cols, n_match=n_match, status=status, row_max=row_max, row_lse=row_lse,
+                row_argmax=row_arg, target_classes=tgt)
+
+
+def set_loss_fwd(logits, m, eos_coef, out=None):
+    n_rows, n_cls = logits.shape
+    if out is None:
+        out = torch.zeros(4, device=logits.device, dtype=torch.float32)
+    call("shg_set_loss_fwd", ptr(logits), int(logits.dtype == BF16), n_rows, n_cls, _ld(logits),
+         ptr(m["target_classes"]), ptr(m["row_lse"]), ptr(m["row_argmax"]), eos_coef, ptr(out), stream())
+    return out
+
+
+def set_loss_bwd(logits, m, eos_coef, sums, grad_scale=1.0, out_dtype=BF16):
+    n_rows, n_cls = logits.shape
+    ld = (n_cls + 7) // 8 * 8
+    buf = torch.zeros(n_rows, ld, device=logits.device, dtype=out_dtype)
+    d = buf[:, :n_cls]
+    call("shg_set_loss_bwd", ptr(logits), int(logits.dtype == BF16), n_rows, n_cls, _ld(logits),
+         ptr(m["target_classes"]), ptr(m["row_lse"]), eos_coef, ptr(sums), grad_scale, ptr(d),
+         int(out_dtype == BF16), ld, stream())
+    return d
