@@ -107,6 +107,29 @@ typedef struct {
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------ attention (tcgen05, head dim 64)
+ * O = softmax(scale * Q K^T + mask) V per (batch, head).  Replaces BertAttention's matmul/softmax/matmul
+ * (lxrt/modeling_capsbert.py:394-417) and nn.MultiheadAttention inside the DETR decoders
+ * (lxrt/transformer.py:220-227).  q/k/v/o are bf16 row-major [batch*len, ld] with head h in columns
+ * [64h, 64h+64) counted from the given pointer (so packed QKV / hoisted K|V buffers are read in place).
+ * mask_mode 0: none; 1: additive fp32 key mask [batch, lk] (BERT's (1-mask)*-10000, :1834);
+ * 2: block-causal by frame — key j visible to query i iff j / k_per_frame <= i / q_per_frame
+ * (lxrt/entry.py:114-121).  lse (fp32 [batch, heads, lq], may be NULL) saves log-sum-exp for the backward.
+ * lk <= 416 (all keys of a head are resident on chip; no online softmax). */
+typedef struct {
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    void* o; int64_t ldo;
+    float* lse;
+    int batch, heads, lq, lk;
+    float scale;
+    int mask_mode;
+    const float* key_mask;
+    int q_per_frame, k_per_frame;
+} shg_attn_args;
+int shg_attn_fwd(const shg_attn_args* args, void* stream);
+
 /* ------------------------------------------------------------------ LayerNorm family (HBM-bound)
  * y = LN(x (+ residual)) * gamma + beta, rows of width n (768 / 1536), statistics fp32.  Replaces
  * BertLayerNorm after BertAttOutput/BertOutput (lxrt/modeling_capsbert.py:431-435,485-489; eps 1e-12),

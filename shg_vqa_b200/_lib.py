@@ -30,6 +30,14 @@ class GemmArgs(ctypes.Structure):
                 ("flags", c_int), ("splits", c_int), ("block_n", c_int)]
 
 
+class AttnArgs(ctypes.Structure):
+    _fields_ = [("q", c_vp), ("ldq", c_i64), ("k", c_vp), ("ldk", c_i64), ("v", c_vp), ("ldv", c_i64),
+                ("o", c_vp), ("ldo", c_i64), ("lse", c_vp),
+                ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
+                ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
+                ("q_per_frame", c_int), ("k_per_frame", c_int)]
+
+
 # name -> argtypes (all return int).  Must list every symbol include/shgvqa.h declares.
 SIGNATURES = {
     "shg_version": [],
@@ -40,6 +48,7 @@ SIGNATURES = {
     "shg_set_loss_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp],
     "shg_set_loss_bwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_int, c_int, c_vp],
     "shg_gemm": [ctypes.POINTER(GemmArgs), c_vp],
+    "shg_attn_fwd": [ctypes.POINTER(AttnArgs), c_vp],
     "shg_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp],
     "shg_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp],
     "shg_colsum_accum": [c_vp, c_i64, c_int, c_int, c_vp, c_vp],

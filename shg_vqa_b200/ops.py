@@ -6,7 +6,7 @@ returns torch tensors it allocated; none falls back to PyTorch math.
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, call, ptr, require_device, stream
+from ._lib import AttnArgs, GemmArgs, call, ptr, require_device, stream
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "tanh": 3}
 MUL = {None: 0, "gelu_grad": 1, "relu_mask": 2}
@@ -58,6 +58,27 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
     args.splits, args.block_n = splits, block_n
     call("shg_gemm", args, stream())
     return out
+
+
+def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, frames=None, out=None,
+                  save_lse=False):
+    """q [batch*lq, >=heads*64], k/v [batch*lk, ...] bf16 views (row stride = ld, unit column stride).
+    key_mask: fp32 [batch, lk] additive.  frames=(q_per_frame, k_per_frame) selects the block-causal mask."""
+    require_device(q)
+    if out is None:
+        out = torch.empty(batch * lq, heads * 64, device=q.device, dtype=BF16)
+    lse = torch.empty(batch, heads, lq, device=q.device, dtype=torch.float32) if save_lse else None
+    a = AttnArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), _ld(q), ptr(k), _ld(k), ptr(v), _ld(v)
+    a.o, a.ldo, a.lse = ptr(out), _ld(out), ptr(lse)
+    a.batch, a.heads, a.lq, a.lk, a.scale = batch, heads, lq, lk, scale
+    a.mask_mode = 1 if key_mask is not None else (2 if frames is not None else 0)
+    if key_mask is not None:
+        assert key_mask.dtype == torch.float32 and key_mask.is_contiguous() and key_mask.shape == (batch, lk)
+    a.key_mask = ptr(key_mask)
+    a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
+    call("shg_attn_fwd", a, stream())
+    return out, lse
 
 
 def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False):

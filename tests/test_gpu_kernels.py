@@ -282,3 +282,47 @@ def test_colsum_add_rows_cast(ops):
     assert torch.equal(y, ref)
     f = torch.randn(1000003, generator=g).to(_dev())
     assert torch.equal(ops.to_bf16(f), f.to(torch.bfloat16))
+
+
+# ----------------------------------------------------------------------------- attention (tcgen05)
+
+def _attn_ref(q, k, v, b, lq, lk, scale, add_mask):
+    qh = q.float().view(b, lq, 12, 64).transpose(1, 2)
+    kh = k.float().view(b, lk, 12, 64).transpose(1, 2)
+    vh = v.float().view(b, lk, 12, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if add_mask is not None:
+        s = s + add_mask
+    pr = torch.softmax(s, -1)
+    return (pr @ vh).transpose(1, 2).reshape(b * lq, 768), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("lq,lk,mode", [(40, 40, "key"), (393, 393, "none"), (40, 393, "none"), (393, 40, "key"),
+                                        (128, 128, "causal8"), (128, 393, "none"), (48, 48, "causal3"),
+                                        (48, 393, "none"), (40, 177, "key"), (177, 40, "key"), (1, 5, "none")])
+def test_attention_fwd_all_path_shapes(ops, lq, lk, mode):
+    """The ten (Lq, Lk, mask) problems of SURVEY §8d, read from packed QKV buffers in place.
+    Tolerance: 2e-2 of the output scale (bf16 P and bf16 output)."""
+    b = 3
+    g = torch.Generator().manual_seed(lq * 1000 + lk)
+    qkv_q = torch.randn(b * lq, 2304, generator=g).to(torch.bfloat16).to(_dev())
+    qkv_k = torch.randn(b * lk, 2304, generator=g).to(torch.bfloat16).to(_dev())
+    q, k, v = qkv_q[:, :768], qkv_k[:, 768:1536], qkv_k[:, 1536:]
+    key_mask, frames, add = None, None, None
+    if mode == "key":
+        valid = torch.randint(max(1, lk // 3), lk + 1, (b,), generator=g)
+        m01 = (torch.arange(lk)[None, :] < valid[:, None]).float()
+        key_mask = ((1 - m01) * -10000.0).to(_dev())
+        add = key_mask[:, None, None, :]
+    elif mode.startswith("causal"):
+        per = int(mode[6:])
+        frames = (per, per)
+        f = torch.arange(lq) // per
+        add = torch.zeros(lq, lk)
+        add[f[None, :lk] > f[:, None]] = float("-inf")
+        add = add.to(_dev())
+    out, lse = ops.attention_fwd(q, k, v, b, lq, lk, key_mask=key_mask, frames=frames, save_lse=True)
+    ref, ref_lse = _attn_ref(q, k, v, b, lq, lk, 0.125, add)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), err
+    assert torch.allclose(lse, ref_lse, atol=2e-2, rtol=1e-3)
