@@ -166,6 +166,12 @@ int shg_embed_scatter_bwd(const void* de, const int64_t* word_ids, const int64_t
 /* y[r,:] = x[r,:] + add[r % add_rows,:] (bf16): type tokens of CrossEncoder (lxrt/modeling_capsbert.py:1168-1181),
  * learned visual position rows (:1019-1024). */
 int shg_add_rows(const void* x, const void* add, int add_rows, void* y, int rows, int n, void* stream);
+/* Strided block copy (bf16): dst[i0*d0 + i1*d1 + e] (+)= src[i0*s0 + i1*s1 + e] (+ add[e]), e < chunk.  Assembles
+ * the hypergraph token sequence [CLS | per frame: 3 action + 8 relation slots] with its type tokens
+ * (tasks/agqa_model.py:255-258, lxrt/modeling_capsbert.py:1168-1184), picks [CLS] rows for BertPooler2, and routes
+ * gradients back (accumulate != 0 adds into dst). */
+int shg_copy3d(const void* src, void* dst, const void* add, int n0, int n1, int chunk, int64_t s0, int64_t s1,
+               int64_t d0, int64_t d1, int accumulate, void* stream);
 /* fp32 -> bf16 shadow copy of parameters / inputs. */
 int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 

@@ -318,6 +318,38 @@ __global__ void __launch_bounds__(256) add_rows_kernel(const __nv_bfloat16* __re
     }
 }
 
+// dst[i0*d0 + i1*d1 + e] = src[i0*s0 + i1*s1 + e] (+ add[e]) for e < chunk: strided block gather/scatter used to
+// assemble the hypergraph token sequence (tasks/agqa_model.py:255-258, lxrt/modeling_capsbert.py:1168-1184),
+// to pick [CLS] rows for the pooler, and to route the matching gradients back.  chunk % 8 == 0.
+__global__ void __launch_bounds__(256) copy3d_kernel(const __nv_bfloat16* __restrict__ src,
+                                                    __nv_bfloat16* __restrict__ dst,
+                                                    const __nv_bfloat16* __restrict__ add, int n0, int n1, int chunk8,
+                                                    int64_t s0, int64_t s1, int64_t d0, int64_t d1, int accumulate) {
+    const int64_t total = (int64_t)n0 * n1 * chunk8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e8 = (int)(i % chunk8);
+        const int64_t blk = i / chunk8;
+        const int i1 = (int)(blk % n1);
+        const int64_t i0 = blk / n1;
+        float v[8];
+        load8(src + i0 * s0 + i1 * s1 + e8 * 8, v);
+        if (add) {
+            float a[8];
+            load8(add + e8 * 8, a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += a[k];
+        }
+        __nv_bfloat16* o = dst + i0 * d0 + i1 * d1 + e8 * 8;
+        if (accumulate) {
+            float a[8];
+            load8(o, a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += a[k];
+        }
+        store8(o, v);
+    }
+}
+
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -428,6 +460,21 @@ int shg_add_rows(const void* x, const void* add, int add_rows, void* y, int rows
     add_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add,
                                                               add_rows, (__nv_bfloat16*)y, total8, n / 8);
     return check_launch("shg_add_rows");
+}
+
+int shg_copy3d(const void* src, void* dst, const void* add, int n0, int n1, int chunk, int64_t s0, int64_t s1,
+               int64_t d0, int64_t d1, int accumulate, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(chunk % 8 == 0 && s0 % 8 == 0 && s1 % 8 == 0 && d0 % 8 == 0 && d1 % 8 == 0, SHG_ESHAPE,
+                "shg_copy3d: chunk and strides must be multiples of 8 elements");
+    if (n0 <= 0 || n1 <= 0 || chunk <= 0) return SHG_OK;
+    const int64_t total = (int64_t)n0 * n1 * (chunk / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    copy3d_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst,
+                                                                 (const __nv_bfloat16*)add, n0, n1, chunk / 8, s0, s1,
+                                                                 d0, d1, accumulate);
+    return check_launch("shg_copy3d");
 }
 
 int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {

@@ -117,6 +117,12 @@ def add_rows(x, add):
     return y
 
 
+def copy3d(src, dst, n0, n1, chunk, s0, s1, d0, d1, add=None, accumulate=False):
+    """Strided block copy over raw bf16 storage; strides in elements (see include/shgvqa.h)."""
+    require_device(src)
+    call("shg_copy3d", ptr(src), ptr(dst), ptr(add), n0, n1, chunk, s0, s1, d0, d1, int(accumulate), stream())
+
+
 def to_bf16(x, out=None):
     require_device(x)
     assert x.dtype == torch.float32 and x.is_contiguous()

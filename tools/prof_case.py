@@ -1,0 +1,24 @@
+"""Tiny single-kernel driver for ncu captures: python tools/prof_case.py attn|gemm|ln"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from shg_vqa_b200 import ops
+dev = torch.device("cuda:0")
+B = 32
+what = sys.argv[1]
+if what == "attn":
+    lq = int(sys.argv[2]) if len(sys.argv) > 2 else 393
+    lk = int(sys.argv[3]) if len(sys.argv) > 3 else 393
+    q = torch.randn(B * lq, 2304, device=dev).to(torch.bfloat16)
+    kv = torch.randn(B * lk, 2304, device=dev).to(torch.bfloat16)
+    for _ in range(3):
+        ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk)
+elif what == "gemm":
+    m, n, k = [int(v) for v in sys.argv[2:5]] if len(sys.argv) > 4 else (B * 393, 3072, 768)
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16)
+    w = torch.randn(n, k, device=dev).to(torch.bfloat16)
+    bias = torch.randn(n, device=dev)
+    for _ in range(3):
+        ops.gemm(a, w, bias=bias)
+torch.cuda.synchronize()
+print("done")
