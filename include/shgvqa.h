@@ -130,6 +130,29 @@ typedef struct {
 } shg_attn_args;
 int shg_attn_fwd(const shg_attn_args* args, void* stream);
 
+/* Backward of the above (autograd of lxrt/modeling_capsbert.py:394-417 / nn.MultiheadAttention).  Recomputes
+ * the probabilities from q, k and the saved lse; d_o is the gradient of o; writes dq/dk/dv (bf16, same head
+ * layout, any leading dimension — e.g. column slices of a packed dQKV buffer) and delta (fp32 [batch,heads,lq]
+ * scratch).  Two launches: a per-query-tile pass for dq and a per-key-tile pass for dk, dv. */
+typedef struct {
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    const void* o; int64_t ldo;
+    const void* d_o; int64_t lddo;
+    const float* lse;
+    float* delta;
+    void* dq; int64_t lddq;
+    void* dk; int64_t lddk;
+    void* dv; int64_t lddv;
+    int batch, heads, lq, lk;
+    float scale;
+    int mask_mode;
+    const float* key_mask;
+    int q_per_frame, k_per_frame;
+} shg_attn_bwd_args;
+int shg_attn_bwd(const shg_attn_bwd_args* args, void* stream);
+
 /* ------------------------------------------------------------------ LayerNorm family (HBM-bound)
  * y = LN(x (+ residual)) * gamma + beta, rows of width n (768 / 1536), statistics fp32.  Replaces
  * BertLayerNorm after BertAttOutput/BertOutput (lxrt/modeling_capsbert.py:431-435,485-489; eps 1e-12),

@@ -38,6 +38,15 @@ class AttnArgs(ctypes.Structure):
                 ("q_per_frame", c_int), ("k_per_frame", c_int)]
 
 
+class AttnBwdArgs(ctypes.Structure):
+    _fields_ = [("q", c_vp), ("ldq", c_i64), ("k", c_vp), ("ldk", c_i64), ("v", c_vp), ("ldv", c_i64),
+                ("o", c_vp), ("ldo", c_i64), ("d_o", c_vp), ("lddo", c_i64), ("lse", c_vp), ("delta", c_vp),
+                ("dq", c_vp), ("lddq", c_i64), ("dk", c_vp), ("lddk", c_i64), ("dv", c_vp), ("lddv", c_i64),
+                ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
+                ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
+                ("q_per_frame", c_int), ("k_per_frame", c_int)]
+
+
 # name -> argtypes (all return int).  Must list every symbol include/shgvqa.h declares.
 SIGNATURES = {
     "shg_version": [],
@@ -49,6 +58,7 @@ SIGNATURES = {
     "shg_set_loss_bwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_int, c_int, c_vp],
     "shg_gemm": [ctypes.POINTER(GemmArgs), c_vp],
     "shg_attn_fwd": [ctypes.POINTER(AttnArgs), c_vp],
+    "shg_attn_bwd": [ctypes.POINTER(AttnBwdArgs), c_vp],
     "shg_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp],
     "shg_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp],
     "shg_colsum_accum": [c_vp, c_i64, c_int, c_int, c_vp, c_vp],

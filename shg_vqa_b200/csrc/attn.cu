@@ -183,6 +183,403 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     }
 }
 
+// =====================================================================================================
+// Backward.  Two passes, each recomputing the probabilities from Q, K and the saved log-sum-exp:
+//   dq pass  : CTA = (128-query tile, head, batch); loops over 128-key chunks;   dQ  = scale * dS . K
+//   dkv pass : CTA = (128-key tile,  head, batch); loops over 128-query chunks;  dV  = P^T . dO,
+//                                                                                dK  = scale * dS^T . Q
+// with dS = P o (dP - delta), dP = dO . V^T, delta = rowsum(dO o O).  Per chunk: two tcgen05 products into
+// TMEM (S and dP, or their transposes), 256 threads turn them into bf16 P / dS tiles in 128B-swizzled shared
+// memory (thread = one row, half the columns), and those tiles feed the accumulating products as K-major A
+// operands while the TMA-loaded K / Q / dO tiles are consumed as MN-major B operands in place.
+// =====================================================================================================
+constexpr int kBwdThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnBwdParams {
+    const __nv_bfloat16* o;    // forward output  [batch*lq, ldo]
+    const __nv_bfloat16* d_o;  // its gradient    [batch*lq, lddo]
+    int64_t ldo, lddo;
+    const float* lse;          // [batch, heads, lq]
+    float* delta;              // [batch, heads, lq]  (written by the dq pass, read by the dkv pass)
+    __nv_bfloat16* dq;
+    __nv_bfloat16* dk;
+    __nv_bfloat16* dv;
+    int64_t lddq, lddk, lddv;
+    const float* key_mask;
+    int batch, heads, lq, lk;
+    float scale;
+    int mask_mode, q_per_frame, k_per_frame;
+};
+
+// 32 consecutive bf16 of row `row` at column c (multiple of 32) of a [128 x 128] K-major tile made of two
+// [128 x 64] 128B-swizzled blocks.
+__device__ __forceinline__ void store_tile_chunk32(uint8_t* tile, int row, int c, const float (&v)[32]) {
+    uint8_t* blk = tile + (c >> 6) * 16384 + row * 128;
+    const int j0 = (c & 32) ? 4 : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]), u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) = u;
+    }
+}
+
+// K-major A descriptor for k-step ks (16 columns) of such a tile; MN-major B descriptor for rows [16ks,16ks+16)
+// of a [128 x 64] TMA tile.
+__device__ __forceinline__ uint64_t tile_a_desc(uint32_t tile, int ks) {
+    return make_smem_desc(tile + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t rows_b_desc(uint32_t tile, int ks) {
+    return make_smem_desc(tile + ks * 2048, 8192, 1024);
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
+                   const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
+                   const AttnBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                       // 16 KB
+    uint8_t* sdO = smem + 16384;              // 16 KB
+    uint8_t* sK = smem + 32768;               // 2 x 16 KB
+    uint8_t* sV = smem + 65536;               // 2 x 16 KB
+    uint8_t* sdS = smem + 98304;              // 2 x 32 KB
+    float* s_lse = reinterpret_cast<float*>(smem + 163840);
+    float* s_delta = s_lse + 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 128);
+    uint64_t* bar_q = bars;          // Q + dO landed
+    uint64_t* bar_kv = bars + 1;     // [2]
+    uint64_t* bar_s = bars + 3;      // S and dP of the current chunk complete
+    uint64_t* bar_dq = bars + 4;     // [2] dQ product of chunk j retired (frees sdS[j&1], sK/sV[j&1])
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_kc = (p.lk + 127) / 128;
+
+    if (tid == 0) {
+        mbar_init(bar_q, 1);
+        mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_dq, 1), mbar_init(bar_dq + 1, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    // delta = rowsum(dO o O), straight from HBM (128 B per row per tensor)
+    if (tid < 128) {
+        const int q = q0 + tid;
+        float d = 0.f, l = INFINITY;
+        if (q < p.lq) {
+            const uint4* po = reinterpret_cast<const uint4*>(p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)b * p.lq + q) * p.lddo + h * kHeadDim);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 a = __ldg(po + i), g = __ldg(pd + i);
+                float2 x, y;
+                x = unpack_bf16x2(a.x), y = unpack_bf16x2(g.x), d += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.y), y = unpack_bf16x2(g.y), d += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.z), y = unpack_bf16x2(g.z), d += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.w), y = unpack_bf16x2(g.w), d += x.x * y.x + x.y * y.y;
+            }
+            l = p.lse[((size_t)b * p.heads + h) * p.lq + q];
+            p.delta[((size_t)b * p.heads + h) * p.lq + q] = d;
+        }
+        s_delta[tid] = d;
+        s_lse[tid] = l * kLog2e;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 256;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
+
+    auto issue_s = [&](int j) {   // S = Q K_j^T ; dP = dO V_j^T
+        const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
+        const uint32_t bk = smem_u32(sK + (j & 1) * 16384), bv = smem_u32(sV + (j & 1) * 16384);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(t_s, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(bk + ks * 32, 16, 1024), idesc_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(t_dp, make_smem_desc(ado + ks * 32, 16, 1024), make_smem_desc(bv + ks * 32, 16, 1024), idesc_s, ks > 0);
+        tc_commit(bar_s);
+    };
+    auto load_kv = [&](int j) {
+        mbar_expect_tx(bar_kv + (j & 1), 32768);
+        tma_load_3d(sK + (j & 1) * 16384, &tma_k, bar_kv + (j & 1), h * kHeadDim, j * 128, b);
+        tma_load_3d(sV + (j & 1) * 16384, &tma_v, bar_kv + (j & 1), h * kHeadDim, j * 128, b);
+    };
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_q, 32768);
+        tma_load_3d(sQ, &tma_q, bar_q, h * kHeadDim, q0, b);
+        tma_load_3d(sdO, &tma_do, bar_q, h * kHeadDim, q0, b);
+        load_kv(0);
+        if (n_kc > 1) load_kv(1);
+        mbar_wait(bar_q, 0);
+        mbar_wait(bar_kv, 0);
+        tc_fence_after();
+        issue_s(0);
+    }
+    __syncwarp();
+
+    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int q = q0 + row;
+    const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
+    const float* kmask = p.mask_mode == 1 ? p.key_mask + (size_t)b * p.lk : nullptr;
+    const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
+    const float c1 = p.scale * kLog2e;
+    const float my_lse = s_lse[row], my_delta = s_delta[row];
+
+    for (int j = 0; j < n_kc; ++j) {
+        mbar_wait(bar_s, j & 1);
+        tc_fence_after();
+        if (j >= 2) mbar_wait(bar_dq + (j & 1), ((j - 2) >> 1) & 1);   // sdS[j&1] free again
+        uint8_t* tile = sdS + (j & 1) * 32768;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 64 + cc * 32;
+            uint32_t rs[32], rp[32];
+            tmem_ld32(t_s + t_row + c, rs);
+            tmem_ld32(t_dp + t_row + c, rp);
+            tmem_ld_wait();
+            float ds[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int key = j * 128 + c + i;
+                float x = __uint_as_float(rs[i]) * c1 - my_lse;
+                if (kmask && key < p.lk) x += __ldg(kmask + key) * kLog2e;
+                const float pr = key < k_lim ? exp2f(x) : 0.f;
+                ds[i] = pr * (__uint_as_float(rp[i]) - my_delta) * p.scale;
+            }
+            store_tile_chunk32(tile, row, c, ds);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a = smem_u32(tile), bk = smem_u32(sK + (j & 1) * 16384);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+                umma_bf16(t_dq, tile_a_desc(a, ks), rows_b_desc(bk, ks), idesc_dq, (j > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(bar_dq + (j & 1));
+            if (j + 1 < n_kc) {
+                mbar_wait(bar_kv + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_s(j + 1);
+            }
+            if (j + 2 < n_kc) {
+                mbar_wait(bar_dq + (j & 1), (j >> 1) & 1);
+                load_kv(j + 2);
+            }
+        }
+        __syncwarp();
+    }
+    mbar_wait(bar_dq + ((n_kc - 1) & 1), ((n_kc - 1) >> 1) & 1);
+    if (n_kc > 1) mbar_wait(bar_dq + ((n_kc - 2) & 1), ((n_kc - 2) >> 1) & 1);
+    tc_fence_after();
+    {
+        uint32_t raw[32];
+        tmem_ld32(t_dq + t_row + half * 32, raw);
+        tmem_ld_wait();
+        if (q < p.lq) {
+            __nv_bfloat16* dst = p.dq + ((size_t)b * p.lq + q) * p.lddq + h * kHeadDim + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+                u.y = pack_bf16x2(__uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+                u.z = pack_bf16x2(__uint_as_float(raw[i + 4]), __uint_as_float(raw[i + 5]));
+                u.w = pack_bf16x2(__uint_as_float(raw[i + 6]), __uint_as_float(raw[i + 7]));
+                *reinterpret_cast<uint4*>(dst + i) = u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
+                    const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
+                    const AttnBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;                       // 16 KB
+    uint8_t* sV = smem + 16384;               // 16 KB
+    uint8_t* sQ = smem + 32768;               // 2 x 16 KB
+    uint8_t* sdO = smem + 65536;              // 2 x 16 KB
+    uint8_t* sPt = smem + 98304;              // 32 KB   P^T  [128 keys x 128 queries]
+    uint8_t* sdSt = smem + 131072;            // 32 KB   dS^T
+    float* s_lse = reinterpret_cast<float*>(smem + 163840);   // [2][128]
+    float* s_delta = s_lse + 256;                               // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
+    uint64_t* bar_kv = bars;
+    uint64_t* bar_q = bars + 1;      // [2]
+    uint64_t* bar_s = bars + 3;
+    uint64_t* bar_acc = bars + 4;    // dK/dV products of chunk i retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_qc = (p.lq + 127) / 128;
+
+    if (tid == 0) {
+        mbar_init(bar_kv, 1);
+        mbar_init(bar_q, 1), mbar_init(bar_q + 1, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_s = tmem, t_dp = tmem + 128, t_dk = tmem + 256, t_dv = tmem + 320;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_acc = make_idesc_bf16(128, kHeadDim, 0, 1);
+
+    auto issue_s = [&](int i) {   // S^T = K Q_i^T ; dP^T = V dO_i^T
+        const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
+        const uint32_t bq = smem_u32(sQ + (i & 1) * 16384), bd = smem_u32(sdO + (i & 1) * 16384);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(t_s, make_smem_desc(ak + ks * 32, 16, 1024), make_smem_desc(bq + ks * 32, 16, 1024), idesc_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(t_dp, make_smem_desc(av + ks * 32, 16, 1024), make_smem_desc(bd + ks * 32, 16, 1024), idesc_s, ks > 0);
+        tc_commit(bar_s);
+    };
+    auto load_q = [&](int i) {
+        mbar_expect_tx(bar_q + (i & 1), 32768);
+        tma_load_3d(sQ + (i & 1) * 16384, &tma_q, bar_q + (i & 1), h * kHeadDim, i * 128, b);
+        tma_load_3d(sdO + (i & 1) * 16384, &tma_do, bar_q + (i & 1), h * kHeadDim, i * 128, b);
+    };
+    auto load_vec = [&](int i) {  // lse / delta of query chunk i -> smem (all 256 threads)
+        const int qq = i * 128 + (tid & 127);
+        const size_t base = ((size_t)b * p.heads + h) * p.lq;
+        if (tid < 128) s_lse[(i & 1) * 128 + tid] = qq < p.lq ? p.lse[base + qq] * kLog2e : INFINITY;
+        else s_delta[(i & 1) * 128 + (tid - 128)] = qq < p.lq ? p.delta[base + qq] : 0.f;
+    };
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_kv, 32768);
+        tma_load_3d(sK, &tma_k, bar_kv, h * kHeadDim, k0, b);
+        tma_load_3d(sV, &tma_v, bar_kv, h * kHeadDim, k0, b);
+        load_q(0);
+        if (n_qc > 1) load_q(1);
+        mbar_wait(bar_kv, 0);
+        mbar_wait(bar_q, 0);
+        tc_fence_after();
+        issue_s(0);
+    }
+    load_vec(0);
+    __syncthreads();
+
+    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int key = k0 + row;
+    const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
+    const float c1 = p.scale * kLog2e;
+    const float kbias = (p.mask_mode == 1 && key < p.lk) ? p.key_mask[(size_t)b * p.lk + key] * kLog2e : 0.f;
+    // block-causal: this key is visible to queries of frame >= its own frame, i.e. q >= q_first
+    const int q_first = p.mask_mode == 2 ? (key / p.k_per_frame) * p.q_per_frame : 0;
+    const bool key_ok = key < p.lk;
+
+    for (int i = 0; i < n_qc; ++i) {
+        if (i + 1 < n_qc) load_vec(i + 1);          // other buffer; consumed after the next __syncthreads
+        mbar_wait(bar_s, i & 1);
+        tc_fence_after();
+        if (i >= 1) mbar_wait(bar_acc, (i - 1) & 1);   // sPt / sdSt free again
+        const float* lse_i = s_lse + (i & 1) * 128;
+        const float* del_i = s_delta + (i & 1) * 128;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 64 + cc * 32;
+            uint32_t rs[32], rp[32];
+            tmem_ld32(t_s + t_row + c, rs);
+            tmem_ld32(t_dp + t_row + c, rp);
+            tmem_ld_wait();
+            float pr[32], ds[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int qq = i * 128 + c + e;
+                const float x = __uint_as_float(rs[e]) * c1 + kbias - lse_i[c + e];   // lse = +inf beyond lq
+                pr[e] = (key_ok && qq >= q_first) ? exp2f(x) : 0.f;
+                ds[e] = pr[e] * (__uint_as_float(rp[e]) - del_i[c + e]) * p.scale;
+            }
+            store_tile_chunk32(sPt, row, c, pr);
+            store_tile_chunk32(sdSt, row, c, ds);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t ap = smem_u32(sPt), ads = smem_u32(sdSt);
+            const uint32_t bq = smem_u32(sQ + (i & 1) * 16384), bd = smem_u32(sdO + (i & 1) * 16384);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+                umma_bf16(t_dv, tile_a_desc(ap, ks), rows_b_desc(bd, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+                umma_bf16(t_dk, tile_a_desc(ads, ks), rows_b_desc(bq, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(bar_acc);
+            if (i + 1 < n_qc) {
+                mbar_wait(bar_q + ((i + 1) & 1), ((i + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_s(i + 1);
+            }
+            if (i + 2 < n_qc) {
+                mbar_wait(bar_acc, i & 1);
+                load_q(i + 2);
+            }
+        }
+        __syncwarp();
+    }
+    mbar_wait(bar_acc, (n_qc - 1) & 1);
+    tc_fence_after();
+    {
+        // warps 0-3 write dK, warps 4-7 write dV (64 columns each)
+        const uint32_t t_src = (half == 0 ? t_dk : t_dv) + t_row;
+        __nv_bfloat16* base = half == 0 ? p.dk : p.dv;
+        const int64_t ld = half == 0 ? p.lddk : p.lddv;
+#pragma unroll
+        for (int c = 0; c < kHeadDim; c += 32) {
+            uint32_t raw[32];
+            tmem_ld32(t_src + c, raw);
+            tmem_ld_wait();
+            if (key_ok) {
+                __nv_bfloat16* dst = base + ((size_t)b * p.lk + key) * ld + h * kHeadDim + c;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]));
+                    u.y = pack_bf16x2(__uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
+                    u.z = pack_bf16x2(__uint_as_float(raw[e + 4]), __uint_as_float(raw[e + 5]));
+                    u.w = pack_bf16x2(__uint_as_float(raw[e + 6]), __uint_as_float(raw[e + 7]));
+                    *reinterpret_cast<uint4*>(dst + e) = u;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 static const CUtensorMap* head_tmap(const void* ptr, int64_t ld, int heads, int len, int batch, int box_rows) {
     uint64_t dims[3] = {(uint64_t)heads * kHeadDim, (uint64_t)len, (uint64_t)batch};
     uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)len};
@@ -229,4 +626,40 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     dim3 grid((a->lq + 127) / 128, a->heads, a->batch);
     attn_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(*tq, *tk, *tv, p);
     return check_launch("shg_attn_fwd");
+}
+
+extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(a && a->q && a->k && a->v && a->o && a->d_o && a->lse && a->delta && a->dq && a->dk && a->dv,
+                SHG_EINVAL, "shg_attn_bwd: null operand");
+    SHG_REQUIRE(a->lk >= 1 && a->lq >= 1, SHG_ESHAPE, "shg_attn_bwd: empty problem");
+    SHG_REQUIRE(a->mask_mode >= 0 && a->mask_mode <= 2 && (a->mask_mode != 1 || a->key_mask), SHG_EINVAL,
+                "shg_attn_bwd: bad mask");
+    SHG_REQUIRE(a->ldo % 8 == 0 && a->lddo % 8 == 0 && a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0,
+                SHG_ESHAPE, "shg_attn_bwd: leading dimensions must be multiples of 8");
+    AttnBwdParams p;
+    p.o = (const __nv_bfloat16*)a->o, p.d_o = (const __nv_bfloat16*)a->d_o, p.ldo = a->ldo, p.lddo = a->lddo;
+    p.lse = a->lse, p.delta = a->delta;
+    p.dq = (__nv_bfloat16*)a->dq, p.dk = (__nv_bfloat16*)a->dk, p.dv = (__nv_bfloat16*)a->dv;
+    p.lddq = a->lddq, p.lddk = a->lddk, p.lddv = a->lddv;
+    p.key_mask = a->key_mask, p.batch = a->batch, p.heads = a->heads, p.lq = a->lq, p.lk = a->lk;
+    p.scale = a->scale, p.mask_mode = a->mask_mode, p.q_per_frame = a->q_per_frame, p.k_per_frame = a->k_per_frame;
+    const CUtensorMap* tq = head_tmap(a->q, a->ldq, a->heads, a->lq, a->batch, 128);
+    const CUtensorMap* tdo = head_tmap(a->d_o, a->lddo, a->heads, a->lq, a->batch, 128);
+    const CUtensorMap* tk = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, 128);
+    const CUtensorMap* tv = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, 128);
+    if (!tq || !tdo || !tk || !tv) return SHG_ECUDA;
+    const size_t smem = 163840 + 2048 + 128 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    attn_bwd_dq_kernel<<<dim3((a->lq + 127) / 128, a->heads, a->batch), kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    int rc = check_launch("shg_attn_bwd(dq)");
+    if (rc) return rc;
+    attn_bwd_dkv_kernel<<<dim3((a->lk + 127) / 128, a->heads, a->batch), kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    return check_launch("shg_attn_bwd(dkv)");
 }

@@ -6,7 +6,7 @@ returns torch tensors it allocated; none falls back to PyTorch math.
 import torch
 
 from . import _lib
-from ._lib import AttnArgs, GemmArgs, call, ptr, require_device, stream
+from ._lib import AttnArgs, AttnBwdArgs, GemmArgs, call, ptr, require_device, stream
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "tanh": 3}
 MUL = {None: 0, "gelu_grad": 1, "relu_mask": 2}
@@ -79,6 +79,23 @@ def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, 
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
     call("shg_attn_fwd", a, stream())
     return out, lse
+
+
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, scale=0.125, key_mask=None,
+                  frames=None):
+    """Writes dq/dk/dv (bf16 views with the same head layout as q/k/v)."""
+    require_device(q)
+    delta = torch.empty_like(lse)
+    a = AttnBwdArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), _ld(q), ptr(k), _ld(k), ptr(v), _ld(v)
+    a.o, a.ldo, a.d_o, a.lddo = ptr(o), _ld(o), ptr(d_o), _ld(d_o)
+    a.lse, a.delta = ptr(lse), ptr(delta)
+    a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = ptr(dq), _ld(dq), ptr(dk), _ld(dk), ptr(dv), _ld(dv)
+    a.batch, a.heads, a.lq, a.lk, a.scale = batch, heads, lq, lk, scale
+    a.mask_mode = 1 if key_mask is not None else (2 if frames is not None else 0)
+    a.key_mask = ptr(key_mask)
+    a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
+    call("shg_attn_bwd", a, stream())
 
 
 def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False):

@@ -326,3 +326,43 @@ def test_attention_fwd_all_path_shapes(ops, lq, lk, mode):
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item(), err
     assert torch.allclose(lse, ref_lse, atol=2e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("lq,lk,mode", [(40, 40, "key"), (393, 393, "none"), (40, 393, "none"), (393, 40, "key"),
+                                        (128, 128, "causal8"), (128, 393, "none"), (48, 48, "causal3"),
+                                        (48, 393, "none"), (40, 177, "none"), (177, 40, "key")])
+def test_attention_bwd_all_path_shapes(ops, lq, lk, mode):
+    """dq/dk/dv against torch autograd of the fp32 attention on the same bf16 inputs; tolerance 3e-2 of each
+    gradient's scale (P, dS and the outputs are bf16)."""
+    b = 2
+    g = torch.Generator().manual_seed(lq * 1000 + lk + 1)
+    qkv_q = (torch.randn(b * lq, 2304, generator=g)).to(torch.bfloat16).to(_dev())
+    qkv_k = (torch.randn(b * lk, 2304, generator=g)).to(torch.bfloat16).to(_dev())
+    q, k, v = qkv_q[:, :768], qkv_k[:, 768:1536], qkv_k[:, 1536:]
+    key_mask, frames, add = None, None, None
+    if mode == "key":
+        valid = torch.randint(max(1, lk // 3), lk + 1, (b,), generator=g)
+        m01 = (torch.arange(lk)[None, :] < valid[:, None]).float()
+        key_mask = ((1 - m01) * -10000.0).to(_dev())
+        add = key_mask[:, None, None, :]
+    elif mode.startswith("causal"):
+        per = int(mode[6:])
+        frames = (per, per)
+        f = torch.arange(lq) // per
+        add = torch.zeros(lq, lk)
+        add[f[None, :lk] > f[:, None]] = float("-inf")
+        add = add.to(_dev())
+    out, lse = ops.attention_fwd(q, k, v, b, lq, lk, key_mask=key_mask, frames=frames, save_lse=True)
+    d_o = torch.randn(b * lq, 768, generator=g).to(torch.bfloat16).to(_dev())
+    dq_buf = torch.zeros(b * lq, 2304, device=_dev(), dtype=torch.bfloat16)
+    dk_buf = torch.zeros(b * lk, 2304, device=_dev(), dtype=torch.bfloat16)
+    ops.attention_bwd(q, k, v, out, d_o, lse, dq_buf[:, :768], dk_buf[:, 768:1536], dk_buf[:, 1536:], b, lq, lk,
+                      key_mask=key_mask, frames=frames)
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _attn_ref(qf, kf, vf, b, lq, lk, 0.125, add)
+    ref.backward(d_o.float())
+    for name, got, want in (("dq", dq_buf[:, :768], qf.grad), ("dk", dk_buf[:, 768:1536], kf.grad),
+                            ("dv", dk_buf[:, 1536:], vf.grad)):
+        err = (got.float() - want).abs().max().item()
+        assert err <= 3e-2 * want.abs().max().item() + 1e-6, (name, err, want.abs().max().item())
+    assert float(dq_buf[:, 768:].abs().max()) == 0.0 and float(dk_buf[:, :768].abs().max()) == 0.0
