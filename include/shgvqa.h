@@ -102,7 +102,7 @@ typedef struct {
     const void* mul_aux;   /* bf16 [M,N], ld = ldd: backward through an activation, applied after act/bias */
     int mul_mode;          /* SHG_MUL_GELU_GRAD: d *= gelu'(mul_aux) ; SHG_MUL_RELU_MASK: d = mul_aux > 0 ? d : 0 */
     int flags;
-    int splits;        /* >= 1; > 1 requires SHG_GEMM_ACCUMULATE */
+    int splits;        /* 0 = choose (split-K only with SHG_GEMM_ACCUMULATE); > 1 requires SHG_GEMM_ACCUMULATE */
     int block_n;       /* 0 = choose; else one of 64,128,192,256 */
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
@@ -170,7 +170,7 @@ int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void
                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
                       int rows, int n, void* stream);
 
-/* out[n] += column sums of the bf16 matrix x [rows, n] (ld elements per row): bias gradients. */
+/* out[n] += column sums of the bf16 matrix x [rows, n] (ld elements per row, ld % 8 == 0): bias gradients. */
 int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, void* stream);
 
 /* Embedding gathers fused with LayerNorm: BertEmbeddings (lxrt/modeling_capsbert.py:341-355; word[ids] +
@@ -189,6 +189,13 @@ int shg_embed_scatter_bwd(const void* de, const int64_t* word_ids, const int64_t
 /* y[r,:] = x[r,:] + add[r % add_rows,:] (bf16): type tokens of CrossEncoder (lxrt/modeling_capsbert.py:1168-1181),
  * learned visual position rows (:1019-1024). */
 int shg_add_rows(const void* x, const void* add, int add_rows, void* y, int rows, int n, void* stream);
+/* dx = dy * act'(aux) over n bf16 elements: act = SHG_ACT_GELU_ERF (aux = saved pre-activation),
+ * SHG_ACT_TANH / SHG_ACT_RELU (aux = saved output).  Backward of the MLP heads and the pooler. */
+int shg_act_bwd(const void* dy, const void* aux, void* dx, int64_t n, int act, void* stream);
+/* Answer loss: out[0] += BCEWithLogitsLoss()(x, target) * cols (tasks/agqaHGQA.py:344-345), x fp32 [rows, cols]
+ * (ldx), target fp32 [rows, cols]; dx (bf16, lddx; may be NULL) = grad_scale * d loss / d x. */
+int shg_bce_logits(const float* x, int64_t ldx, const float* target, int rows, int cols, float grad_scale, float* out,
+                   void* dx, int64_t lddx, void* stream);
 /* Strided block copy (bf16): dst[i0*d0 + i1*d1 + e] (+)= src[i0*s0 + i1*s1 + e] (+ add[e]), e < chunk.  Assembles
  * the hypergraph token sequence [CLS | per frame: 3 action + 8 relation slots] with its type tokens
  * (tasks/agqa_model.py:255-258, lxrt/modeling_capsbert.py:1168-1184), picks [CLS] rows for BertPooler2, and routes
@@ -197,6 +204,22 @@ int shg_copy3d(const void* src, void* dst, const void* add, int n0, int n1, int 
                int64_t d0, int64_t d1, int accumulate, void* stream);
 /* fp32 -> bf16 shadow copy of parameters / inputs. */
 int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ optimiser (HBM-bound, flat buffers)
+ * Replaces clip_grad_norm_(params, 5.) + BertAdam.step() (tasks/agqaHGQA.py:391-392, lxrt/optimization.py:101-180:
+ * no bias correction, decoupled weight decay on every tensor, lr from warmup_linear).  The buffers are flat fp32
+ * arrays; the "live" parameters (those that receive gradients — the reference skips p.grad is None) are given as
+ * segments: seg_start[i] = offset of segment i, seg_prefix[i] = number of live elements before it (both multiples
+ * of 4, device int64), total = live element count.
+ * shg_grad_sumsq: out[0] += sum g^2.  shg_bert_adam_step: g' = g * grad_scale * min(1, max_norm/(|g*grad_scale|+1e-6))
+ * (max_norm <= 0: no clipping), then the Adam update in place; refreshes the bf16 shadow (first n_shadow elements
+ * of the flat space) and optionally zeroes the gradient for the next step. */
+int shg_grad_sumsq(const float* grad, const int64_t* seg_start, const int64_t* seg_prefix, int n_seg,
+                   int64_t total, float* out, void* stream);
+int shg_bert_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow, int64_t n_shadow,
+                       const int64_t* seg_start, const int64_t* seg_prefix, int n_seg, int64_t total,
+                       const float* sumsq, float max_norm, float lr, float b1, float b2, float eps, float weight_decay,
+                       float grad_scale, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

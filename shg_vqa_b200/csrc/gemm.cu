@@ -343,8 +343,19 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     using namespace shg;
     SHG_REQUIRE(a && a->a && a->b && a->d, SHG_EINVAL, "shg_gemm: null operand");
     SHG_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, SHG_EINVAL, "shg_gemm: empty problem %dx%dx%d", a->m, a->n, a->k);
-    const int splits = a->splits < 1 ? 1 : a->splits;
     const bool accumulate = (a->flags & SHG_GEMM_ACCUMULATE) != 0;
+    int splits = a->splits;
+    if (splits < 1) {
+        // auto split-K (accumulating products only): enough CTAs to cover the chip, >= 8 k-blocks per split
+        splits = 1;
+        if (accumulate) {
+            const int tiles = ((a->m + BM - 1) / BM) * ((a->n + 255) / 256);
+            const int kb = (a->k + BK - 1) / BK;
+            splits = (kNumSMs + tiles / 2) / tiles;
+            if (splits > kb / 8) splits = kb / 8;
+            if (splits < 1) splits = 1;
+        }
+    }
     SHG_REQUIRE(splits == 1 || accumulate, SHG_EINVAL, "shg_gemm: splits>1 needs SHG_GEMM_ACCUMULATE");
     SHG_REQUIRE(!accumulate || !(a->preact || a->residual || a->act || a->mul_aux), SHG_EINVAL,
                 "shg_gemm: accumulate mode takes no activation/residual/preact");

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x][i];
-            atomicAdd(out + c + i, s);
+            if (c + i < n) atomicAdd(out + c + i, s);
         }
     }
 }
@@ -350,6 +350,49 @@ __global__ void __launch_bounds__(256) copy3d_kernel(const __nv_bfloat16* __rest
     }
 }
 
+// dx = dy * act'(aux): GELU from the saved pre-activation, tanh / ReLU from the saved output.
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                     const __nv_bfloat16* __restrict__ aux,
+                                                     __nv_bfloat16* __restrict__ dx, int64_t n8, int mode) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float g[8], a[8];
+        load8(dy + i * 8, g);
+        load8(aux + i * 8, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (mode == SHG_ACT_GELU_ERF) g[k] *= gelu_erf_grad(a[k]);
+            else if (mode == SHG_ACT_TANH) g[k] *= 1.0f - a[k] * a[k];
+            else g[k] = a[k] > 0.f ? g[k] : 0.f;
+        }
+        store8(dx + i * 8, g);
+    }
+}
+
+// BCEWithLogitsLoss()(x, t) * n_cols (tasks/agqaHGQA.py:344-345) = (1/rows) * sum over all elements; and its
+// gradient (sigmoid(x) - t) * grad_scale / rows as bf16.  out[0] += loss.
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ x, int64_t ldx,
+                                                        const float* __restrict__ t, int rows, int cols,
+                                                        float grad_scale, float* __restrict__ out,
+                                                        __nv_bfloat16* __restrict__ dx, int64_t lddx) {
+    float acc = 0.f;
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+        const float v = x[r * ldx + c], tv = t[i];
+        acc += fmaxf(v, 0.f) - v * tv + log1pf(expf(-fabsf(v)));
+        if (dx) dx[r * lddx + c] = __float2bfloat16((1.0f / (1.0f + expf(-v)) - tv) * grad_scale / rows);
+    }
+    acc = warp_sum(acc);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        atomicAdd(out, s / rows);
+    }
+}
+
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -411,10 +454,10 @@ int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void
 
 int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, void* stream) {
     using namespace shg;
-    SHG_REQUIRE(n % 8 == 0 && ld % 8 == 0, SHG_ESHAPE, "shg_colsum_accum: n=%d ld=%lld must be multiples of 8", n,
-                (long long)ld);
+    SHG_REQUIRE(ld % 8 == 0 && ld >= (n + 7) / 8 * 8, SHG_ESHAPE,
+                "shg_colsum_accum: ld=%lld must be a multiple of 8 covering n=%d rounded up to 8", (long long)ld, n);
     if (rows <= 0) return SHG_OK;
-    const int col_blocks = (n / 8 + 31) / 32;
+    const int col_blocks = ((n + 7) / 8 + 31) / 32;
     int row_blocks = (2 * kNumSMs + col_blocks - 1) / col_blocks;
     int rpb = (rows + row_blocks - 1) / row_blocks;
     if (rpb < 64) rpb = 64;
@@ -475,6 +518,29 @@ int shg_copy3d(const void* src, void* dst, const void* add, int n0, int n1, int 
                                                                  (const __nv_bfloat16*)add, n0, n1, chunk / 8, s0, s1,
                                                                  d0, d1, accumulate);
     return check_launch("shg_copy3d");
+}
+
+int shg_act_bwd(const void* dy, const void* aux, void* dx, int64_t n, int act, void* stream) {
+    using namespace shg;
+    SHG_REQUIRE(n % 8 == 0, SHG_ESHAPE, "shg_act_bwd: n=%lld must be a multiple of 8", (long long)n);
+    SHG_REQUIRE(act >= SHG_ACT_GELU_ERF && act <= SHG_ACT_TANH, SHG_EINVAL, "shg_act_bwd: act=%d", act);
+    if (n <= 0) return SHG_OK;
+    int64_t blocks = (n / 8 + 255) / 256;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    act_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux,
+                                                                  (__nv_bfloat16*)dx, n / 8, act);
+    return check_launch("shg_act_bwd");
+}
+
+int shg_bce_logits(const float* x, int64_t ldx, const float* target, int rows, int cols, float grad_scale, float* out,
+                   void* dx, int64_t lddx, void* stream) {
+    using namespace shg;
+    if (rows <= 0 || cols <= 0) return SHG_OK;
+    int blocks = (int)(((int64_t)rows * cols + 255) / 256);
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    bce_logits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, target, rows, cols, grad_scale, out,
+                                                                (__nv_bfloat16*)dx, lddx);
+    return check_launch("shg_bce_logits");
 }
 
 int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {

@@ -1,0 +1,520 @@
+"""Forward and hand-written backward of the SHG-VQA hot path over libshgvqa.
+
+This is the host-side schedule of the path SURVEY.md §8a names — embeddings (E0),
+language / relation BertLayers (L, R), the weight-shared CrossLayers (X), the two
+DETR decoders over per-frame relation / action queries (D), the MLP heads (H),
+the hypergraph x question CrossEncoder (HG), the poolers (P), the per-frame
+Hungarian matching and the set loss (M1-M4) — expressed as a flat sequence of
+C-ABI launches on the current CUDA stream.  No torch autograd, no torch math on
+the path: torch owns buffers and streams only, so a whole step is capturable in
+one CUDA graph.
+
+B200-first choices (vs the reference's module-by-module eager fp32):
+  * q|k|v (and the decoders' packed in_proj) are one [2304,768] projection;
+  * the ten decoder layers' memory K/V projections are hoisted into ONE
+    [B*393,768] x [768,15360] GEMM (and one dgrad on the way back);
+  * bias, GELU/ReLU/tanh, residual adds and the backward-through-activation are GEMM
+    epilogues; LayerNorm backward also emits the bias gradient of the Linear before it;
+  * forward/dgrad/wgrad all read operands where they lie (MN-major UMMA descriptors),
+    wgrad accumulates with split-K fp32 atomics straight into the flat gradient buffer;
+  * matching + weighted CE + its gradient never leave the device.
+"""
+import torch
+
+from . import ops
+from .params import ParamStore
+
+BF16 = torch.bfloat16
+H = 768
+EPS_BERT = 1e-12     # lxrt/modeling_capsbert.py:310,338,428,482 ; tasks/agqa_model.py:108
+EPS_DETR = 1e-5      # lxrt/transformer.py:199-201
+
+
+class Lin:
+    """One projection: bf16 shadow weight [N,K], fp32 bias [N], fp32 gradient views."""
+
+    def __init__(self, w, b, gw, gb):
+        self.w, self.b, self.gw, self.gb = w, b, gw, gb
+
+
+class Norm:
+    def __init__(self, g, b, gg, gb):
+        self.g, self.b, self.gg, self.gb = g, b, gg, gb
+
+
+class Engine:
+    def __init__(self, store: ParamStore, task="hgqa", n_frames=16, n_rel=8, n_act=3, l_layers=5, r_layers=5,
+                 x_layers=2, d_layers=5):
+        self.st = store
+        self.task = task
+        self.T, self.n_rel, self.n_act = n_frames, n_rel, n_act
+        self.nl, self.nr, self.nx, self.nd = l_layers, r_layers, x_layers, d_layers
+        self.dev = store.device
+        self._build_handles()
+
+    # ------------------------------------------------------------------ parameter handles
+    def _lin(self, wkey, bkey=None):
+        st = self.st
+        bkey = bkey or wkey.replace(".weight", ".bias")
+        return Lin(st.w(wkey), st.p(bkey), st.g(wkey) if st.grad is not None else None,
+                   st.g(bkey) if st.grad is not None else None)
+
+    def _norm(self, prefix):
+        st = self.st
+        g = st.grad is not None
+        return Norm(st.p(prefix + ".weight"), st.p(prefix + ".bias"),
+                    st.g(prefix + ".weight") if g else None, st.g(prefix + ".bias") if g else None)
+
+    def _qkv(self, prefix):
+        """query|key|value of a BertAttention as one [2304,768] projection (adjacent in the flat buffers)."""
+        st = self.st
+        g = st.grad is not None
+        return Lin(st.fused(st.shadow, prefix + ".query.weight", 3 * H, H),
+                   st.fused(st.master, prefix + ".query.bias", 3 * H),
+                   st.fused(st.grad, prefix + ".query.weight", 3 * H, H) if g else None,
+                   st.fused(st.grad, prefix + ".query.bias", 3 * H) if g else None)
+
+    def _rows(self, lin, r0, r1):
+        return Lin(lin.w[r0:r1], lin.b[r0:r1], lin.gw[r0:r1] if lin.gw is not None else None,
+                   lin.gb[r0:r1] if lin.gb is not None else None)
+
+    def _bert_layer(self, p):
+        return dict(qkv=self._qkv(p + ".attention.self"), o=self._lin(p + ".attention.output.dense.weight"),
+                    ln1=self._norm(p + ".attention.output.LayerNorm"),
+                    f1=self._lin(p + ".intermediate.dense.weight"), f2=self._lin(p + ".output.dense.weight"),
+                    ln2=self._norm(p + ".output.LayerNorm"))
+
+    def _cross_layer(self, p):
+        a = p + ".visual_attention"
+        return dict(qkv=self._qkv(a + ".att"), o=self._lin(a + ".output.dense.weight"),
+                    lno=self._norm(a + ".output.LayerNorm"),
+                    lf1=self._lin(p + ".lang_inter.dense.weight"), lf2=self._lin(p + ".lang_output.dense.weight"),
+                    lln=self._norm(p + ".lang_output.LayerNorm"),
+                    vf1=self._lin(p + ".visn_inter.dense.weight"), vf2=self._lin(p + ".visn_output.dense.weight"),
+                    vln=self._norm(p + ".visn_output.LayerNorm"))
+
+    def _decoder_layer(self, p):
+        sa = self._lin(p + ".self_attn.in_proj_weight", p + ".self_attn.in_proj_bias")
+        ca = self._lin(p + ".multihead_attn.in_proj_weight", p + ".multihead_attn.in_proj_bias")
+        return dict(sa_qk=self._rows(sa, 0, 2 * H), sa_v=self._rows(sa, 2 * H, 3 * H),
+                    sa_o=self._lin(p + ".self_attn.out_proj.weight"),
+                    ca_q=self._rows(ca, 0, H), ca_kv=self._rows(ca, H, 3 * H),
+                    ca_o=self._lin(p + ".multihead_attn.out_proj.weight"),
+                    l1=self._lin(p + ".linear1.weight"), l2=self._lin(p + ".linear2.weight"),
+                    n1=self._norm(p + ".norm1"), n2=self._norm(p + ".norm2"), n3=self._norm(p + ".norm3"))
+
+    def _head(self, p):
+        return dict(l0=self._lin(p + ".0.weight"), ln=self._norm(p + ".2"), l3=self._lin(p + ".3.weight"))
+
+    def _build_handles(self):
+        st = self.st
+        e = "lxrt_encoder.model.bert"
+        g = st.grad is not None
+        self.emb = dict(word=st.p(e + ".embeddings.word_embeddings.weight"),
+                        pos=st.p(e + ".embeddings.position_embeddings.weight"),
+                        type=st.p(e + ".embeddings.token_type_embeddings.weight"),
+                        ln=self._norm(e + ".embeddings.LayerNorm"),
+                        gword=st.g(e + ".embeddings.word_embeddings.weight") if g else None,
+                        gpos=st.g(e + ".embeddings.position_embeddings.weight") if g else None,
+                        gtype=st.g(e + ".embeddings.token_type_embeddings.weight") if g else None)
+        self.l_layers = [self._bert_layer("%s.encoder.layer.%d" % (e, i)) for i in range(self.nl)]
+        self.r_layers = [self._bert_layer("%s.encoder.r_layers.%d" % (e, i)) for i in range(self.nr)]
+        self.x_layer = self._cross_layer(e + ".encoder.cross_attn_layer.cross")
+        self.pooler = self._lin(e + ".pooler_dict.cross.dense2.weight")
+        self.logit_fc = self._head("logit_fc")
+        if self.task != "hgqa":
+            return
+        self.hgx_layer = self._cross_layer("hgq_encoder.cross_attn_layer.cross")
+        self.hg_pooler = self._lin("hgq_encoder.pooler_dict.cross.dense2.weight")
+        self.rel_q = self._hg_embed("relation_query_embed")
+        self.act_q = self._hg_embed("action_query_embed")
+        self.rel_dec = [self._decoder_layer("rel_decoder.layers.%d" % i) for i in range(self.nd)]
+        self.act_dec = [self._decoder_layer("action_decoder.layers.%d" % i) for i in range(self.nd)]
+        self.class_embed = self._head("class_embed")
+        self.action_embed = self._head("action_embed")
+        # hoisted memory K/V projection of all decoder layers: packed bf16 [n_dec*2*768, 768] + fp32 bias
+        n = 2 * self.nd
+        self.kv_w = torch.empty(n * 2 * H, H, device=self.dev, dtype=BF16)
+        self.kv_b = torch.empty(n * 2 * H, device=self.dev, dtype=torch.float32)
+        self.tok = torch.empty((self.n_act + self.n_rel + 1) * H, device=self.dev, dtype=BF16)
+
+    def _hg_embed(self, p):
+        st = self.st
+        g = st.grad is not None
+        return dict(word=st.p(p + ".word_embeddings.weight"), type=st.p(p + ".token_type_embeddings.weight"),
+                    ln=self._norm(p + ".LayerNorm"),
+                    gword=st.g(p + ".word_embeddings.weight") if g else None,
+                    gtype=st.g(p + ".token_type_embeddings.weight") if g else None)
+
+    def _dec_layers(self):
+        return self.rel_dec + self.act_dec
+
+    def refresh_derived(self):
+        """bf16 copies that are not plain shadows: the packed K/V weights of the 10 decoder layers and the
+        CrossEncoder's type / cls tokens.  Call after the weights change (load or optimiser step)."""
+        if self.task != "hgqa":
+            return
+        st = self.st
+        for i, name in enumerate(["rel_decoder.layers.%d" % j for j in range(self.nd)]
+                                 + ["action_decoder.layers.%d" % j for j in range(self.nd)]):
+            w = st.p(name + ".multihead_attn.in_proj_weight")
+            ops.to_bf16(w[H:], out=self.kv_w[i * 2 * H:(i + 1) * 2 * H])
+            self.kv_b[i * 2 * H:(i + 1) * 2 * H].copy_(st.p(name + ".multihead_attn.in_proj_bias")[H:])
+        # [act_token x n_act | rel_token x n_rel | cls_token]
+        for j in range(self.n_act):
+            ops.to_bf16(st.p("hgq_encoder.act_token").view(-1), out=self.tok[j * H:(j + 1) * H])
+        for j in range(self.n_rel):
+            o = (self.n_act + j) * H
+            ops.to_bf16(st.p("hgq_encoder.rel_token").view(-1), out=self.tok[o:o + H])
+        o = (self.n_act + self.n_rel) * H
+        ops.to_bf16(st.p("hgq_encoder.cls_token").view(-1), out=self.tok[o:o + H])
+
+    # ------------------------------------------------------------------ primitive fwd/bwd helpers
+    @staticmethod
+    def _wgrad(lin, dy, x, bias=True):
+        ops.gemm(dy, x, a_t=True, b_t=True, out=lin.gw, accumulate=True)
+        if bias:
+            ops.colsum_accum(dy, lin.gb)
+
+    def _ffn_fwd(self, f1, f2, ln, a, save, act="gelu", eps=EPS_BERT, addend=None):
+        pre = torch.empty(a.shape[0], f1.w.shape[0], device=self.dev, dtype=BF16) if (save and act == "gelu") else None
+        h = ops.gemm(a, f1.w, bias=f1.b, act=act, preact=pre)
+        s2 = ops.gemm(h, f2.w, bias=f2.b, residual=a)
+        y, y2, m, r = ops.layernorm_fwd(s2, ln.g, ln.b, eps, addend=addend, save_stats=save)
+        return y, y2, (a, pre, h, s2, m, r)
+
+    def _ffn_bwd(self, f1, f2, ln, saved, dy, dy2=None, act="gelu"):
+        a, pre, h, s2, m, r = saved
+        ds2 = ops.layernorm_bwd(dy, s2, ln.g, m, r, ln.gg, ln.gb, dy2=dy2, dxsum=f2.gb)
+        self._wgrad(f2, ds2, h, bias=False)
+        if act == "gelu":
+            dpre = ops.gemm(ds2, f2.w, b_t=True, mul_aux=pre, mul_mode="gelu_grad")
+        else:
+            dpre = ops.gemm(ds2, f2.w, b_t=True, mul_aux=h, mul_mode="relu_mask")
+        self._wgrad(f1, dpre, a)
+        return ops.gemm(dpre, f1.w, b_t=True, residual=ds2)      # d a  (FFN path + residual path)
+
+    # ------------------------------------------------------------------ BertLayer (L, R)
+    def _bert_fwd(self, L, x, B, n, key_mask, save):
+        qkv = ops.gemm(x, L["qkv"].w, bias=L["qkv"].b)
+        ctx, lse = ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, n, n, key_mask=key_mask,
+                                     save_lse=save)
+        s1 = ops.gemm(ctx, L["o"].w, bias=L["o"].b, residual=x)
+        a, _, m1, r1 = ops.layernorm_fwd(s1, L["ln1"].g, L["ln1"].b, EPS_BERT, save_stats=save)
+        y, _, ffn = self._ffn_fwd(L["f1"], L["f2"], L["ln2"], a, save)
+        return y, (x, qkv, ctx, lse, s1, m1, r1, ffn)
+
+    def _bert_bwd(self, L, saved, dy, B, n, key_mask, need_dx=True):
+        x, qkv, ctx, lse, s1, m1, r1, ffn = saved
+        da = self._ffn_bwd(L["f1"], L["f2"], L["ln2"], ffn, dy)
+        ds1 = ops.layernorm_bwd(da, s1, L["ln1"].g, m1, r1, L["ln1"].gg, L["ln1"].gb, dxsum=L["o"].gb)
+        self._wgrad(L["o"], ds1, ctx, bias=False)
+        dctx = ops.gemm(ds1, L["o"].w, b_t=True)
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, dctx, lse, dqkv[:, :H], dqkv[:, H:2 * H],
+                          dqkv[:, 2 * H:], B, n, n, key_mask=key_mask)
+        self._wgrad(L["qkv"], dqkv, x)
+        if not need_dx:
+            return None
+        return ops.gemm(dqkv, L["qkv"].w, b_t=True, residual=ds1)
+
+    # ------------------------------------------------------------------ CrossLayer (X, HG)
+    def _cross_fwd(self, X, lang, visn, B, nl, nv, lang_kmask, visn_kmask, save):
+        q = X["qkv"]
+        qkv_l = ops.gemm(lang, q.w, bias=q.b)
+        qkv_v = ops.gemm(visn, q.w, bias=q.b)
+        # one attention block, both directions (lxrt/modeling_capsbert.py:643-644)
+        ctx_l, lse_l = ops.attention_fwd(qkv_l[:, :H], qkv_v[:, H:2 * H], qkv_v[:, 2 * H:], B, nl, nv,
+                                         key_mask=visn_kmask, save_lse=save)
+        ctx_v, lse_v = ops.attention_fwd(qkv_v[:, :H], qkv_l[:, H:2 * H], qkv_l[:, 2 * H:], B, nv, nl,
+                                         key_mask=lang_kmask, save_lse=save)
+        s_l = ops.gemm(ctx_l, X["o"].w, bias=X["o"].b, residual=lang)
+        s_v = ops.gemm(ctx_v, X["o"].w, bias=X["o"].b, residual=visn)
+        a_l, _, ml, rl = ops.layernorm_fwd(s_l, X["lno"].g, X["lno"].b, EPS_BERT, save_stats=save)
+        a_v, _, mv, rv = ops.layernorm_fwd(s_v, X["lno"].g, X["lno"].b, EPS_BERT, save_stats=save)
+        y_l, _, ffn_l = self._ffn_fwd(X["lf1"], X["lf2"], X["lln"], a_l, save)
+        y_v, _, ffn_v = self._ffn_fwd(X["vf1"], X["vf2"], X["vln"], a_v, save)
+        return y_l, y_v, (lang, visn, qkv_l, qkv_v, ctx_l, lse_l, ctx_v, lse_v, s_l, ml, rl, s_v, mv, rv, ffn_l, ffn_v)
+
+    def _cross_bwd(self, X, saved, dy_l, dy_v, B, nl, nv, lang_kmask, visn_kmask):
+        lang, visn, qkv_l, qkv_v, ctx_l, lse_l, ctx_v, lse_v, s_l, ml, rl, s_v, mv, rv, ffn_l, ffn_v = saved
+        da_l = self._ffn_bwd(X["lf1"], X["lf2"], X["lln"], ffn_l, dy_l)
+        da_v = self._ffn_bwd(X["vf1"], X["vf2"], X["vln"], ffn_v, dy_v)
+        ds_l = ops.layernorm_bwd(da_l, s_l, X["lno"].g, ml, rl, X["lno"].gg, X["lno"].gb, dxsum=X["o"].gb)
+        ds_v = ops.layernorm_bwd(da_v, s_v, X["lno"].g, mv, rv, X["lno"].gg, X["lno"].gb, dxsum=X["o"].gb)
+        self._wgrad(X["o"], ds_l, ctx_l, bias=False)
+        self._wgrad(X["o"], ds_v, ctx_v, bias=False)
+        dctx_l = ops.gemm(ds_l, X["o"].w, b_t=True)
+        dctx_v = ops.gemm(ds_v, X["o"].w, b_t=True)
+        dqkv_l, dqkv_v = torch.empty_like(qkv_l), torch.empty_like(qkv_v)
+        ops.attention_bwd(qkv_l[:, :H], qkv_v[:, H:2 * H], qkv_v[:, 2 * H:], ctx_l, dctx_l, lse_l,
+                          dqkv_l[:, :H], dqkv_v[:, H:2 * H], dqkv_v[:, 2 * H:], B, nl, nv, key_mask=visn_kmask)
+        ops.attention_bwd(qkv_v[:, :H], qkv_l[:, H:2 * H], qkv_l[:, 2 * H:], ctx_v, dctx_v, lse_v,
+                          dqkv_v[:, :H], dqkv_l[:, H:2 * H], dqkv_l[:, 2 * H:], B, nv, nl, key_mask=lang_kmask)
+        self._wgrad(X["qkv"], dqkv_l, lang)
+        self._wgrad(X["qkv"], dqkv_v, visn)
+        d_lang = ops.gemm(dqkv_l, X["qkv"].w, b_t=True, residual=ds_l)
+        d_visn = ops.gemm(dqkv_v, X["qkv"].w, b_t=True, residual=ds_v)
+        return d_lang, d_visn
+
+    # ------------------------------------------------------------------ DETR decoder layer (D)
+    def _dec_fwd(self, D, tgt, tgt_p, qpos, k_mem, v_mem, B, nq, per, save, first):
+        qk = ops.gemm(tgt_p, D["sa_qk"].w, bias=D["sa_qk"].b)
+        v = ops.gemm(tgt, D["sa_v"].w, bias=D["sa_v"].b)
+        sa, lse1 = ops.attention_fwd(qk[:, :H], qk[:, H:], v, B, nq, nq, frames=(per, per), save_lse=save)
+        s1 = ops.gemm(sa, D["sa_o"].w, bias=D["sa_o"].b, residual=tgt)
+        t1, t1p, m1, r1 = ops.layernorm_fwd(s1, D["n1"].g, D["n1"].b, EPS_DETR, addend=qpos, save_stats=save)
+        cq = ops.gemm(t1p, D["ca_q"].w, bias=D["ca_q"].b)
+        ca, lse2 = ops.attention_fwd(cq, k_mem, v_mem, B, nq, 393, save_lse=save)
+        s2 = ops.gemm(ca, D["ca_o"].w, bias=D["ca_o"].b, residual=t1)
+        t2, _, m2, r2 = ops.layernorm_fwd(s2, D["n2"].g, D["n2"].b, EPS_DETR, save_stats=save)
+        t3, t3p, ffn = self._ffn_fwd(D["l1"], D["l2"], D["n3"], t2, save, act="relu", eps=EPS_DETR, addend=qpos)
+        return t3, t3p, (tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, ffn, first)
+
+    def _dec_bwd(self, D, saved, dt3, dt3p, dqpos, k_mem, v_mem, dk_mem, dv_mem, B, nq, per):
+        tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, ffn, first = saved
+        if dt3p is not None:
+            self._acc(dqpos, dt3p)
+        dt2 = self._ffn_bwd(D["l1"], D["l2"], D["n3"], ffn, dt3, dy2=dt3p, act="relu")
+        ds2 = ops.layernorm_bwd(dt2, s2, D["n2"].g, m2, r2, D["n2"].gg, D["n2"].gb, dxsum=D["ca_o"].gb)
+        self._wgrad(D["ca_o"], ds2, ca, bias=False)
+        dca = ops.gemm(ds2, D["ca_o"].w, b_t=True)
+        dcq = torch.empty_like(cq)
+        ops.attention_bwd(cq, k_mem, v_mem, ca, dca, lse2, dcq, dk_mem, dv_mem, B, nq, 393)
+        self._wgrad(D["ca_q"], dcq, t1p)
+        dt1p = ops.gemm(dcq, D["ca_q"].w, b_t=True)
+        self._acc(dqpos, dt1p)
+        ds1 = ops.layernorm_bwd(ds2, s1, D["n1"].g, m1, r1, D["n1"].gg, D["n1"].gb, dy2=dt1p, dxsum=D["sa_o"].gb)
+        self._wgrad(D["sa_o"], ds1, sa, bias=False)
+        dsa = ops.gemm(ds1, D["sa_o"].w, b_t=True)
+        dqk, dv = torch.empty_like(qk), torch.empty_like(v)
+        ops.attention_bwd(qk[:, :H], qk[:, H:], v, sa, dsa, lse1, dqk[:, :H], dqk[:, H:], dv, B, nq, nq,
+                          frames=(per, per))
+        self._wgrad(D["sa_qk"], dqk, tgt_p)
+        dtgt_p = ops.gemm(dqk, D["sa_qk"].w, b_t=True)
+        if first:
+            # tgt is the constant zero tensor (tasks/agqa_model.py:235): only the bias of the value projection learns
+            ops.colsum_accum(dv, D["sa_v"].gb)
+            self._acc(dqpos, dtgt_p)
+            return None, None
+        self._wgrad(D["sa_v"], dv, tgt)
+        dtgt = ops.gemm(dv, D["sa_v"].w, b_t=True, residual=ds1)
+        return dtgt, dtgt_p
+
+    @staticmethod
+    def _acc(dst, src):
+        ops.copy3d(src, dst, 1, 1, src.numel(), 0, 0, 0, 0, accumulate=True)
+
+    def _decoder_fwd(self, layers, qpos, kv_mem, layer0, B, nq, per, save):
+        tgt = torch.zeros_like(qpos)
+        tgt_p = qpos
+        saved = []
+        for i, D in enumerate(layers):
+            c = (layer0 + i) * 2 * H
+            tgt, tgt_p, s = self._dec_fwd(D, tgt, tgt_p, qpos, kv_mem[:, c:c + H], kv_mem[:, c + H:c + 2 * H], B, nq,
+                                          per, save, first=(i == 0))
+            saved.append(s)
+        return tgt, saved
+
+    def _decoder_bwd(self, layers, saved, d_out, kv_mem, dkv_mem, layer0, B, nq, per):
+        dqpos = torch.zeros_like(d_out)
+        dt3, dt3p = d_out, None
+        for i in reversed(range(len(layers))):
+            c = (layer0 + i) * 2 * H
+            dt3, dt3p = self._dec_bwd(layers[i], saved[i], dt3, dt3p, dqpos, kv_mem[:, c:c + H],
+                                      kv_mem[:, c + H:c + 2 * H], dkv_mem[:, c:c + H], dkv_mem[:, c + H:c + 2 * H],
+                                      B, nq, per)
+        return dqpos
+
+    # ------------------------------------------------------------------ heads, poolers, embeddings
+    def _head_fwd(self, Hd, x, save):
+        pre = torch.empty(x.shape[0], 2 * H, device=self.dev, dtype=BF16) if save else None
+        h1 = ops.gemm(x, Hd["l0"].w, bias=Hd["l0"].b, act="gelu", preact=pre)
+        n, _, m, r = ops.layernorm_fwd(h1, Hd["ln"].g, Hd["ln"].b, EPS_BERT, save_stats=save)
+        c = Hd["l3"].w.shape[0]
+        ld = (c + 3) // 4 * 4
+        logits = torch.empty(x.shape[0], ld, device=self.dev, dtype=torch.float32)[:, :c]
+        ops.gemm(n, Hd["l3"].w, bias=Hd["l3"].b, out=logits)
+        return logits, (x, pre, h1, m, r, n)
+
+    def _head_bwd(self, Hd, saved, dlogits, need_dx=True):
+        x, pre, h1, m, r, n = saved
+        self._wgrad(Hd["l3"], dlogits, n)
+        dn = ops.gemm(dlogits, Hd["l3"].w, b_t=True)
+        dh1 = ops.layernorm_bwd(dn, h1, Hd["ln"].g, m, r, Hd["ln"].gg, Hd["ln"].gb)
+        dpre = ops.act_bwd(dh1, pre, "gelu")
+        self._wgrad(Hd["l0"], dpre, x)
+        return ops.gemm(dpre, Hd["l0"].w, b_t=True) if need_dx else None
+
+    def _pool_fwd(self, P, first, n_first, second, n_second, B):
+        """BertPooler2 (lxrt/modeling_capsbert.py:1525-1533): tanh(W [first[:,0] ; second[:,0]] + b)."""
+        cat = torch.empty(B, 2 * H, device=self.dev, dtype=BF16)
+        ops.copy3d(first, cat, B, 1, H, n_first * H, 0, 2 * H, 0)
+        ops.copy3d(second, cat[:, H:], B, 1, H, n_second * H, 0, 2 * H, 0)
+        pooled = ops.gemm(cat, P.w, bias=P.b, act="tanh")
+        return pooled, (cat, pooled)
+
+    def _pool_bwd(self, P, saved, dpooled, d_first, n_first, d_second, n_second, B):
+        cat, pooled = saved
+        dz = ops.act_bwd(dpooled, pooled, "tanh")
+        self._wgrad(P, dz, cat)
+        dcat = ops.gemm(dz, P.w, b_t=True)
+        ops.copy3d(dcat, d_first, B, 1, H, 2 * H, 0, n_first * H, 0, accumulate=True)
+        ops.copy3d(dcat[:, H:], d_second, B, 1, H, 2 * H, 0, n_second * H, 0, accumulate=True)
+
+    def _hg_embed_fwd(self, E, seg_ids, B, nq, save):
+        rows = B * nq
+        y = torch.empty(rows, H, device=self.dev, dtype=BF16)
+        pre = torch.empty_like(y) if save else None
+        mean = torch.empty(rows, device=self.dev, dtype=torch.float32) if save else None
+        rstd = torch.empty_like(mean) if save else None
+        ops.call("shg_embed_ln_fwd", ops.ptr(E["word"]), None, None, ops.ptr(E["type"]), ops.ptr(seg_ids),
+                 ops.ptr(E["ln"].g), ops.ptr(E["ln"].b), EPS_BERT, ops.ptr(y), ops.ptr(pre), ops.ptr(mean),
+                 ops.ptr(rstd), rows, nq, H, ops.stream())
+        return y, (seg_ids, pre, mean, rstd)
+
+    def _hg_embed_bwd(self, E, saved, dq, B, nq):
+        seg_ids, pre, mean, rstd = saved
+        de = ops.layernorm_bwd(dq, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
+        # word table is used whole (no lookup → no padding mask); frame-id table is nn.Embedding(padding_idx=0)
+        ops.call("shg_embed_scatter_bwd", ops.ptr(de), None, ops.ptr(seg_ids), ops.ptr(E["gword"]), -1, None, -1,
+                 ops.ptr(E["gtype"]), 0, B * nq, nq, H, ops.stream())
+
+    # ------------------------------------------------------------------ whole path
+    def forward(self, inp, train=False):
+        """inp (device tensors): visn_tokens bf16 [B*393,768] (output of the stock Conv3d front-end + cls + pos),
+        input_ids/input_mask/segment_ids int64 [B,40], rel_segment_ids [B,128], act_segment_ids [B,48]."""
+        save = train
+        B = inp["input_ids"].shape[0]
+        ctx = dict(B=B)
+        ids, seg = inp["input_ids"].reshape(-1), inp["segment_ids"].reshape(-1)
+        nl = inp["input_ids"].shape[1]
+        lang = torch.empty(B * nl, H, device=self.dev, dtype=BF16)
+        pre = torch.empty_like(lang) if save else None
+        mean = torch.empty(B * nl, device=self.dev, dtype=torch.float32) if save else None
+        rstd = torch.empty_like(mean) if save else None
+        E = self.emb
+        ops.call("shg_embed_ln_fwd", ops.ptr(E["word"]), ops.ptr(ids), ops.ptr(E["pos"]), ops.ptr(E["type"]),
+                 ops.ptr(seg), ops.ptr(E["ln"].g), ops.ptr(E["ln"].b), EPS_BERT, ops.ptr(lang), ops.ptr(pre),
+                 ops.ptr(mean), ops.ptr(rstd), B * nl, nl, H, ops.stream())
+        ctx["emb"] = (ids, seg, pre, mean, rstd, nl)
+        # additive key mask (1-mask)*-10000 (lxrt/modeling_capsbert.py:1826-1834); the visual mask is all zeros (:1836)
+        kmask = ((1.0 - inp["input_mask"].to(torch.float32)) * -10000.0).contiguous()
+        ctx["kmask"] = kmask
+        ctx["L"] = []
+        for L in self.l_layers:
+            lang, s = self._bert_fwd(L, lang, B, nl, kmask, save)
+            ctx["L"].append(s)
+        lang_l = lang
+        visn = inp["visn_tokens"]
+        nv = visn.shape[0] // B
+        ctx["R"] = []
+        for L in self.r_layers:
+            visn, s = self._bert_fwd(L, visn, B, nv, None, save)
+            ctx["R"].append(s)
+        visn_r = visn
+        ctx["visn_r"] = visn_r
+        out = dict(lang_l=lang_l, visn_r=visn_r, kmask=kmask)
+        if inp.get("skip_x", False) is False:
+            xl, xv = lang_l, visn_r
+            for _ in range(self.nx):                 # the same module twice (lxrt/modeling_capsbert.py:1247-1249)
+                xl, xv, _ = self._cross_fwd(self.x_layer, xl, xv, B, nl, nv, kmask, None, False)
+            pooled, _ = self._pool_fwd(self.pooler, xv, nv, xl, nl, B)
+            out["logit"], _ = self._head_fwd(self.logit_fc, pooled, False)
+            out["lang"], out["visn"], out["pooled"] = xl, xv, pooled
+        if self.task != "hgqa":
+            return out, ctx
+        # decoders over the relation-layer memory (tasks/agqa_model.py:218-249)
+        kv_mem = ops.gemm(visn_r, self.kv_w, bias=self.kv_b)
+        ctx["kv_mem"] = kv_mem
+        nq_r, nq_a = self.T * self.n_rel, self.T * self.n_act
+        rel_q, ctx["rel_q"] = self._hg_embed_fwd(self.rel_q, inp["rel_segment_ids"].reshape(-1), B, nq_r, save)
+        rel_out, ctx["rel_dec"] = self._decoder_fwd(self.rel_dec, rel_q, kv_mem, 0, B, nq_r, self.n_rel, save)
+        act_q, ctx["act_q"] = self._hg_embed_fwd(self.act_q, inp["act_segment_ids"].reshape(-1), B, nq_a, save)
+        act_out, ctx["act_dec"] = self._decoder_fwd(self.act_dec, act_q, kv_mem, self.nd, B, nq_a, self.n_act, save)
+        out["rel_logits"], ctx["rel_head"] = self._head_fwd(self.class_embed, rel_out, save)
+        out["act_logits"], ctx["act_head"] = self._head_fwd(self.action_embed, act_out, save)
+        out["rel_out"], out["act_out"] = rel_out, act_out
+        # hypergraph tokens: [cls | per frame: actions + act_token, relations + rel_token]
+        per = self.n_act + self.n_rel
+        ng = self.T * per + 1
+        hg = torch.empty(B * ng, H, device=self.dev, dtype=BF16)
+        tok = self.tok
+        ops.copy3d(tok[per * H:], hg, B, 1, H, 0, 0, ng * H, 0)
+        ops.copy3d(act_out, hg[1:], B, self.T, self.n_act * H, nq_a * H, self.n_act * H, ng * H, per * H,
+                   add=tok[:self.n_act * H])
+        ops.copy3d(rel_out, hg[1 + self.n_act:], B, self.T, self.n_rel * H, nq_r * H, self.n_rel * H, ng * H, per * H,
+                   add=tok[self.n_act * H:per * H])
+        hg_kmask = None
+        if inp.get("hg_key_mask") is not None:     # --useHGMask (tasks/agqa_model.py:261-264); [B, 177] additive
+            hg_kmask = inp["hg_key_mask"]
+        ctx["hg_kmask"] = hg_kmask
+        xl, xg = lang_l, hg
+        ctx["HGX"] = []
+        for _ in range(self.nx):
+            xl, xg, s = self._cross_fwd(self.hgx_layer, xl, xg, B, nl, ng, kmask, hg_kmask, save)
+            ctx["HGX"].append(s)
+        hg_pooled, ctx["hg_pool"] = self._pool_fwd(self.hg_pooler, xg, ng, xl, nl, B)
+        out["hg_logit"], ctx["hg_head"] = self._head_fwd(self.logit_fc, hg_pooled, save)
+        out["hg_pooled"] = hg_pooled
+        ctx["dims"] = (nl, nv, ng, nq_r, nq_a)
+        return out, ctx
+
+    def backward(self, ctx, d_hg_logit, d_rel_logits, d_act_logits, need_dvisn=False):
+        """Gradients of the --taskHGQA loss (hg answer loss + relation CE + action CE, tasks/agqaHGQA.py:344-378)
+        accumulated into the flat gradient buffer.  d_* are bf16 [rows, n_cls] views with ld % 8 == 0."""
+        B = ctx["B"]
+        nl, nv, ng, nq_r, nq_a = ctx["dims"]
+        kmask = ctx["kmask"]
+        per = self.n_act + self.n_rel
+        # answer head → pooler → CrossEncoder
+        d_pool = self._head_bwd(self.logit_fc, ctx["hg_head"], d_hg_logit)
+        d_xg = torch.zeros(B * ng, H, device=self.dev, dtype=BF16)
+        d_xl = torch.zeros(B * nl, H, device=self.dev, dtype=BF16)
+        self._pool_bwd(self.hg_pooler, ctx["hg_pool"], d_pool, d_xg, ng, d_xl, nl, B)
+        for s in reversed(ctx["HGX"]):
+            d_xl, d_xg = self._cross_bwd(self.hgx_layer, s, d_xl, d_xg, B, nl, ng, kmask, ctx["hg_kmask"])
+        d_lang_l = d_xl
+        # hypergraph assembly backward: cls / type-token gradients and the decoder-output gradients
+        st = self.st
+        ops.colsum_accum(d_xg.view(B, ng * H)[:, :H], st.g("hgq_encoder.cls_token").view(-1))
+        d_act_hg = torch.empty(B * nq_a, H, device=self.dev, dtype=BF16)
+        d_rel_hg = torch.empty(B * nq_r, H, device=self.dev, dtype=BF16)
+        ops.copy3d(d_xg[1:], d_act_hg, B, self.T, self.n_act * H, ng * H, per * H, nq_a * H, self.n_act * H)
+        ops.copy3d(d_xg[1 + self.n_act:], d_rel_hg, B, self.T, self.n_rel * H, ng * H, per * H, nq_r * H,
+                   self.n_rel * H)
+        ops.colsum_accum(d_act_hg, st.g("hgq_encoder.act_token").view(-1))
+        ops.colsum_accum(d_rel_hg, st.g("hgq_encoder.rel_token").view(-1))
+        # classifier heads add their share to the decoder outputs
+        d_rel_out = self._head_bwd(self.class_embed, ctx["rel_head"], d_rel_logits)
+        d_act_out = self._head_bwd(self.action_embed, ctx["act_head"], d_act_logits)
+        self._acc(d_rel_out, d_rel_hg)
+        self._acc(d_act_out, d_act_hg)
+        kv_mem = ctx["kv_mem"]
+        dkv_mem = torch.empty_like(kv_mem)
+        dq_r = self._decoder_bwd(self.rel_dec, ctx["rel_dec"], d_rel_out, kv_mem, dkv_mem, 0, B, nq_r, self.n_rel)
+        dq_a = self._decoder_bwd(self.act_dec, ctx["act_dec"], d_act_out, kv_mem, dkv_mem, self.nd, B, nq_a,
+                                 self.n_act)
+        self._hg_embed_bwd(self.rel_q, ctx["rel_q"], dq_r, B, nq_r)
+        self._hg_embed_bwd(self.act_q, ctx["act_q"], dq_a, B, nq_a)
+        # hoisted K/V projection backward: one dgrad over all 10 layers, one wgrad per layer
+        mem = ctx["visn_r"]
+        d_mem = ops.gemm(dkv_mem, self.kv_w, b_t=True)
+        for i, D in enumerate(self._dec_layers()):
+            c = i * 2 * H
+            self._wgrad(D["ca_kv"], dkv_mem[:, c:c + 2 * H], mem)
+        # relation layers
+        d_visn = d_mem
+        for i in reversed(range(self.nr)):
+            d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None,
+                                    need_dx=(i > 0 or need_dvisn))
+        # language layers → embeddings
+        d_lang = d_lang_l
+        for i in reversed(range(self.nl)):
+            d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
+        ids, seg, pre, mean, rstd, _ = ctx["emb"]
+        E = self.emb
+        de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
+        ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
+                 ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
+        return d_visn

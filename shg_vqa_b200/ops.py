@@ -21,7 +21,7 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, preact=None, mul_aux=None,
-         mul_mode=None, out=None, out_f32=False, accumulate=False, splits=1, block_n=0):
+         mul_mode=None, out=None, out_f32=False, accumulate=False, splits=0, block_n=0):
     """D = epilogue(A . B^T).  a: [M,K] (or stored [K,M] with a_t), b: [N,K] (or stored [K,N] with b_t); bf16."""
     require_device(a)
     assert a.dtype == BF16 and b.dtype == BF16
@@ -132,6 +132,25 @@ def add_rows(x, add):
     y = torch.empty_like(x)
     call("shg_add_rows", ptr(x), ptr(add), add.shape[0], ptr(y), rows, n, stream())
     return y
+
+
+def act_bwd(dy, aux, act):
+    require_device(dy)
+    dx = torch.empty_like(dy)
+    call("shg_act_bwd", ptr(dy), ptr(aux), ptr(dx), dy.numel(), ACT[act], stream())
+    return dx
+
+
+def bce_logits(x, target, out, grad_scale=1.0, want_grad=True):
+    """x fp32 [rows, cols] (row stride = ld). Adds the loss into out[0]; returns d loss/dx as bf16 (ld % 8 == 0)."""
+    require_device(x)
+    rows, cols = x.shape
+    dx = None
+    ld = (cols + 7) // 8 * 8
+    if want_grad:
+        dx = torch.zeros(rows, ld, device=x.device, dtype=BF16)[:, :cols]
+    call("shg_bce_logits", ptr(x), _ld(x), ptr(target), rows, cols, grad_scale, ptr(out), ptr(dx), ld, stream())
+    return dx
 
 
 def copy3d(src, dst, n0, n1, chunk, s0, s1, d0, d1, add=None, accumulate=False):

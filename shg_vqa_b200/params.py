@@ -159,34 +159,54 @@ def _is_matrix(key, shape):
 class ParamStore:
     """Flat fp32 master / fp32 grad / bf16 shadow buffers with named views."""
 
-    def __init__(self, key_shapes, device, with_grad=True):
+    def __init__(self, key_shapes, device, with_grad=True, live=None):
+        """live: key -> bool, "receives a gradient in training" (None: everything).  The flat order is
+        [frozen matrices | live matrices | live vectors+tables | frozen rest], so the live range — what the
+        all-reduce and the optimiser walk — is ONE contiguous span and the bf16 shadow is the leading span."""
         self.key_shapes = key_shapes
         self.device = torch.device(device)
         canon = collections.OrderedDict()
         for k, (shape, dtype) in key_shapes.items():
             if dtype == "float32":
                 canon.setdefault(canonical_key(k), tuple(shape))
-        # flat order: matrices first (q,k,v already adjacent in key order is NOT true — biases interleave —
-        # so matrices and vectors are laid out in two separate passes, which makes q|k|v contiguous in both)
+        is_live = (lambda k: True) if live is None else live
         mats = [k for k, s in canon.items() if _is_matrix(k, s)]
         rest = [k for k, s in canon.items() if not _is_matrix(k, s)]
+        # q|k|v weights (and biases) stay adjacent inside each group: key order is preserved within a group
+        order = ([k for k in mats if not is_live(k)] + [k for k in mats if is_live(k)]
+                 + [k for k in rest if is_live(k)] + [k for k in rest if not is_live(k)])
         self.offsets = {}
+        self.live_keys = [k for k in order if is_live(k)]
         off = 0
-        for k in mats + rest:
+        self.live_begin = self.live_end = None
+        n_mats = len(mats)
+        for idx, k in enumerate(order):
+            if idx == n_mats:
+                self.n_matrix = off
+            if is_live(k) and self.live_begin is None:
+                self.live_begin = off
             n = 1
             for d in canon[k]:
                 n *= d
             self.offsets[k] = (off, n, canon[k])
             off += (n + 7) // 8 * 8          # 32-byte aligned fp32 / 16-byte aligned bf16 views
-            if k == mats[-1]:
-                self.n_matrix = off
+            if is_live(k):
+                self.live_end = off
+        if n_mats == len(order):
+            self.n_matrix = off
         self.n_total = off
+        self.n_live = self.live_end - self.live_begin
+        self.live_extent = slice(self.live_begin, self.live_end)
         self.master = torch.zeros(self.n_total, device=self.device, dtype=torch.float32)
         self.grad = torch.zeros(self.n_total, device=self.device, dtype=torch.float32) if with_grad else None
         self.shadow = torch.zeros(self.n_matrix, device=self.device, dtype=torch.bfloat16) \
             if self.device.type == "cuda" else None
         self.int_buffers = {k: torch.arange(s[-1], device=self.device).expand(s).clone()
                             for k, (s, d) in key_shapes.items() if d == "int64"}
+        # optimiser segment table (one contiguous live span)
+        self.n_seg = 1
+        self.seg_start = torch.tensor([self.live_begin], dtype=torch.int64, device=self.device)
+        self.seg_prefix = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._shadow_fresh = False
 
     # ------------------------------------------------------------------ views
