@@ -89,7 +89,9 @@ class HotPathTrainer:
 
     # ------------------------------------------------------------------ loss on device
     def loss_and_grads(self, out, batch, want_grad=True):
-        """batch: target fp32 [B, n_ans]; rel_labels/rel_off, act_labels/act_off int32 CSR.
+        """batch: target fp32 [B, n_ans]; rel_labels/rel_off, act_labels/act_off int32 CSR.  Optional
+        rel_target_classes / act_target_classes (int32 [B*Q]) replace the matcher's scatter — used by the parity
+        tests to hold the reference's assignment fixed.
         Returns (scalars tensor view, d_hg_logit, d_rel_logits, d_act_logits, match dicts).
         scal[0]=qa loss, [1..4]=rel sums (w*nll, w, matched, correct), [5..8]=act sums."""
         scal = self.scal
@@ -100,6 +102,8 @@ class HotPathTrainer:
         for fam, q_f, o in (("rel", self.engine.n_rel, 1), ("act", self.engine.n_act, 5)):
             lg = out[fam + "_logits"]
             m = ops.match_from_logits(lg, batch[fam + "_labels"], batch[fam + "_off"], q_f)
+            if batch.get(fam + "_target_classes") is not None:
+                m = dict(m, target_classes=batch[fam + "_target_classes"])
             ops.set_loss_fwd(lg, m, self.eos, out=scal[o:o + 4])
             res.append(ops.set_loss_bwd(lg, m, self.eos, scal[o:o + 4], 1.0) if want_grad else None)
             matches.append(m)
