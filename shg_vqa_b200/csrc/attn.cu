@@ -239,6 +239,10 @@ __global__ void __launch_bounds__(kBwdThreads)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
                    const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
                    const AttnBwdParams p) {
+    // Two sweeps over the key chunks.  Sweep 1 only accumulates, per query row, sum(p) and sum(p * dP) in fp32 and
+    // forms delta = sum(p dP) / sum(p) from the SAME p and dP that build dS in sweep 2.  The textbook
+    // delta = rowsum(dO o O) reads the bf16-rounded O; when the value rows of a head are nearly identical (the
+    // decoder states of this model are) dP - delta cancels to ~1e-3 of dP and that rounding dominates dQ/dK.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                       // 16 KB
@@ -246,18 +250,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     uint8_t* sK = smem + 32768;               // 2 x 16 KB
     uint8_t* sV = smem + 65536;               // 2 x 16 KB
     uint8_t* sdS = smem + 98304;              // 2 x 32 KB
-    float* s_lse = reinterpret_cast<float*>(smem + 163840);
-    float* s_delta = s_lse + 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 128);
+    float* s_part = reinterpret_cast<float*>(smem + 163840);   // [2 halves][128 rows][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 512);
     uint64_t* bar_q = bars;          // Q + dO landed
     uint64_t* bar_kv = bars + 1;     // [2]
     uint64_t* bar_s = bars + 3;      // S and dP of the current chunk complete
-    uint64_t* bar_dq = bars + 4;     // [2] dQ product of chunk j retired (frees sdS[j&1], sK/sV[j&1])
+    uint64_t* bar_dq = bars + 4;     // [2] dQ product retired (frees its dS tile and K/V buffer)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_kc = (p.lk + 127) / 128;
+    const int n_it = 2 * n_kc;
 
     if (tid == 0) {
         mbar_init(bar_q, 1);
@@ -267,28 +271,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
-    // delta = rowsum(dO o O), straight from HBM (128 B per row per tensor)
-    if (tid < 128) {
-        const int q = q0 + tid;
-        float d = 0.f, l = INFINITY;
-        if (q < p.lq) {
-            const uint4* po = reinterpret_cast<const uint4*>(p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim);
-            const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)b * p.lq + q) * p.lddo + h * kHeadDim);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint4 a = __ldg(po + i), g = __ldg(pd + i);
-                float2 x, y;
-                x = unpack_bf16x2(a.x), y = unpack_bf16x2(g.x), d += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.y), y = unpack_bf16x2(g.y), d += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.z), y = unpack_bf16x2(g.z), d += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.w), y = unpack_bf16x2(g.w), d += x.x * y.x + x.y * y.y;
-            }
-            l = p.lse[((size_t)b * p.heads + h) * p.lq + q];
-            p.delta[((size_t)b * p.heads + h) * p.lq + q] = d;
-        }
-        s_delta[tid] = d;
-        s_lse[tid] = l * kLog2e;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -297,9 +279,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
 
-    auto issue_s = [&](int j) {   // S = Q K_j^T ; dP = dO V_j^T
+    auto issue_s = [&](int jj) {   // S = Q K_j^T ; dP = dO V_j^T   (operands of iteration jj sit in buffer jj & 1)
         const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
-        const uint32_t bk = smem_u32(sK + (j & 1) * 16384), bv = smem_u32(sV + (j & 1) * 16384);
+        const uint32_t bk = smem_u32(sK + (jj & 1) * 16384), bv = smem_u32(sV + (jj & 1) * 16384);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
             umma_bf16(t_s, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(bk + ks * 32, 16, 1024), idesc_s, ks > 0);
@@ -308,10 +290,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             umma_bf16(t_dp, make_smem_desc(ado + ks * 32, 16, 1024), make_smem_desc(bv + ks * 32, 16, 1024), idesc_s, ks > 0);
         tc_commit(bar_s);
     };
-    auto load_kv = [&](int j) {
-        mbar_expect_tx(bar_kv + (j & 1), 32768);
-        tma_load_3d(sK + (j & 1) * 16384, &tma_k, bar_kv + (j & 1), h * kHeadDim, j * 128, b);
-        tma_load_3d(sV + (j & 1) * 16384, &tma_v, bar_kv + (j & 1), h * kHeadDim, j * 128, b);
+    auto load_kv = [&](int jj) {
+        const int j = jj < n_kc ? jj : jj - n_kc;
+        mbar_expect_tx(bar_kv + (jj & 1), 32768);
+        tma_load_3d(sK + (jj & 1) * 16384, &tma_k, bar_kv + (jj & 1), h * kHeadDim, j * 128, b);
+        tma_load_3d(sV + (jj & 1) * 16384, &tma_v, bar_kv + (jj & 1), h * kHeadDim, j * 128, b);
     };
 
     if (tid == 0) {
@@ -319,7 +302,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         tma_load_3d(sQ, &tma_q, bar_q, h * kHeadDim, q0, b);
         tma_load_3d(sdO, &tma_do, bar_q, h * kHeadDim, q0, b);
         load_kv(0);
-        if (n_kc > 1) load_kv(1);
+        load_kv(1);
         mbar_wait(bar_q, 0);
         mbar_wait(bar_kv, 0);
         tc_fence_after();
@@ -333,13 +316,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const float* kmask = p.mask_mode == 1 ? p.key_mask + (size_t)b * p.lk : nullptr;
     const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
     const float c1 = p.scale * kLog2e;
-    const float my_lse = s_lse[row], my_delta = s_delta[row];
+    const float my_lse = q < p.lq ? p.lse[((size_t)b * p.heads + h) * p.lq + q] * kLog2e : INFINITY;
+    float acc_p = 0.f, acc_pd = 0.f, my_delta = 0.f;
 
-    for (int j = 0; j < n_kc; ++j) {
-        mbar_wait(bar_s, j & 1);
+    for (int jj = 0; jj < n_it; ++jj) {
+        const bool sweep2 = jj >= n_kc;
+        const int j = sweep2 ? jj - n_kc : jj;      // key chunk
+        const int j2 = jj - n_kc;                   // index within sweep 2
+        mbar_wait(bar_s, jj & 1);
         tc_fence_after();
-        if (j >= 2) mbar_wait(bar_dq + (j & 1), ((j - 2) >> 1) & 1);   // sdS[j&1] free again
-        uint8_t* tile = sdS + (j & 1) * 32768;
+        if (sweep2 && j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
+        uint8_t* tile = sdS + (j2 & 1) * 32768;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const int c = half * 64 + cc * 32;
@@ -354,34 +341,53 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 float x = __uint_as_float(rs[i]) * c1 - my_lse;
                 if (kmask && key < p.lk) x += __ldg(kmask + key) * kLog2e;
                 const float pr = key < k_lim ? exp2f(x) : 0.f;
-                ds[i] = pr * (__uint_as_float(rp[i]) - my_delta) * p.scale;
+                const float dp = __uint_as_float(rp[i]);
+                if (!sweep2) {
+                    acc_p += pr;
+                    acc_pd += pr * dp;
+                } else {
+                    ds[i] = pr * (dp - my_delta) * p.scale;
+                }
             }
-            store_tile_chunk32(tile, row, c, ds);
+            if (sweep2) store_tile_chunk32(tile, row, c, ds);
         }
-        fence_proxy_async_smem();
+        if (sweep2) fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (jj == n_kc - 1) {
+            // end of sweep 1: combine the two half-row partials
+            s_part[(half * 128 + row) * 2] = acc_p;
+            s_part[(half * 128 + row) * 2 + 1] = acc_pd;
+            __syncthreads();
+            const float z = s_part[row * 2] + s_part[(128 + row) * 2];
+            const float pd = s_part[row * 2 + 1] + s_part[(128 + row) * 2 + 1];
+            my_delta = z > 0.f ? pd / z : 0.f;
+            if (half == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
+        }
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t a = smem_u32(tile), bk = smem_u32(sK + (j & 1) * 16384);
+            if (sweep2) {
+                const uint32_t a = smem_u32(tile), bk = smem_u32(sK + (jj & 1) * 16384);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(t_dq, tile_a_desc(a, ks), rows_b_desc(bk, ks), idesc_dq, (j > 0 || ks > 0) ? 1u : 0u);
-            tc_commit(bar_dq + (j & 1));
-            if (j + 1 < n_kc) {
-                mbar_wait(bar_kv + ((j + 1) & 1), ((j + 1) >> 1) & 1);
-                tc_fence_after();
-                issue_s(j + 1);
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(t_dq, tile_a_desc(a, ks), rows_b_desc(bk, ks), idesc_dq, (j2 > 0 || ks > 0) ? 1u : 0u);
+                tc_commit(bar_dq + (j2 & 1));
             }
-            if (j + 2 < n_kc) {
-                mbar_wait(bar_dq + (j & 1), (j >> 1) & 1);
-                load_kv(j + 2);
+            if (jj + 1 < n_it) {
+                mbar_wait(bar_kv + ((jj + 1) & 1), ((jj + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_s(jj + 1);
+            }
+            if (jj + 2 < n_it) {
+                // buffer jj & 1 is free once its last reader retired: the S/dP products in sweep 1 (bar_s already
+                // observed), the dQ product in sweep 2
+                if (sweep2) mbar_wait(bar_dq + (j2 & 1), (j2 >> 1) & 1);
+                load_kv(jj + 2);
             }
         }
         __syncwarp();
     }
     mbar_wait(bar_dq + ((n_kc - 1) & 1), ((n_kc - 1) >> 1) & 1);
-    if (n_kc > 1) mbar_wait(bar_dq + ((n_kc - 2) & 1), ((n_kc - 2) >> 1) & 1);
     tc_fence_after();
     {
         uint32_t raw[32];
@@ -649,7 +655,7 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     const CUtensorMap* tk = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, 128);
     const CUtensorMap* tv = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, 128);
     if (!tq || !tdo || !tk || !tv) return SHG_ECUDA;
-    const size_t smem = 163840 + 2048 + 128 + 1024;
+    const size_t smem = 163840 + 2048 + 128 + 1024;   // tiles + per-row vectors + barriers + alignment slack
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

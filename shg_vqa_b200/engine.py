@@ -283,6 +283,8 @@ class Engine:
         ops.attention_bwd(cq, k_mem, v_mem, ca, dca, lse2, dcq, dk_mem, dv_mem, B, nq, 393)
         self._wgrad(D["ca_q"], dcq, t1p)
         dt1p = ops.gemm(dcq, D["ca_q"].w, b_t=True)
+        if getattr(self, "_trace", None) is not None:
+            self._trace.append(("dt1p", dt1p.float().cpu(), dcq.float().cpu()))
         self._acc(dqpos, dt1p)
         ds1 = ops.layernorm_bwd(ds2, s1, D["n1"].g, m1, r1, D["n1"].gg, D["n1"].gb, dy2=dt1p, dxsum=D["sa_o"].gb)
         self._wgrad(D["sa_o"], ds1, sa, bias=False)
@@ -290,8 +292,13 @@ class Engine:
         dqk, dv = torch.empty_like(qk), torch.empty_like(v)
         ops.attention_bwd(qk[:, :H], qk[:, H:], v, sa, dsa, lse1, dqk[:, :H], dqk[:, H:], dv, B, nq, nq,
                           frames=(per, per))
+        if getattr(self, "_trace", None) is not None:
+            self._trace_self = getattr(self, "_trace_self", [])
+            self._trace_self.append(tuple(t.float().cpu() for t in (qk, v, dsa, dqk, dv, sa)))
         self._wgrad(D["sa_qk"], dqk, tgt_p)
         dtgt_p = ops.gemm(dqk, D["sa_qk"].w, b_t=True)
+        if getattr(self, "_trace", None) is not None:
+            self._trace.append(("dtgt_p", dtgt_p.float().cpu(), dqk.float().cpu()))
         if first:
             # tgt is the constant zero tensor (tasks/agqa_model.py:235): only the bias of the value projection learns
             ops.colsum_accum(dv, D["sa_v"].gb)
@@ -495,6 +502,7 @@ class Engine:
         dq_r = self._decoder_bwd(self.rel_dec, ctx["rel_dec"], d_rel_out, kv_mem, dkv_mem, 0, B, nq_r, self.n_rel)
         dq_a = self._decoder_bwd(self.act_dec, ctx["act_dec"], d_act_out, kv_mem, dkv_mem, self.nd, B, nq_a,
                                  self.n_act)
+        self._dbg = dict(dq_r=dq_r, dq_a=dq_a, d_rel_out=d_rel_out, d_act_out=d_act_out)
         self._hg_embed_bwd(self.rel_q, ctx["rel_q"], dq_r, B, nq_r)
         self._hg_embed_bwd(self.act_q, ctx["act_q"], dq_a, B, nq_a)
         # hoisted K/V projection backward: one dgrad over all 10 layers, one wgrad per layer
