@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Headline benchmark: train clips/s of the SHG-VQA hot path at bs32/GPU on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our path (one rank per GPU under torchrun)
+  python bench.py --impl reference [...]                          # the reference's CPU path (oracle port), host cores
+
+A "step" is one full pass of the hot path over one synthetic AGQA-shaped batch (32 clips per GPU): embeddings,
+5 language + 5 relation layers, the 2 shared LXRT cross layers + pooler + answer head (forward only, as in the
+reference's --taskHGQA training), both 5-layer hypergraph decoders, heads, the hypergraph x question encoder,
+per-frame Hungarian matching, set loss + answer loss, the whole backward, the NCCL gradient all-reduce (N>1),
+grad-norm clipping and BertAdam.  The slow_r50 backbone and the Conv3d front-end stay on stock PyTorch and are
+OUTSIDE the measured path (SURVEY.md §8a V*, §2 #9): the step starts from the [B,393,768] visual tokens.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 32
+TRAIN_GFLOP_PER_CLIP = 199.3      # 3 x 62.29 (fwd+bwd blocks) + 12.45 (forward-only LXRT x-layers)
+WORKLOAD = ("AGQA taskHGQA hot-path train step, bs32/GPU, from [B,393,768] visual tokens + question ids: "
+            "l5/r5/x2 LXRT stack, 2x5-layer hypergraph decoders, heads, CrossEncoder, per-frame Hungarian matching, "
+            "set+answer loss, backward, grad clip, BertAdam (slow_r50 + Conv3d front-end excluded: stock PyTorch)")
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"], tensor=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in o.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_batch(seed, pin):
+    import torch
+    from shg_vqa_b200.synthetic import make_inputs
+    from shg_vqa_b200.trainer import csr_from_padded
+    raw = make_inputs(BATCH_PER_GPU, seed=seed, with_feat=False, visn_tokens=True)
+    inp = {k: raw[k] for k in ("input_ids", "input_mask", "segment_ids", "rel_segment_ids", "act_segment_ids")}
+    inp["visn_tokens"] = raw["visn_tokens"].reshape(-1, 768).to(torch.bfloat16)
+    batch = {"target": raw["target"]}
+    batch["rel_labels"], batch["rel_off"] = csr_from_padded(raw["rel_tokens"], raw["rel_lengths"])
+    batch["act_labels"], batch["act_off"] = csr_from_padded(raw["act_tokens"], raw["act_lengths"])
+    if pin:
+        inp = {k: v.contiguous().pin_memory() for k, v in inp.items()}
+        batch = {k: v.contiguous().pin_memory() for k, v in batch.items()}
+    return inp, batch
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from shg_vqa_b200 import _lib
+    from shg_vqa_b200.trainer import HotPathTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tr = HotPathTrainer(dev, world_size=world, t_total=100000, warmup=0.1, lr=1e-5)
+    tr.init_weights(seed=9595)                      # identical replicas: same seed on every rank
+    h_inp, h_batch = make_batch(1234 + rank, pin=True)
+    inp = {k: v.to(dev) for k, v in h_inp.items()}
+    batch = {k: v.to(dev) for k, v in h_batch.items()}
+    h2d = sum(v.numel() * v.element_size() for v in list(h_inp.values()) + list(h_batch.values()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---------------------------------------------------------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        tr.train_step(inp, batch)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        out, scal = tr.train_step(inp, batch)
+    e.record()
+    barrier()
+    launches = _lib.launch_count - l0
+    ms_step = max_over_ranks(s.elapsed_time(e) / args.steps)
+    losses = tr.losses_from_scalars(scal)
+
+    # ---------------------------------------------------------------- end to end from pinned host buffers (`e2e`)
+    barrier()
+    t0 = time.perf_counter()
+    s.record()
+    for _ in range(args.steps):
+        tr.train_step_host(h_inp, h_batch)          # H2D of the inputs + step + D2H of the loss sums, every step
+    e.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(s.elapsed_time(e), (time.perf_counter() - t0) * 1e3) / args.steps)
+    sampler.stop_flag = True
+
+    # ---------------------------------------------------------------- live per-kernel timing for the roofline
+    barrier()
+    prof = _lib.Profiler()
+    _lib.profiler = prof
+    tr.train_step(inp, batch)
+    agg = prof.summary()
+    _lib.profiler = None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = read_peaks()
+    step_ms_prof = sum(a["ms"] for a in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    name, a = top
+    if a["kind"] == "tensor":
+        achieved = a["work"] / (a["ms"] * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel=name, achieved=round(achieved, 1), peak=peaks["tensor"], unit="TFLOP/s",
+                    frac=round(achieved / peaks["tensor"], 3), traffic=None)
+    else:
+        achieved = a["work"] / (a["ms"] * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel=name, achieved=round(achieved, 1), peak=peaks["hbm"], unit="GB/s",
+                    frac=round(achieved / peaks["hbm"], 3), traffic=None)
+    roof.update(peak_source=peaks["src"] + (" (sustained: kernel timed inside a long step)" if a["kind"] == "tensor" else ""),
+                launches_per_step=a["calls"], share_of_step=round(a["ms"] / step_ms_prof, 3),
+                avg_launch_us=round(1e3 * a["ms"] / a["calls"], 2))
+    kernels = {}
+    for n, x in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        rate = x["work"] / (x["ms"] * 1e-3) / (1e12 if x["kind"] == "tensor" else 1e9) if x["ms"] > 0 else 0.0
+        kernels[n] = dict(calls=x["calls"], ms=round(x["ms"], 3), share=round(x["ms"] / step_ms_prof, 3),
+                          rate=round(rate, 1), unit="TFLOP/s" if x["kind"] == "tensor" else "GB/s")
+
+    clips = BATCH_PER_GPU * world
+    line = {
+        "metric": "train clips/sec at bs32/GPU (hot path)", "value": round(clips / (ms_step * 1e-3), 2),
+        "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": clips, "per_gpu_batch": BATCH_PER_GPU,
+                   "parallelism": "dp%d" % world,
+                   "l2": "no flush needed: each step streams ~5 GB of parameters/moments/activations (>> 126 MB L2)",
+                   "hot_path_tflop_per_step_per_gpu": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3, 2)},
+        "e2e": {"value": round(clips / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 64, "ms_per_step": round(e2e_ms, 3)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roof,
+        "model_flops_utilisation": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3 / (ms_step * 1e-3) / peaks["tensor"], 3),
+        "kernels": kernels,
+        "loss": {k: round(v, 4) for k, v in losses.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_throughput(steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_throughput(steps, warmup, sample_clips=8):
+    """The reference's own algorithm on the host cores: oracle/shg_oracle.py (torch fp32 port, pinned against the
+    unmodified reference by tests/golden) — forward, scipy-equivalent matching (oracle/lsap.c), loss, backward —
+    on a bounded sample of the bs32 workload."""
+    import torch
+    from oracle import shg_oracle as so
+    from shg_vqa_b200.params import build_key_shapes
+    from shg_vqa_b200.synthetic import make_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ks = {k: [list(s), d] for k, (s, d) in build_key_shapes("hgqa").items()}
+    ks = {k: v for k, v in ks.items() if ".visn_fc.conv" not in k}          # front-end is outside the path
+    sd = so.make_state_dict(ks, seed=0)
+    leaves = {}
+    for k, v in sd.items():
+        ck = so.canonical_key(k)
+        if ck not in leaves:
+            leaves[ck] = v.clone().requires_grad_(v.is_floating_point())
+    full = {k: leaves[so.canonical_key(k)] for k in sd}
+    inp = make_inputs(sample_clips, seed=1234, with_feat=False, visn_tokens=True)
+
+    state = {}
+
+    def step():
+        for t in leaves.values():
+            t.grad = None
+        out = so.agqa_forward(full, inp)
+        so.hgqa_total_loss(out, inp)["total"].backward()
+        # clip_grad_norm_(5.) + BertAdam (tasks/agqaHGQA.py:391-392, lxrt/optimization.py:101-180)
+        live = [t for t in leaves.values() if t.grad is not None]
+        torch.nn.utils.clip_grad_norm_(live, 5.0)
+        with torch.no_grad():
+            for t in live:
+                m, v = state.setdefault(id(t), (torch.zeros_like(t), torch.zeros_like(t)))
+                m.mul_(0.9).add_(t.grad, alpha=0.1)
+                v.mul_(0.999).addcmul_(t.grad, t.grad, value=0.001)
+                t.add_(m / (v.sqrt() + 1e-6) + 0.01 * t, alpha=-1e-5)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(sample_clips / dt, 3), "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": "%d-clip batches of the same workload (fwd + matching + loss + bwd + clip + BertAdam, fp32, "
+                      "%d torch threads), %.2f s/step" % (sample_clips, cores, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    base = cpu_reference_throughput(steps=steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "train clips/sec at bs32/GPU (hot path)", "value": base["value"],
+            "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": round(8 / base["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": "cpu x%d threads" % base["cores"]},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -120,5 +120,39 @@ def check(rc):
         raise ShgError("libshgvqa error %d: %s" % (rc, lib().shg_last_error().decode()))
 
 
-def call(name, *args):
+# kernels launched per entry point (for the bench's gpu_launches count)
+LAUNCHES = {"shg_attn_bwd": 2, "shg_version": 0, "shg_device_check": 0}
+launch_count = 0
+profiler = None     # set to a Profiler to time every call with CUDA events on the launching stream
+
+
+class Profiler:
+    """Per-entry-point CUDA-event timing on the current stream (bench.py's live roofline numbers)."""
+
+    def __init__(self):
+        self.records = []      # (name, kind, work, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, kind, work, s, e in self.records:
+            a = agg.setdefault(name, dict(kind=kind, calls=0, ms=0.0, work=0.0))
+            a["calls"] += 1
+            a["ms"] += s.elapsed_time(e)
+            a["work"] += work
+        return agg
+
+
+def call(name, *args, work=None):
+    """work = ("tensor", flops) | ("hbm", bytes): algorithmic work of this launch, for the roofline."""
+    global launch_count
+    launch_count += LAUNCHES.get(name, 1)
+    if profiler is None:
+        check(getattr(lib(), name)(*args))
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
     check(getattr(lib(), name)(*args))
+    e.record()
+    kind, amount = work if work is not None else ("hbm", 0.0)
+    profiler.records.append((name, kind, float(amount), s, e))

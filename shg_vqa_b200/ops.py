@@ -56,7 +56,7 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
     args.mul_aux, args.mul_mode = ptr(mul_aux), MUL[mul_mode]
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
     args.splits, args.block_n = splits, block_n
-    call("shg_gemm", args, stream())
+    call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k))
     return out
 
 
@@ -77,7 +77,7 @@ def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, 
         assert key_mask.dtype == torch.float32 and key_mask.is_contiguous() and key_mask.shape == (batch, lk)
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
-    call("shg_attn_fwd", a, stream())
+    call("shg_attn_fwd", a, stream(), work=("tensor", 4.0 * batch * heads * lq * lk * 64))
     return out, lse
 
 
@@ -95,7 +95,7 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     a.mask_mode = 1 if key_mask is not None else (2 if frames is not None else 0)
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
-    call("shg_attn_bwd", a, stream())
+    call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64))
 
 
 def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False):
@@ -107,7 +107,8 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty_like(mean) if save_stats else None
     call("shg_layernorm_fwd", ptr(x), ptr(residual), ptr(gamma), ptr(beta), eps, ptr(y), ptr(y2), ptr(addend),
-         addend_rows, ptr(mean), ptr(rstd), rows, n, stream())
+         addend_rows, ptr(mean), ptr(rstd), rows, n, stream(),
+         work=("hbm", 2.0 * rows * n * (2 + (residual is not None) + 2 * (addend is not None))))
     return y, y2, mean, rstd
 
 
@@ -116,14 +117,15 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dy2=None, residual=No
     rows, n = x.shape
     dx = torch.empty_like(x)
     call("shg_layernorm_bwd", ptr(dy), ptr(dy2), ptr(x), ptr(residual), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx),
-         ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, stream())
+         ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, stream(),
+         work=("hbm", 2.0 * rows * n * (3 + (dy2 is not None) + (residual is not None))))
     return dx
 
 
 def colsum_accum(x, out):
     require_device(x)
     rows, n = x.shape
-    call("shg_colsum_accum", ptr(x), _ld(x), rows, n, ptr(out), stream())
+    call("shg_colsum_accum", ptr(x), _ld(x), rows, n, ptr(out), stream(), work=("hbm", 2.0 * rows * n))
 
 
 def add_rows(x, add):
@@ -137,7 +139,7 @@ def add_rows(x, add):
 def act_bwd(dy, aux, act):
     require_device(dy)
     dx = torch.empty_like(dy)
-    call("shg_act_bwd", ptr(dy), ptr(aux), ptr(dx), dy.numel(), ACT[act], stream())
+    call("shg_act_bwd", ptr(dy), ptr(aux), ptr(dx), dy.numel(), ACT[act], stream(), work=("hbm", 6.0 * dy.numel()))
     return dx
 
 
@@ -156,7 +158,8 @@ def bce_logits(x, target, out, grad_scale=1.0, want_grad=True):
 def copy3d(src, dst, n0, n1, chunk, s0, s1, d0, d1, add=None, accumulate=False):
     """Strided block copy over raw bf16 storage; strides in elements (see include/shgvqa.h)."""
     require_device(src)
-    call("shg_copy3d", ptr(src), ptr(dst), ptr(add), n0, n1, chunk, s0, s1, d0, d1, int(accumulate), stream())
+    call("shg_copy3d", ptr(src), ptr(dst), ptr(add), n0, n1, chunk, s0, s1, d0, d1, int(accumulate), stream(),
+         work=("hbm", 2.0 * n0 * n1 * chunk * (2 + bool(accumulate))))
 
 
 def to_bf16(x, out=None):
@@ -164,7 +167,7 @@ def to_bf16(x, out=None):
     assert x.dtype == torch.float32 and x.is_contiguous()
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=BF16)
-    call("shg_f32_to_bf16", ptr(x), ptr(out), x.numel(), stream())
+    call("shg_f32_to_bf16", ptr(x), ptr(out), x.numel(), stream(), work=("hbm", 6.0 * x.numel()))
     return out
 
 
@@ -201,7 +204,7 @@ def match_from_logits(logits, labels, label_off, q_f, want_targets=True):
     tgt = torch.empty(n_rows, device=dev, dtype=torch.int32) if want_targets else None
     call("shg_match_from_logits", ptr(logits), int(logits.dtype == BF16), n_frames, q_f, n_cls, _ld(logits),
          ptr(labels), ptr(label_off), ptr(rows), ptr(cols), ptr(n_match), ptr(status), ptr(row_max), ptr(row_lse),
-         ptr(row_arg), ptr(tgt), stream())
+         ptr(row_arg), ptr(tgt), stream(), work=("hbm", float(logits.element_size()) * n_rows * n_cls))
     return dict(rows=rows, cols=cols, n_match=n_match, status=status, row_max=row_max, row_lse=row_lse,
                 row_argmax=row_arg, target_classes=tgt)
 

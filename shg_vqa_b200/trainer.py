@@ -79,6 +79,26 @@ class HotPathTrainer:
         self.scal = torch.zeros(16, device=self.device, dtype=torch.float32)   # loss sums / grad sumsq
 
     # ------------------------------------------------------------------ weights
+    def init_weights(self, seed=9595):
+        """Random init with the reference's distributions (--fromScratch: init_bert_weights,
+        lxrt/modeling_capsbert.py:1640-1651 — N(0, 0.02) matrices/embeddings, LayerNorm 1/0, zero biases;
+        HGEmbeddings keep nn.Embedding's N(0,1) with a zero padding row; zero tokens)."""
+        st = self.store
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        st.master.zero_()
+        for k, (off, n, shape) in st.offsets.items():
+            v = st.master[off:off + n].view(shape)
+            if k.endswith(("LayerNorm.weight", "norm1.weight", "norm2.weight", "norm3.weight", "layer_norm.weight")) \
+                    or k in ("class_embed.2.weight", "action_embed.2.weight", "logit_fc.2.weight"):
+                v.fill_(1.0)
+            elif k.startswith(("relation_query_embed.", "action_query_embed.")) and k.endswith("embeddings.weight"):
+                v.normal_(0.0, 1.0, generator=g)
+                v[0].zero_()
+            elif len(shape) >= 2 and not k.endswith(("cls_token", "act_token", "rel_token")):
+                v.normal_(0.0, 0.02, generator=g)
+        st.refresh_shadow()
+        self.engine.refresh_derived()
+
     def load_state_dict(self, sd, strict=True):
         r = self.store.load_state_dict(sd, strict)
         self.engine.refresh_derived()
@@ -137,11 +157,11 @@ class HotPathTrainer:
         sumsq.zero_()
         n_live = st.n_live
         ops.call("shg_grad_sumsq", ops.ptr(st.grad), ops.ptr(st.seg_start), ops.ptr(st.seg_prefix), st.n_seg, n_live,
-                 ops.ptr(sumsq), ops.stream())
+                 ops.ptr(sumsq), ops.stream(), work=("hbm", 4.0 * n_live))
         ops.call("shg_bert_adam_step", ops.ptr(st.master), ops.ptr(st.grad), ops.ptr(self.exp_avg),
                  ops.ptr(self.exp_avg_sq), ops.ptr(st.shadow), st.n_matrix, ops.ptr(st.seg_start),
                  ops.ptr(st.seg_prefix), st.n_seg, n_live, ops.ptr(sumsq), self.max_norm, lr, self.b1, self.b2,
-                 self.eps, self.wd, 1.0 / self.world_size, 1, ops.stream())
+                 self.eps, self.wd, 1.0 / self.world_size, 1, ops.stream(), work=("hbm", 34.0 * n_live))
         self.engine.refresh_derived()
         self.step_count += 1
 
@@ -160,6 +180,14 @@ class HotPathTrainer:
         self.all_reduce_grads()
         self.optimizer_step()
         return out, scal
+
+    def train_step_host(self, host_inp, host_batch):
+        """The call a user of the path makes with HOST (pinned) buffers: H2D copies of the step's inputs, the
+        step, and a D2H read of the loss sums.  Returns the loss dict."""
+        inp = {k: v.to(self.device, non_blocking=True) for k, v in host_inp.items()}
+        batch = {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
+        _, scal = self.train_step(inp, batch)
+        return self.losses_from_scalars(scal)
 
     @torch.no_grad()
     def eval_step(self, inp):
