@@ -2,8 +2,8 @@
 //
 // One CTA per (128-query tile, head, batch element).  Every key/value row of the head fits in shared memory
 // (Lk <= 400 on this path: 40 text, 393 visual, 128/48 queries, 177 hypergraph tokens), so there is no online
-// softmax: S = Q.K^T is produced whole in TMEM (<= 416 fp32 columns), each of the 128 softmax threads owns one
-// query row (tcgen05.ld 32x32b — no shuffles), applies scale + mask, exponentiates, and writes P as bf16 into
+// softmax: S = Q.K^T is produced whole in TMEM (<= 416 fp32 columns), a pair of the 256 softmax threads owns one
+// query row (tcgen05.ld 32x32b — no shuffles), applies scale + mask, exponentiates (exp2), and writes P as bf16 into
 // 128B-swizzled shared memory (aliasing the dead Q/K tiles) as the A operand of O = P.V, with V read as an
 // MN-major B operand exactly where TMA dropped it.  Masks: none | additive key mask (BERT's -10000 padding,
 // lxrt/modeling_capsbert.py:1834) | block-causal by frame (-inf for later frames, lxrt/entry.py:114-121).
@@ -12,7 +12,7 @@
 namespace shg {
 
 constexpr int kHeadDim = 64;
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;
 
 struct AttnParams {
     __nv_bfloat16* o;
@@ -28,6 +28,8 @@ struct AttnParams {
     int mask_mode, q_per_frame, k_per_frame;
 };
 
+// 256 threads: thread (row, half) owns query row `row` of the tile and one half of the key chunks.
+template <bool HAS_KMASK>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -37,7 +39,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     uint8_t* sK = smem + 16384;         // n_kbox x (64 x 128 B)
     uint8_t* sP = smem;                 // aliases Q/K once S is complete: blocks of 128 x 128 B
     uint8_t* sV = smem + p.v_off;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.n_kbox * 8192);
+    float* s_kmask = reinterpret_cast<float*>(sV + p.n_kbox * 8192);   // [448] additive key mask * log2(e)
+    float* s_red = s_kmask + 448;                                       // [2][128] row max, then row sum
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 256);
     uint64_t* bar_qk = bars;
     uint64_t* bar_v = bars + 1;
     uint64_t* bar_s = bars + 2;
@@ -58,6 +62,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         tma_prefetch_desc(&tma_v);
     }
     if (warp == 0) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (HAS_KMASK)
+        for (int k = tid; k < p.lk32; k += kAttnThreads)
+            s_kmask[k] = k < p.lk ? p.key_mask[(size_t)b * p.lk + k] * 1.4426950408889634f : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -85,46 +92,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     }
     __syncwarp();
 
-    // ---------------------------------------------------------------- softmax: thread = query row
-    const int row = warp * 32 + lane;      // warp w may touch TMEM lanes [32w, 32w+32)
+    // ---------------------------------------------------------------- softmax in the log2 domain
+    const int row = (warp & 3) * 32 + lane, half = warp >> 2;   // warp w may touch TMEM lanes [32(w%4), +32)
     const int q = q0 + row;
-    const uint32_t t_row = tmem + (uint32_t(warp * 32) << 16);
-    const float* kmask = p.mask_mode == 1 ? p.key_mask + (size_t)b * p.lk : nullptr;
-    const int q_frame = p.mask_mode == 2 ? q / p.q_per_frame : 0;
+    const uint32_t t_row = tmem + (uint32_t((warp & 3) * 32) << 16);
     // keys < k_lim are visible to this row (block-causal: frames <= the query's frame)
-    const int k_lim = p.mask_mode == 2 ? min(p.lk, (q_frame + 1) * p.k_per_frame) : p.lk;
-    const float sc = p.scale;
+    const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
+    const float c1 = p.scale * 1.4426950408889634f;
+    const int n_ch = p.lk32 >> 5;
+    const int ch0 = half == 0 ? 0 : (n_ch + 1) >> 1, ch1 = half == 0 ? (n_ch + 1) >> 1 : n_ch;
 
     mbar_wait(bar_s, 0);
     tc_fence_after();
     float mx = -INFINITY;
-    for (int c = 0; c < p.lk32; c += 32) {
+    for (int ch = ch0; ch < ch1; ++ch) {
+        const int c = ch << 5;
         uint32_t raw[32];
         tmem_ld32(t_row + c, raw);
         tmem_ld_wait();
+        if (HAS_KMASK) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int k = c + i;
-            float s = __uint_as_float(raw[i]) * sc;
-            if (kmask && k < p.lk) s += __ldg(kmask + k);
-            if (k < k_lim) mx = fmaxf(mx, s);
+            for (int i = 0; i < 32; ++i) {
+                const float t = fmaf(__uint_as_float(raw[i]), c1, s_kmask[c + i]);
+                mx = fmaxf(mx, c + i < k_lim ? t : -INFINITY);
+            }
+        } else if (c + 32 <= k_lim) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, c + i < k_lim ? __uint_as_float(raw[i]) : -INFINITY);
         }
     }
+    if (!HAS_KMASK) mx *= c1;    // scale > 0: the max commutes with the scaling
+    s_red[half * 128 + row] = mx;
+    __syncthreads();
+    mx = fmaxf(s_red[row], s_red[128 + row]);
     if (mx == -INFINITY) mx = 0.f;
+    __syncthreads();             // s_red is reused for the sums below
     float sum = 0.f;
-    for (int c = 0; c < p.lk32; c += 32) {
+    for (int ch = ch0; ch < ch1; ++ch) {
+        const int c = ch << 5;
         uint32_t raw[32];
         tmem_ld32(t_row + c, raw);
         tmem_ld_wait();
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const int k = c + i;
-            float s = __uint_as_float(raw[i]) * sc;
-            if (kmask && k < p.lk) s += __ldg(kmask + k);
-            const float e = k < k_lim ? __expf(s - mx) : 0.f;
-            // the PV product consumes the bf16-rounded probability: normalise by the sum of what is consumed
-            pv[i] = __bfloat162float(__float2bfloat16(e));
+            float t = HAS_KMASK ? fmaf(__uint_as_float(raw[i]), c1, s_kmask[c + i] - mx)
+                                : fmaf(__uint_as_float(raw[i]), c1, -mx);
+            pv[i] = c + i < k_lim ? exp2f(t) : 0.f;
             sum += pv[i];
         }
         uint8_t* blk = sP + (c >> 6) * 16384 + row * 128;
@@ -137,9 +154,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) = u;
         }
     }
+    s_red[half * 128 + row] = sum;
     fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core's async proxy
     tc_fence_before();
     __syncthreads();
+    sum = s_red[row] + s_red[128 + row];
 
     if (tid == 0) {
         tc_fence_after();
@@ -156,13 +175,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const float inv = 1.0f / sum;
-#pragma unroll
-    for (int c = 0; c < kHeadDim; c += 32) {
+    {
         uint32_t raw[32];
-        tmem_ld32(t_row + p.o_col + c, raw);
+        tmem_ld32(t_row + p.o_col + half * 32, raw);
         tmem_ld_wait();
         if (q < p.lq) {
-            __nv_bfloat16* dst = p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim + c;
+            __nv_bfloat16* dst = p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim + half * 32;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
                 uint4 u;
@@ -174,7 +192,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             }
         }
     }
-    if (p.lse && q < p.lq) p.lse[((size_t)b * p.heads + h) * p.lq + q] = mx + __logf(sum);
+    // natural-log log-sum-exp of the scaled, masked scores
+    if (p.lse && half == 0 && q < p.lq)
+        p.lse[((size_t)b * p.heads + h) * p.lq + q] = (mx + log2f(sum)) * 0.6931471805599453f;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -617,7 +637,7 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     const int need = p.o_col + kHeadDim;
     p.tmem_cols = need <= 128 ? 128 : (need <= 256 ? 256 : 512);
     p.scale = a->scale, p.mask_mode = a->mask_mode, p.q_per_frame = a->q_per_frame, p.k_per_frame = a->k_per_frame;
-    const size_t smem = (size_t)p.v_off + p.n_kbox * 8192 + 64 + 1024;
+    const size_t smem = (size_t)p.v_off + p.n_kbox * 8192 + (448 + 256) * 4 + 64 + 1024;
     SHG_REQUIRE(smem <= 227 * 1024, SHG_ESHAPE, "shg_attn_fwd: %zu B of shared memory needed", smem);
 
     const CUtensorMap* tq = head_tmap(a->q, a->ldq, a->heads, a->lq, a->batch, 128);
@@ -626,11 +646,15 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     if (!tq || !tk || !tv) return SHG_ECUDA;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     dim3 grid((a->lq + 127) / 128, a->heads, a->batch);
-    attn_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(*tq, *tk, *tv, p);
+    if (a->mask_mode == 1)
+        attn_fwd_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(*tq, *tk, *tv, p);
+    else
+        attn_fwd_kernel<false><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(*tq, *tk, *tv, p);
     return check_launch("shg_attn_fwd");
 }
 
