@@ -131,6 +131,17 @@ class Profiler:
 
     def __init__(self):
         self.records = []      # (name, kind, work, start_event, end_event)
+        self.tags = []
+
+    def by_tag(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for (name, kind, work, s, e), tag in zip(self.records, self.tags):
+            a = agg.setdefault((name, tag), dict(calls=0, ms=0.0, work=0.0))
+            a["calls"] += 1
+            a["ms"] += s.elapsed_time(e)
+            a["work"] += work
+        return agg
 
     def summary(self):
         torch.cuda.synchronize()
@@ -154,5 +165,6 @@ def call(name, *args, work=None):
     s.record()
     check(getattr(lib(), name)(*args))
     e.record()
-    kind, amount = work if work is not None else ("hbm", 0.0)
+    kind, amount = (work[0], work[1]) if work is not None else ("hbm", 0.0)
     profiler.records.append((name, kind, float(amount), s, e))
+    profiler.tags.append(work[2] if work is not None and len(work) > 2 else "")

@@ -137,12 +137,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         tmem_ld32(t_row + c, raw);
         tmem_ld_wait();
         float pv[32];
+        if (c + 32 <= k_lim) {          // whole chunk visible: no per-element predicate
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float t = HAS_KMASK ? fmaf(__uint_as_float(raw[i]), c1, s_kmask[c + i] - mx)
-                                : fmaf(__uint_as_float(raw[i]), c1, -mx);
-            pv[i] = c + i < k_lim ? exp2f(t) : 0.f;
-            sum += pv[i];
+            for (int i = 0; i < 32; ++i) {
+                pv[i] = ex2_approx(HAS_KMASK ? fmaf(__uint_as_float(raw[i]), c1, s_kmask[c + i] - mx)
+                                             : fmaf(__uint_as_float(raw[i]), c1, -mx));
+                sum += pv[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float t = HAS_KMASK ? fmaf(__uint_as_float(raw[i]), c1, s_kmask[c + i] - mx)
+                                          : fmaf(__uint_as_float(raw[i]), c1, -mx);
+                pv[i] = c + i < k_lim ? ex2_approx(t) : 0.f;
+                sum += pv[i];
+            }
         }
         uint8_t* blk = sP + (c >> 6) * 16384 + row * 128;
         const int j0 = (c & 32) ? 4 : 0;
@@ -270,8 +279,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     uint8_t* sK = smem + 32768;               // 2 x 16 KB
     uint8_t* sV = smem + 65536;               // 2 x 16 KB
     uint8_t* sdS = smem + 98304;              // 2 x 32 KB
-    float* s_part = reinterpret_cast<float*>(smem + 163840);   // [2 halves][128 rows][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 512);
+    float* s_part = reinterpret_cast<float*>(smem + 163840);   // [2 halves][128 rows][2], then [448] key mask
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 512 + 448);
     uint64_t* bar_q = bars;          // Q + dO landed
     uint64_t* bar_kv = bars + 1;     // [2]
     uint64_t* bar_s = bars + 3;      // S and dP of the current chunk complete
@@ -337,7 +346,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
     const float c1 = p.scale * kLog2e;
     const float my_lse = q < p.lq ? p.lse[((size_t)b * p.heads + h) * p.lq + q] * kLog2e : INFINITY;
-    float acc_p = 0.f, acc_pd = 0.f, my_delta = 0.f;
+    float acc_p = 0.f, acc_pd = 0.f, neg_delta_scaled = 0.f;
+    // additive key mask of this batch element, pre-scaled by log2(e), staged once in shared memory
+    float* s_kmask = s_part + 512;
+    if (kmask) {
+        for (int k = tid; k < p.lk; k += kBwdThreads) s_kmask[k] = kmask[k] * kLog2e;
+        __syncthreads();
+    }
 
     for (int jj = 0; jj < n_it; ++jj) {
         const bool sweep2 = jj >= n_kc;
@@ -355,18 +370,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             tmem_ld32(t_dp + t_row + c, rp);
             tmem_ld_wait();
             float ds[32];
+            const int key0 = j * 128 + c;
+            const bool all_visible = key0 + 32 <= k_lim;      // no per-element predicate needed
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const int key = j * 128 + c + i;
-                float x = __uint_as_float(rs[i]) * c1 - my_lse;
-                if (kmask && key < p.lk) x += __ldg(kmask + key) * kLog2e;
-                const float pr = key < k_lim ? exp2f(x) : 0.f;
+                float x = fmaf(__uint_as_float(rs[i]), c1, -my_lse);
+                if (kmask) x += s_kmask[min(key0 + i, p.lk - 1)];
+                float pr = ex2_approx(x);
+                if (!all_visible) pr = key0 + i < k_lim ? pr : 0.f;
                 const float dp = __uint_as_float(rp[i]);
                 if (!sweep2) {
                     acc_p += pr;
-                    acc_pd += pr * dp;
+                    acc_pd = fmaf(pr, dp, acc_pd);
                 } else {
-                    ds[i] = pr * (dp - my_delta) * p.scale;
+                    ds[i] = pr * fmaf(dp, p.scale, neg_delta_scaled);
                 }
             }
             if (sweep2) store_tile_chunk32(tile, row, c, ds);
@@ -381,7 +398,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             __syncthreads();
             const float z = s_part[row * 2] + s_part[(128 + row) * 2];
             const float pd = s_part[row * 2 + 1] + s_part[(128 + row) * 2 + 1];
-            my_delta = z > 0.f ? pd / z : 0.f;
+            const float my_delta = z > 0.f ? pd / z : 0.f;
+            neg_delta_scaled = -my_delta * p.scale;
             if (half == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
         }
         if (tid == 0) {
@@ -495,7 +513,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         const int qq = i * 128 + (tid & 127);
         const size_t base = ((size_t)b * p.heads + h) * p.lq;
         if (tid < 128) s_lse[(i & 1) * 128 + tid] = qq < p.lq ? p.lse[base + qq] * kLog2e : INFINITY;
-        else s_delta[(i & 1) * 128 + (tid - 128)] = qq < p.lq ? p.delta[base + qq] : 0.f;
+        else s_delta[(i & 1) * 128 + (tid - 128)] = qq < p.lq ? p.delta[base + qq] * p.scale : 0.f;   // pre-scaled
     };
 
     if (tid == 0) {
@@ -536,12 +554,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             tmem_ld32(t_dp + t_row + c, rp);
             tmem_ld_wait();
             float pr[32], ds[32];
+            const bool all_visible = key_ok && i * 128 + c >= q_first;   // queries beyond lq carry lse = +inf -> p = 0
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-                const int qq = i * 128 + c + e;
-                const float x = __uint_as_float(rs[e]) * c1 + kbias - lse_i[c + e];   // lse = +inf beyond lq
-                pr[e] = (key_ok && qq >= q_first) ? exp2f(x) : 0.f;
-                ds[e] = pr[e] * (__uint_as_float(rp[e]) - del_i[c + e]) * p.scale;
+                const float x = fmaf(__uint_as_float(rs[e]), c1, kbias - lse_i[c + e]);
+                float pe = ex2_approx(x);
+                if (!all_visible) pe = (key_ok && i * 128 + c + e >= q_first) ? pe : 0.f;
+                pr[e] = pe;
+                ds[e] = pe * fmaf(__uint_as_float(rp[e]), p.scale, -del_i[c + e]);
             }
             store_tile_chunk32(sPt, row, c, pr);
             store_tile_chunk32(sdSt, row, c, ds);
@@ -679,7 +699,7 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     const CUtensorMap* tk = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, 128);
     const CUtensorMap* tv = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, 128);
     if (!tq || !tdo || !tk || !tv) return SHG_ECUDA;
-    const size_t smem = 163840 + 2048 + 128 + 1024;   // tiles + per-row vectors + barriers + alignment slack
+    const size_t smem = 163840 + 2048 + 1792 + 128 + 1024;   // tiles + per-row vectors + key mask + barriers + slack
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

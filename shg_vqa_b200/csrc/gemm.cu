@@ -4,8 +4,10 @@
 //   warp 1      : TMEM allocation (whole warp) + MMA issuer (one lane): tcgen05.mma 128 x block_n x 16,
 //                 fp32 accumulators in TMEM, two accumulator stages so the epilogue of tile t overlaps
 //                 the main loop of tile t+1
-//   warps 2..5  : epilogue — tcgen05.ld (thread = one output row), bias / pre-activation store /
-//                 GELU|ReLU|tanh / residual / bf16|fp32 store or fp32 atomic accumulate (split-K wgrad)
+//   warps 2..9  : epilogue — two warps per TMEM lane quarter (alternating 32-column chunks), tcgen05.ld with
+//                 thread = one output row; bias staged in smem, residual / activation-derivative operands
+//                 prefetched from HBM ahead of the accumulator wait; bias / pre-activation store /
+//                 GELU|ReLU|tanh / x act'(aux) / residual / bf16|fp32 store or fp32 atomic accumulate (split-K)
 //
 // Operand majors are runtime-selectable so the forward (x.W^T), dgrad (dy.W) and wgrad (dy^T.x) products
 // all read the tensors where they already lie in HBM — no transposed copies.
@@ -15,7 +17,7 @@ namespace shg {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
 
 struct GemmParams {
@@ -56,6 +58,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2 stages][256], 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -65,7 +68,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full + s, 1);
-            mbar_init(tmem_empty + s, 4);
+            mbar_init(tmem_empty + s, 8);
         }
         fence_barrier_init();
         tma_prefetch_desc(&tma_a);
@@ -153,24 +156,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue (warps 2..5)
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+        // ---------------------------------------------------------------- epilogue (warps 2..9)
+        // Two warps per TMEM lane quarter, each taking every other 32-column chunk; thread = one output row.
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
+        const int grp = (warp - 2) >> 2;       // which half of the chunks
+        const int etid = (warp - 2) * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
         const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
         const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
         const bool vec_ok_aux = p.mul_aux && (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mul_aux) & 15) == 0);
-        const bool bias_vec_ok = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
         const bool vec_ok_res = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int rem = tile % (p.m_tiles * p.n_tiles);
             const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
             const int row = m0 + quarter * 32 + lane;
             const bool row_ok = row < p.m;
+            // bias of this tile -> shared memory (zero past N), while the main loop is still running
+            float* sb = s_bias + as * 256;
+            sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // operands of the first chunk that come from HBM: issue before waiting for the accumulator
+            uint4 res[4], aux[4];
+            auto prefetch = [&](int c) {
+                const int col0 = n0 + c;
+                const bool full = col0 + 32 <= p.n;
+                if (row_ok && full && vec_ok_res) {
+                    const uint4* src = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) res[i] = __ldg(src + i);
+                }
+                if (row_ok && full && vec_ok_aux) {
+                    const uint4* src = reinterpret_cast<const uint4*>(p.mul_aux + (size_t)row * p.ldd + col0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) aux[i] = __ldg(src + i);
+                }
+            };
+            prefetch(grp * 32);
             mbar_wait(tmem_full + as, aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            for (int c = 0; c < p.block_n; c += 32) {
+            for (int c = grp * 32; c < p.block_n; c += 64) {
                 const int col0 = n0 + c;
                 if (col0 >= p.n) break;  // warp-uniform
                 uint32_t raw[32];
@@ -178,22 +204,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 tmem_ld32(t_row + c, raw);
                 tmem_ld_wait();
                 float acc[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(raw[i]);
                 const bool full_chunk = col0 + 32 <= p.n;
-                if (p.bias) {
-                    if (full_chunk && bias_vec_ok) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                            acc[i] += b4.x, acc[i + 1] += b4.y, acc[i + 2] += b4.z, acc[i + 3] += b4.w;
-                        }
-                    } else {
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sb + c + i);
+                    acc[i] = __uint_as_float(raw[i]) + b4.x, acc[i + 1] = __uint_as_float(raw[i + 1]) + b4.y;
+                    acc[i + 2] = __uint_as_float(raw[i + 2]) + b4.z, acc[i + 3] = __uint_as_float(raw[i + 3]) + b4.w;
+                }
+                // this chunk's prefetched operands -> registers of their own, then prefetch the next chunk's
+                float rv[32], av[32];
+                const bool have_res = row_ok && full_chunk && vec_ok_res;
+                const bool have_aux = row_ok && full_chunk && vec_ok_aux;
+                if (have_res) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.n) acc[i] += __ldg(p.bias + col0 + i);
+                    for (int i = 0; i < 4; ++i) {
+                        float2 f;
+                        f = unpack_bf16x2(res[i].x), rv[8 * i] = f.x, rv[8 * i + 1] = f.y;
+                        f = unpack_bf16x2(res[i].y), rv[8 * i + 2] = f.x, rv[8 * i + 3] = f.y;
+                        f = unpack_bf16x2(res[i].z), rv[8 * i + 4] = f.x, rv[8 * i + 5] = f.y;
+                        f = unpack_bf16x2(res[i].w), rv[8 * i + 6] = f.x, rv[8 * i + 7] = f.y;
                     }
                 }
+                if (have_aux) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float2 f;
+                        f = unpack_bf16x2(aux[i].x), av[8 * i] = f.x, av[8 * i + 1] = f.y;
+                        f = unpack_bf16x2(aux[i].y), av[8 * i + 2] = f.x, av[8 * i + 3] = f.y;
+                        f = unpack_bf16x2(aux[i].z), av[8 * i + 4] = f.x, av[8 * i + 5] = f.y;
+                        f = unpack_bf16x2(aux[i].w), av[8 * i + 6] = f.x, av[8 * i + 7] = f.y;
+                    }
+                }
+                if (c + 64 < p.block_n) prefetch(c + 64);
                 if (row_ok) {
                 if (p.preact) {
                     __nv_bfloat16* pr = p.preact + (size_t)row * p.ldd + col0;
@@ -211,26 +253,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                             if (col0 + i < p.n) pr[i] = __float2bfloat16(acc[i]);
                     }
                 }
-                if (p.act != SHG_ACT_NONE) {
+                if (p.act == SHG_ACT_GELU_ERF) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = gelu_erf(acc[i]);
+                } else if (p.act != SHG_ACT_NONE) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = apply_act(acc[i], p.act);
                 }
                 if (p.mul_mode) {
                     // backward through an activation: acc *= act'(aux) (aux = saved pre-activation for GELU,
                     // saved output for ReLU)
-                    const __nv_bfloat16* ax = p.mul_aux + (size_t)row * p.ldd + col0;
-                    float av[32];
-                    if (full_chunk && vec_ok_aux) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(ax + i));
-                            float2 f;
-                            f = unpack_bf16x2(u.x), av[i] = f.x, av[i + 1] = f.y;
-                            f = unpack_bf16x2(u.y), av[i + 2] = f.x, av[i + 3] = f.y;
-                            f = unpack_bf16x2(u.z), av[i + 4] = f.x, av[i + 5] = f.y;
-                            f = unpack_bf16x2(u.w), av[i + 6] = f.x, av[i + 7] = f.y;
-                        }
-                    } else {
+                    if (!have_aux) {
+                        const __nv_bfloat16* ax = p.mul_aux + (size_t)row * p.ldd + col0;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) av[i] = col0 + i < p.n ? __bfloat162float(ax[i]) : 0.f;
                     }
@@ -243,22 +277,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     }
                 }
                 if (p.residual) {
-                    const __nv_bfloat16* rs = p.residual + (size_t)row * p.ldr + col0;
-                    if (full_chunk && vec_ok_res) {
+                    if (!have_res) {
+                        const __nv_bfloat16* rs = p.residual + (size_t)row * p.ldr + col0;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rs + i));
-                            float2 f;
-                            f = unpack_bf16x2(u.x), acc[i] += f.x, acc[i + 1] += f.y;
-                            f = unpack_bf16x2(u.y), acc[i + 2] += f.x, acc[i + 3] += f.y;
-                            f = unpack_bf16x2(u.z), acc[i + 4] += f.x, acc[i + 5] += f.y;
-                            f = unpack_bf16x2(u.w), acc[i + 6] += f.x, acc[i + 7] += f.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.n) acc[i] += __bfloat162float(rs[i]);
+                        for (int i = 0; i < 32; ++i) rv[i] = col0 + i < p.n ? __bfloat162float(rs[i]) : 0.f;
                     }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] += rv[i];
                 }
                 if (p.accumulate) {
                     float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
@@ -375,7 +400,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
     const int stage_bytes = BM * BK * 2 + bn * BK * 2;
-    const int bar_bytes = 1024;
+    const int bar_bytes = 1024 + 2048;   // barriers + TMEM slot + bias staging
     int n_stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
     p.n_stages = n_stages;

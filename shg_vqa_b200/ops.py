@@ -56,7 +56,7 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
     args.mul_aux, args.mul_mode = ptr(mul_aux), MUL[mul_mode]
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
     args.splits, args.block_n = splits, block_n
-    call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k))
+    call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k, "%dx%dx%d %s%s%s" % (m, n, k, "T" if a_t else "N", "T" if b_t else "N", " acc" if accumulate else "")))
     return out
 
 
@@ -77,7 +77,7 @@ def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, 
         assert key_mask.dtype == torch.float32 and key_mask.is_contiguous() and key_mask.shape == (batch, lk)
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
-    call("shg_attn_fwd", a, stream(), work=("tensor", 4.0 * batch * heads * lq * lk * 64))
+    call("shg_attn_fwd", a, stream(), work=("tensor", 4.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
     return out, lse
 
 
@@ -95,7 +95,7 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     a.mask_mode = 1 if key_mask is not None else (2 if frames is not None else 0)
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
-    call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64))
+    call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
 
 
 def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False):
