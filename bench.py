@@ -39,36 +39,44 @@ def read_peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons streamed (-lms 100) during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.proc, self.stop_flag = index, None, False
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in o.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        if not self.samples:
+        samples = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            for line in out.strip().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 7:
+                    samples.append(f)
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(float(s[0])) for s in self.samples)
+        sm = sorted(int(float(s[0])) for s in samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(samples[0][1])), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in samples), "samples": len(sm)}
 
 
 def make_batch(seed, pin):
@@ -147,7 +155,6 @@ def run_ours(args):
     e.record()
     barrier()
     e2e_ms = max_over_ranks(max(s.elapsed_time(e), (time.perf_counter() - t0) * 1e3) / args.steps)
-    sampler.stop_flag = True
 
     # ---------------------------------------------------------------- live per-kernel timing for the roofline
     barrier()

@@ -61,6 +61,20 @@ def csr_from_padded(tokens, lengths):
     return flat, off
 
 
+def all_reduce_live_grads(store, world_size, group=None):
+    """The path's only exchange step: SUM the contiguous live-gradient span of the flat buffer
+    over the data-parallel ranks (NCCL over NVLink on GPUs; gloo in the CPU tests).  Averaging is left to the
+    optimiser's grad_scale = 1/world_size, so no extra pass over the buffer is needed."""
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(store.grad[store.live_extent], op=dist.ReduceOp.SUM, group=group)
+
+
+def shard_seed(base_seed, rank):
+    """Each rank draws its own 32 clips (weak scaling): disjoint synthetic shards by seed."""
+    return base_seed + rank
+
+
 class HotPathTrainer:
     def __init__(self, device, task="hgqa", n_answers=171, n_rel_cls=457, n_act_cls=158, lr=1e-5, t_total=-1,
                  warmup=0.1, weight_decay=0.01, max_grad_norm=5.0, eos_coef=0.1, world_size=1, process_group=None,
@@ -168,9 +182,7 @@ class HotPathTrainer:
     def all_reduce_grads(self):
         """The step's only collective: sum the flat live-gradient range over ranks (NCCL over NVLink); the
         1/world_size average is folded into the optimiser's grad_scale."""
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.store.grad[self.store.live_extent], group=self.pg)
+        all_reduce_live_grads(self.store, self.world_size, self.pg)
 
     # ------------------------------------------------------------------ steps
     def train_step(self, inp, batch):

@@ -188,3 +188,44 @@ def test_optimizer_step_matches_bert_adam(run):
     n_sh = min(st.n_matrix, st.live_end) - st.live_begin
     assert torch.equal(st.shadow[st.live_begin:st.live_begin + n_sh],
                        st.master[st.live_begin:st.live_begin + n_sh].to(torch.bfloat16))
+
+
+def test_compat_matcher_returns_reference_structure(golden_hgqa, inputs_b2):
+    """HungarianMatcher mirror: same call contract as lxrt/matcher.py (dict in, list of (int64, int64) CPU
+    tensors out), identical assignments on the reference's own logits."""
+    from shg_vqa_b200.compat import HungarianMatcher
+    dev = torch.device("cuda:0")
+    g = golden_hgqa
+    m = HungarianMatcher(cost_class=1, loss_hg_per_frame=True, clip_len=16)
+    for fam, q_f in (("rel", 8), ("act", 3)):
+        labels = inputs_b2[fam + "_labels"]
+        targets = [{"labels": [l.to(dev) for l in labels[b * 16:(b + 1) * 16]]} for b in range(2)]
+        res = m({"pred_logits": torch.from_numpy(g[fam + "_logits"]).to(dev)}, targets)
+        assert len(res) == 32
+        for f, (r, c) in enumerate(res):
+            assert r.dtype == torch.int64 and c.dtype == torch.int64 and not r.is_cuda
+            k = len(r)
+            assert np.array_equal(r.numpy(), g[fam + "_rows"][f, :k]) and (g[fam + "_rows"][f, k:] == -1).all()
+            assert np.array_equal(c.numpy(), g[fam + "_cols"][f, :k])
+    with pytest.raises(AssertionError):
+        HungarianMatcher(cost_class=0)
+
+
+def test_compat_model_forward_from_backbone_features(oracle_weights, inputs_b2, golden_hgqa):
+    """AGQAModel-shaped forward (stock-PyTorch Conv3d front-end + engine) from the same seeded backbone features
+    the reference consumed: the 5-tuple of tasks/agqa_model.py:269 within the bf16 tolerance."""
+    from shg_vqa_b200.compat import AGQAHotPath
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.allow_tf32 = False
+    model = AGQAHotPath(171, num_queries=128, num_classes=456, num_actions=157)
+    model.load_state_dict(oracle_weights, strict=True)
+    i = {k: v.to(dev) for k, v in inputs_b2.items() if torch.is_tensor(v)}
+    logit, rel, act, hg_logit, attn = model(i["feat"], i["boxes"], i["input_ids"], i["input_mask"], i["segment_ids"],
+                                            i["rel_segment_ids"], None, i["act_segment_ids"], None, i["hg_mask"])
+    g = golden_hgqa
+    for name, mine in (("logit", logit), ("rel_logits", rel), ("act_logits", act), ("hg_logit", hg_logit)):
+        ref = torch.from_numpy(g[name])
+        assert tuple(mine.shape) == tuple(ref.shape)
+        assert float((mine.float().cpu() - ref).abs().max()) <= 3e-2 * float(ref.abs().max()), name
+    assert len(attn) == 5
+    assert list(model.state_dict()) == list(oracle_weights)
