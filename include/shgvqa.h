@@ -103,7 +103,8 @@ typedef struct {
     int mul_mode;          /* SHG_MUL_GELU_GRAD: d *= gelu'(mul_aux) ; SHG_MUL_RELU_MASK: d = mul_aux > 0 ? d : 0 */
     int flags;
     int splits;        /* 0 = choose (split-K only with SHG_GEMM_ACCUMULATE); > 1 requires SHG_GEMM_ACCUMULATE */
-    int block_n;       /* 0 = choose; else one of 64,128,192,256 */
+    int block_n;       /* 0 = choose; else 64|128|192|256, optionally | 1024 to force CTA-pair (256-row) tiles
+                          (128/256 only) or | 2048 to forbid them */
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
 

@@ -44,138 +44,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     }
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const GemmParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t a_bytes = BM * BK * 2;
-    const uint32_t b_bytes = p.block_n * BK * 2;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
-    uint64_t* empty_bar = full_bar + kMaxStages;
-    uint64_t* tmem_full = empty_bar + kMaxStages;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2 stages][256], 16 B aligned
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.n_stages; ++s) {
-            mbar_init(full_bar + s, 1);
-            mbar_init(empty_bar + s, 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(tmem_full + s, 1);
-            mbar_init(tmem_empty + s, 8);
-        }
-        fence_barrier_init();
-        tma_prefetch_desc(&tma_a);
-        tma_prefetch_desc(&tma_b);
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = tile / (p.m_tiles * p.n_tiles);
-                const int rem = tile - split * (p.m_tiles * p.n_tiles);
-                const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty_bar + stage, phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    mbar_expect_tx(full_bar + stage, stage_bytes);
-                    const int k0 = kb * BK;
-                    if (!A_MN) {
-                        tma_load_2d(sa, &tma_a, full_bar + stage, k0, m0);
-                    } else {
-                        tma_load_2d(sa, &tma_a, full_bar + stage, m0, k0);
-                        tma_load_2d(sa + 8192, &tma_a, full_bar + stage, m0 + 64, k0);
-                    }
-                    if (!B_MN) {
-                        tma_load_2d(sb, &tma_b, full_bar + stage, k0, n0);
-                    } else {
-                        for (int h = 0; h * 64 < p.block_n; ++h)
-                            tma_load_2d(sb + h * 8192, &tma_b, full_bar + stage, n0 + h * 64, k0);
-                    }
-                    if (++stage == p.n_stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BM, p.block_n, A_MN, B_MN);
-            int stage = 0, as = 0;
-            uint32_t phase = 0, aphase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = tile / (p.m_tiles * p.n_tiles);
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                mbar_wait(tmem_empty + as, aphase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 256;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(full_bar + stage, phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
-#pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) {
-                        const uint64_t adesc = A_MN ? make_smem_desc(sa + ks * 2048, 8192, 1024)
-                                                    : make_smem_desc(sa + ks * 32, 16, 1024);
-                        const uint64_t bdesc = B_MN ? make_smem_desc(sb + ks * 2048, 8192, 1024)
-                                                    : make_smem_desc(sb + ks * 32, 16, 1024);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
-                    }
-                    tc_commit(empty_bar + stage);  // frees the smem slot once these MMAs retire
-                    if (++stage == p.n_stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                tc_commit(tmem_full + as);
-                if (++as == 2) {
-                    as = 0;
-                    aphase ^= 1;
-                }
-            }
-        }
-    } else {
-        // ---------------------------------------------------------------- epilogue (warps 2..9)
-        // Two warps per TMEM lane quarter, each taking every other 32-column chunk; thread = one output row.
-        const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
-        const int grp = (warp - 2) >> 2;       // which half of the chunks
-        const int etid = (warp - 2) * 32 + lane;
-        int as = 0;
-        uint32_t aphase = 0;
+// One output tile's epilogue for one thread (= one output row, every other 32-column chunk starting at grp*32).
+// `wait_accumulator` blocks until the tile's accumulator is complete in TMEM; HBM operands of the first chunk are
+// requested before it.
+template <class WaitFn>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* sb, uint32_t t_row, int row, bool row_ok,
+                                              int n0, int grp, WaitFn wait_accumulator) {
         const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
         const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
         const bool vec_ok_aux = p.mul_aux && (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mul_aux) & 15) == 0);
         const bool vec_ok_res = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int rem = tile % (p.m_tiles * p.n_tiles);
-            const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < p.m;
-            // bias of this tile -> shared memory (zero past N), while the main loop is still running
-            float* sb = s_bias + as * 256;
-            sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             // operands of the first chunk that come from HBM: issue before waiting for the accumulator
             uint4 res[4], aux[4];
             auto prefetch = [&](int c) {
@@ -193,9 +71,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
             };
             prefetch(grp * 32);
-            mbar_wait(tmem_full + as, aphase);
+            wait_accumulator();
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
             for (int c = grp * 32; c < p.block_n; c += 64) {
                 const int col0 = n0 + c;
                 if (col0 >= p.n) break;  // warp-uniform
@@ -326,6 +203,138 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
                 }  // row_ok
             }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = BM * BK * 2;
+    const uint32_t b_bytes = p.block_n * BK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2 stages][256], 16 B aligned
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.n_stages; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full + s, 1);
+            mbar_init(tmem_empty + s, 8);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int rem = tile - split * (p.m_tiles * p.n_tiles);
+                const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + a_bytes;
+                    mbar_expect_tx(full_bar + stage, stage_bytes);
+                    const int k0 = kb * BK;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tma_a, full_bar + stage, k0, m0);
+                    } else {
+                        tma_load_2d(sa, &tma_a, full_bar + stage, m0, k0);
+                        tma_load_2d(sa + 8192, &tma_a, full_bar + stage, m0 + 64, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tma_b, full_bar + stage, k0, n0);
+                    } else {
+                        for (int h = 0; h * 64 < p.block_n; ++h)
+                            tma_load_2d(sb + h * 8192, &tma_b, full_bar + stage, n0 + h * 64, k0);
+                    }
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BM, p.block_n, A_MN, B_MN);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                mbar_wait(tmem_empty + as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        const uint64_t adesc = A_MN ? make_smem_desc(sa + ks * 2048, 8192, 1024)
+                                                    : make_smem_desc(sa + ks * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? make_smem_desc(sb + ks * 2048, 8192, 1024)
+                                                    : make_smem_desc(sb + ks * 32, 16, 1024);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar + stage);  // frees the smem slot once these MMAs retire
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(tmem_full + as);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (warps 2..9)
+        // Two warps per TMEM lane quarter, each taking every other 32-column chunk; thread = one output row.
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
+        const int grp = (warp - 2) >> 2;       // which half of the chunks
+        const int etid = (warp - 2) * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int rem = tile % (p.m_tiles * p.n_tiles);
+            const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
+            const int row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < p.m;
+            // bias of this tile -> shared memory (zero past N), while the main loop is still running
+            float* sb = s_bias + as * 256;
+            sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
+            epilogue_tile(p, sb, t_row, row, row_ok, n0, grp, [&] { mbar_wait(tmem_full + as, aphase); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + as);
@@ -341,6 +350,192 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster share one 256 x block_n tile.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile; the leader's tcgen05.mma reads both shared memories, so per output
+// element the pair pulls 1.5x fewer operand bytes through L2 than two independent 128 x block_n tiles — the
+// main-loop limiter of the K = 768 projections.  Accumulators: 128 lanes x block_n columns in each CTA's TMEM.
+// ---------------------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+             const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = BM * BK * 2;
+    const int half_n = p.block_n / 2;
+    const uint32_t b_bytes = half_n * BK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.n_stages; ++s) {
+            mbar_init(full_bar + s, 1);      // leader's: one arrive.expect_tx covering both CTAs' bytes
+            mbar_init(empty_bar + s, 1);     // each CTA's: multicast commit from the leader's MMA
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full + s, 1);     // each CTA's: multicast commit
+            mbar_init(tmem_empty + s, 16);   // leader's: 8 epilogue warps of each CTA
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    cluster_sync_all();                      // barriers of both CTAs exist before anything signals across
+    if (warp == 1) tmem_alloc2(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;     // m_tiles counts 256-row pair tiles here
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int rem = tile - split * (p.m_tiles * p.n_tiles);
+                const int m0 = (rem / p.n_tiles) * 256 + rank * BM;
+                const int n0 = (rem % p.n_tiles) * p.block_n + rank * half_n;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + a_bytes;
+                    if (leader) mbar_expect_tx(full_bar + stage, 2 * stage_bytes);
+                    const int k0 = kb * BK;
+                    if (!A_MN) {
+                        tma_load_2d_pair(sa, &tma_a, full_bar + stage, k0, m0);
+                    } else {
+                        tma_load_2d_pair(sa, &tma_a, full_bar + stage, m0, k0);
+                        tma_load_2d_pair(sa + 8192, &tma_a, full_bar + stage, m0 + 64, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d_pair(sb, &tma_b, full_bar + stage, k0, n0);
+                    } else {
+                        for (int h = 0; h * 64 < half_n; ++h)
+                            tma_load_2d_pair(sb + h * 8192, &tma_b, full_bar + stage, n0 + h * 64, k0);
+                    }
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(256, p.block_n, A_MN, B_MN);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                mbar_wait(tmem_empty + as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        const uint64_t adesc = A_MN ? make_smem_desc(sa + ks * 2048, 8192, 1024)
+                                                    : make_smem_desc(sa + ks * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? make_smem_desc(sb + ks * 2048, 8192, 1024)
+                                                    : make_smem_desc(sb + ks * 32, 16, 1024);
+                        umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit_pair(empty_bar + stage);
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit_pair(tmem_full + as);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else {
+        const int quarter = warp & 3, grp = (warp - 2) >> 2;
+        const int etid = (warp - 2) * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        const uint32_t leader_empty0 = mapa_u32(smem_u32(tmem_empty), 0);
+        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+            const int rem = tile % (p.m_tiles * p.n_tiles);
+            const int m0 = (rem / p.n_tiles) * 256 + rank * BM, n0 = (rem % p.n_tiles) * p.block_n;
+            const int row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < p.m;
+            float* sb = s_bias + as * 256;
+            sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
+            epilogue_tile(p, sb, t_row, row, row_ok, n0, grp, [&] { mbar_wait(tmem_full + as, aphase); });
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_empty0 + as * 8);
+            if (++as == 2) {
+                as = 0;
+                aphase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // the peer may still be reading this CTA's smem / signalling its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 512);
+    }
+}
+
+// Modelled cost of covering the output with tiles: waves over the chip x time per tile, the tile time being the
+// larger of the MMA time and the operand bytes each CTA pulls through L2 (single CTA: 128 + bn rows per k-block,
+// CTA pair: 128 + bn/2), plus a fixed per-tile overhead.
+static double tile_cost(int m, int n, int k, int splits, int bn, bool pair) {
+    const int rows = pair ? 256 : 128;
+    const long tiles = (long)((m + rows - 1) / rows) * ((n + bn - 1) / bn) * splits;
+    const int slots = pair ? kNumSMs / 2 : kNumSMs;
+    const long waves = (tiles + slots - 1) / slots;
+    const double kb = (double)((k + BK - 1) / BK) / splits;
+    const double mma = bn * 2.0;                                    // cycles per k-block at 128 x bn x 64 per CTA
+    const double l2 = (128.0 + (pair ? bn / 2 : bn)) * 128.0 / 38.0; // bytes per k-block / (B/clk/SM of L2 feed)
+    const double per_tile = kb * (mma > l2 ? mma : l2) + 1500.0;
+    return waves * per_tile;
+}
+static bool prefer_pair(int m, int n, int k, int splits, int bn) {
+    if (m < 512) return false;
+    double best1 = 1e30, best2 = 1e30;
+    const int c1[4] = {256, 192, 128, 64};
+    for (int b : c1) best1 = fmin(best1, tile_cost(m, n, k, splits, b, false));
+    const int c2[2] = {256, 128};
+    for (int b : c2) best2 = fmin(best2, tile_cost(m, n, k, splits, b, true));
+    (void)bn;
+    return best2 < best1;
+}
+static int pick_pair_block_n(int m, int n, int splits) {
+    return tile_cost(m, n, 768, splits, 256, true) <= tile_cost(m, n, 768, splits, 128, true) ? 256 : 128;
 }
 
 static int pick_block_n(int m_tiles, int n) {
@@ -391,15 +586,21 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     p.mul_aux = (const __nv_bfloat16*)a->mul_aux, p.mul_mode = a->mul_aux ? a->mul_mode : 0;
     p.out_f32 = (a->flags & SHG_GEMM_OUT_F32) || accumulate, p.accumulate = accumulate;
     p.m_tiles = (a->m + BM - 1) / BM;
-    int bn = a->block_n ? a->block_n : pick_block_n(p.m_tiles * splits, a->n);
+    // block_n: 0 = choose everything; low bits = tile width; | 1024 forces CTA-pair tiles (256 x bn), | 2048 forbids them
+    const int bn_req = a->block_n & 1023;
+    bool pair = (a->block_n & 1024) != 0;
+    if (!(a->block_n & (1024 | 2048)) && !bn_req) pair = prefer_pair(a->m, a->n, a->k, splits, 0);
+    int bn = bn_req ? bn_req : (pair ? pick_pair_block_n(a->m, a->n, splits) : pick_block_n(p.m_tiles * splits, a->n));
     SHG_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, SHG_ESHAPE, "shg_gemm: block_n=%d", bn);
+    SHG_REQUIRE(!pair || bn == 128 || bn == 256, SHG_ESHAPE, "shg_gemm: CTA-pair tiles need block_n 128 or 256");
+    if (pair) p.m_tiles = (a->m + 255) / 256;
     p.block_n = bn;
     p.n_tiles = (a->n + bn - 1) / bn;
     p.kb_total = (a->k + BK - 1) / BK;
     p.splits = splits > p.kb_total ? p.kb_total : splits;
     p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
-    const int stage_bytes = BM * BK * 2 + bn * BK * 2;
+    const int stage_bytes = BM * BK * 2 + (pair ? bn / 2 : bn) * BK * 2;
     const int bar_bytes = 1024 + 2048;   // barriers + TMEM slot + bias staging
     int n_stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
@@ -415,15 +616,33 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     strides[0] = (uint64_t)a->lda * 2;
     ta = get_tmap_bf16(a->a, 2, dims, strides, box);
     if (!ta) return SHG_ECUDA;
-    if (!a->b_mn_major) { dims[0] = a->k, dims[1] = a->n, box[0] = BK, box[1] = (uint32_t)bn; }
+    if (!a->b_mn_major) { dims[0] = a->k, dims[1] = a->n, box[0] = BK, box[1] = (uint32_t)(pair ? bn / 2 : bn); }
     else { dims[0] = a->n, dims[1] = a->k, box[0] = 64, box[1] = BK; }
     strides[0] = (uint64_t)a->ldb * 2;
     tb = get_tmap_bf16(a->b, 2, dims, strides, box);
     if (!tb) return SHG_ECUDA;
 
     const int total = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = total < kNumSMs ? total : kNumSMs;
+    int grid = total < kNumSMs ? total : kNumSMs;
+    if (pair) grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
     cudaStream_t s = (cudaStream_t)stream;
+#define SHG_GEMM2_LAUNCH(AM, BMJ)                                                                              \
+    do {                                                                                                       \
+        static bool attr_set2 = false;                                                                         \
+        if (!attr_set2) {                                                                                      \
+            cudaFuncSetAttribute(gemm2_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            attr_set2 = true;                                                                                  \
+        }                                                                                                      \
+        gemm2_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, p);                                   \
+    } while (0)
+    if (pair) {
+        if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);
+        else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM2_LAUNCH(false, true);
+        else if (a->a_mn_major && a->b_mn_major) SHG_GEMM2_LAUNCH(true, true);
+        else SHG_GEMM2_LAUNCH(true, false);
+        return check_launch("shg_gemm(pair)");
+    }
+#undef SHG_GEMM2_LAUNCH
 #define SHG_GEMM_LAUNCH(AM, BMJ)                                                                              \
     do {                                                                                                      \
         static bool attr_set = false;                                                                         \

@@ -366,3 +366,28 @@ def test_attention_bwd_all_path_shapes(ops, lq, lk, mode):
         err = (got.float() - want).abs().max().item()
         assert err <= 3e-2 * want.abs().max().item() + 1e-6, (name, err, want.abs().max().item())
     assert float(dq_buf[:, 768:].abs().max()) == 0.0 and float(dk_buf[:, :768].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("m,n,k", [(12576, 768, 768), (1000, 3072, 768), (4096, 457, 1536), (512, 768, 3072)])
+def test_gemm_cta_pair_tiles(ops, m, n, k, bn):
+    """cta_group::2 path forced (block_n | 1024): forward with every epilogue input, dgrad and split-K wgrad layouts."""
+    g = torch.Generator().manual_seed(m + n + k + bn)
+    x = torch.randn(m, k, generator=g).to(torch.bfloat16).to(_dev())
+    w = (torch.randn(n, k, generator=g) * 0.04).to(torch.bfloat16).to(_dev())
+    bias = (torch.randn(n, generator=g) * 0.1).to(_dev())
+    ld = (n + 7) // 8 * 8
+    res = torch.randn(m, ld, generator=g).to(torch.bfloat16).to(_dev())[:, :n]
+    out = torch.zeros(m, ld, device=_dev(), dtype=torch.bfloat16)[:, :n]
+    ops.gemm(x, w, bias=bias, residual=res, out=out, block_n=bn | 1024)
+    ref = x.float() @ w.float().t() + bias + res.float()
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    dy = torch.randn(m, ld, generator=g).to(torch.bfloat16).to(_dev())[:, :n]
+    dx = ops.gemm(dy, w, b_t=True, block_n=bn | 1024)
+    ref = dy.float() @ w.float()
+    assert (dx.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    if n % 8 == 0:
+        dw = torch.ones(n, k, device=_dev(), dtype=torch.float32)
+        ops.gemm(dy, x, a_t=True, b_t=True, out=dw, accumulate=True, splits=3, block_n=bn | 1024)
+        ref = 1.0 + dy.float().t() @ x.float()
+        assert (dw - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()

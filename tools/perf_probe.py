@@ -47,8 +47,9 @@ if __name__ == "__main__":
                       (B * 40, 2304, 768), (B * 40, 3072, 768), (B * 128, 2304, 768), (B * 128, 2048, 768),
                       (B * 128, 768, 2048), (B * 393, 15360, 768), (B * 128, 457, 1536), (8192, 8192, 8192)]:
         gemm_case(m, n, k)
-    for bn in (64, 128, 192, 256):
-        gemm_case(B * 393, 3072, 768, block_n=bn)
+    for (m, n, k) in [(B * 393, 3072, 768), (B * 393, 768, 768), (B * 393, 768, 3072), (B * 393, 2304, 768), (4096, 2048, 768), (8192, 8192, 8192)]:
+        for bn in (128 | 2048, 192 | 2048, 256 | 2048, 128 | 1024, 256 | 1024):
+            gemm_case(m, n, k, block_n=bn)
     for (lq, lk, fr) in [(393, 393, None), (40, 40, None), (128, 393, None), (48, 393, None), (128, 128, (8, 8)),
                          (393, 40, None), (40, 393, None), (177, 40, None)]:
         attn_case(B, lq, lk, fr)
