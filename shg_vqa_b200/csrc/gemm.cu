@@ -337,7 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             epilogue_tile(p, sb, t_row, row, row_ok, n0, grp, [&] { mbar_wait(tmem_full + as, aphase); });
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + as);
+            if (lane == 0) mbar_arrive_relaxed(tmem_empty + as);
             if (++as == 2) {
                 as = 0;
                 aphase ^= 1;
@@ -524,15 +524,14 @@ static double tile_cost(int m, int n, int k, int splits, int bn, bool pair) {
     const double per_tile = kb * (mma > l2 ? mma : l2) + 1500.0;
     return waves * per_tile;
 }
+// Measured on B200 (tools/step_breakdown.py, pair tiles forbidden vs forced): the CTA pair wins once the problem is
+// several waves deep (12576 x {2304,3072,15360}: -6..-10 %), and loses on the small grids (M <= 4096, N = 768: the
+// pair's cluster sync and 2-SM commit latency are not amortised).  Split-K wgrads are a wash; they stay single-CTA.
 static bool prefer_pair(int m, int n, int k, int splits, int bn) {
-    if (m < 512) return false;
-    double best1 = 1e30, best2 = 1e30;
-    const int c1[4] = {256, 192, 128, 64};
-    for (int b : c1) best1 = fmin(best1, tile_cost(m, n, k, splits, b, false));
-    const int c2[2] = {256, 128};
-    for (int b : c2) best2 = fmin(best2, tile_cost(m, n, k, splits, b, true));
-    (void)bn;
-    return best2 < best1;
+    (void)k, (void)bn;
+    if (splits > 1) return false;
+    const long tiles = (long)((m + BM - 1) / BM) * ((n + 255) / 256);
+    return tiles >= 400;
 }
 static int pick_pair_block_n(int m, int n, int splits) {
     return tile_cost(m, n, 768, splits, 256, true) <= tile_cost(m, n, 768, splits, 128, true) ? 256 : 128;

@@ -13,6 +13,8 @@ MUL = {None: 0, "gelu_grad": 1, "relu_mask": 2}
 GEMM_OUT_F32 = 1
 GEMM_ACCUMULATE = 2
 BF16 = torch.bfloat16
+import os as _os
+_PAIR_FLAG = {"0": 2048, "1": 1024}.get(_os.environ.get("SHG_GEMM_PAIR", ""), 0)   # debugging: forbid / force CTA-pair tiles
 
 
 def _ld(t):
@@ -55,7 +57,7 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
         assert mul_aux.dtype == BF16 and _ld(mul_aux) == _ld(out) and mul_aux.shape == out.shape
     args.mul_aux, args.mul_mode = ptr(mul_aux), MUL[mul_mode]
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
-    args.splits, args.block_n = splits, block_n
+    args.splits, args.block_n = splits, (block_n | _PAIR_FLAG if block_n == 0 and _PAIR_FLAG else block_n)
     call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k, "%dx%dx%d %s%s%s" % (m, n, k, "T" if a_t else "N", "T" if b_t else "N", " acc" if accumulate else "")))
     return out
 
