@@ -45,8 +45,10 @@ __global__ void __launch_bounds__(256) bert_adam_kernel(float* __restrict__ p, f
                                                        const int64_t* __restrict__ seg_start,
                                                        const int64_t* __restrict__ seg_prefix, int n_seg,
                                                        int64_t total4, const float* __restrict__ sumsq,
-                                                       float max_norm, float lr, float b1, float b2, float eps,
-                                                       float wd, float grad_scale, int zero_grad) {
+                                                       float max_norm, float lr, const float* __restrict__ lr_dev,
+                                                       float b1, float b2, float eps, float wd, float grad_scale,
+                                                       int zero_grad) {
+    if (lr_dev) lr = lr_dev[0];     // device-resident learning rate: the launch stays valid inside a CUDA graph
     float clip = 1.0f;
     if (max_norm > 0.f) {
         const float norm = sqrtf(sumsq[0]) * grad_scale;
@@ -105,8 +107,8 @@ int shg_grad_sumsq(const float* grad, const int64_t* seg_start, const int64_t* s
 
 int shg_bert_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow, int64_t n_shadow,
                        const int64_t* seg_start, const int64_t* seg_prefix, int n_seg, int64_t total,
-                       const float* sumsq, float max_norm, float lr, float b1, float b2, float eps, float weight_decay,
-                       float grad_scale, int zero_grad, void* stream) {
+                       const float* sumsq, float max_norm, float lr, const float* lr_dev, float b1, float b2, float eps,
+                       float weight_decay, float grad_scale, int zero_grad, void* stream) {
     using namespace shg;
     SHG_REQUIRE(total % 4 == 0 && n_seg >= 1, SHG_ESHAPE, "shg_bert_adam_step: total=%lld must be a multiple of 4",
                 (long long)total);
@@ -115,7 +117,7 @@ int shg_bert_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     bert_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow, shadow ? n_shadow : 0, seg_start, seg_prefix, n_seg,
-        total / 4, sumsq, max_norm, lr, b1, b2, eps, weight_decay, grad_scale, zero_grad);
+        total / 4, sumsq, max_norm, lr, lr_dev, b1, b2, eps, weight_decay, grad_scale, zero_grad);
     return check_launch("shg_bert_adam_step");
 }
 }

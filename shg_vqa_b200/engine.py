@@ -51,6 +51,31 @@ class Engine:
         self.nl, self.nr, self.nx, self.nd = l_layers, r_layers, x_layers, d_layers
         self.dev = store.device
         self._build_handles()
+        # Independent sub-graphs run on side streams so that the small-M launches (40-token language side,
+        # 48-query action decoder) fill SMs the 148-CTA persistent kernels of the visual side leave idle.
+        self.use_streams = self.dev.type == "cuda"
+        self.s1 = torch.cuda.Stream(self.dev) if self.use_streams else None
+        self.s2 = torch.cuda.Stream(self.dev) if self.use_streams else None
+
+    def _fork(self, *streams):
+        """streams start after everything queued so far on the current stream."""
+        if not self.use_streams:
+            return
+        ev = torch.cuda.current_stream().record_event()
+        for st in streams:
+            st.wait_event(ev)
+
+    def _join(self, *streams):
+        """the current stream waits for the given streams."""
+        if not self.use_streams:
+            return
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            cur.wait_event(st.record_event())
+
+    def _on(self, st):
+        import contextlib
+        return torch.cuda.stream(st) if (self.use_streams and st is not None) else contextlib.nullcontext()
 
     # ------------------------------------------------------------------ parameter handles
     def _lin(self, wkey, bkey=None):
@@ -408,10 +433,13 @@ class Engine:
         # additive key mask (1-mask)*-10000 (lxrt/modeling_capsbert.py:1826-1834); the visual mask is all zeros (:1836)
         kmask = ((1.0 - inp["input_mask"].to(torch.float32)) * -10000.0).contiguous()
         ctx["kmask"] = kmask
+        # language layers on a side stream, relation layers on the main one
+        self._fork(self.s1)
         ctx["L"] = []
-        for L in self.l_layers:
-            lang, s = self._bert_fwd(L, lang, B, nl, kmask, save)
-            ctx["L"].append(s)
+        with self._on(self.s1):
+            for L in self.l_layers:
+                lang, s = self._bert_fwd(L, lang, B, nl, kmask, save)
+                ctx["L"].append(s)
         lang_l = lang
         visn = inp["visn_tokens"]
         nv = visn.shape[0] // B
@@ -421,26 +449,35 @@ class Engine:
             ctx["R"].append(s)
         visn_r = visn
         ctx["visn_r"] = visn_r
+        self._join(self.s1)
         out = dict(lang_l=lang_l, visn_r=visn_r, kmask=kmask)
+        hgqa = self.task == "hgqa"
+        if hgqa:
+            # hoisted memory K/V projection for all decoder layers (tasks/agqa_model.py:218-249)
+            kv_mem = ops.gemm(visn_r, self.kv_w, bias=self.kv_b)
+            ctx["kv_mem"] = kv_mem
+            self._fork(self.s1, self.s2)
         if inp.get("skip_x", False) is False:
-            xl, xv = lang_l, visn_r
-            for _ in range(self.nx):                 # the same module twice (lxrt/modeling_capsbert.py:1247-1249)
-                xl, xv, _ = self._cross_fwd(self.x_layer, xl, xv, B, nl, nv, kmask, None, False)
-            pooled, _ = self._pool_fwd(self.pooler, xv, nv, xl, nl, B)
-            out["logit"], _ = self._head_fwd(self.logit_fc, pooled, False)
-            out["lang"], out["visn"], out["pooled"] = xl, xv, pooled
-        if self.task != "hgqa":
+            # LXRT cross layers + pooler + answer head: forward-only in --taskHGQA training → side stream
+            with self._on(self.s1) if hgqa else self._on(None):
+                xl, xv = lang_l, visn_r
+                for _ in range(self.nx):             # the same module twice (lxrt/modeling_capsbert.py:1247-1249)
+                    xl, xv, _ = self._cross_fwd(self.x_layer, xl, xv, B, nl, nv, kmask, None, False)
+                pooled, _ = self._pool_fwd(self.pooler, xv, nv, xl, nl, B)
+                out["logit"], _ = self._head_fwd(self.logit_fc, pooled, False)
+                out["lang"], out["visn"], out["pooled"] = xl, xv, pooled
+        if not hgqa:
             return out, ctx
-        # decoders over the relation-layer memory (tasks/agqa_model.py:218-249)
-        kv_mem = ops.gemm(visn_r, self.kv_w, bias=self.kv_b)
-        ctx["kv_mem"] = kv_mem
         nq_r, nq_a = self.T * self.n_rel, self.T * self.n_act
         rel_q, ctx["rel_q"] = self._hg_embed_fwd(self.rel_q, inp["rel_segment_ids"].reshape(-1), B, nq_r, save)
         rel_out, ctx["rel_dec"] = self._decoder_fwd(self.rel_dec, rel_q, kv_mem, 0, B, nq_r, self.n_rel, save)
-        act_q, ctx["act_q"] = self._hg_embed_fwd(self.act_q, inp["act_segment_ids"].reshape(-1), B, nq_a, save)
-        act_out, ctx["act_dec"] = self._decoder_fwd(self.act_dec, act_q, kv_mem, self.nd, B, nq_a, self.n_act, save)
         out["rel_logits"], ctx["rel_head"] = self._head_fwd(self.class_embed, rel_out, save)
-        out["act_logits"], ctx["act_head"] = self._head_fwd(self.action_embed, act_out, save)
+        with self._on(self.s2):
+            act_q, ctx["act_q"] = self._hg_embed_fwd(self.act_q, inp["act_segment_ids"].reshape(-1), B, nq_a, save)
+            act_out, ctx["act_dec"] = self._decoder_fwd(self.act_dec, act_q, kv_mem, self.nd, B, nq_a, self.n_act,
+                                                        save)
+            out["act_logits"], ctx["act_head"] = self._head_fwd(self.action_embed, act_out, save)
+        self._join(self.s1, self.s2)
         out["rel_out"], out["act_out"] = rel_out, act_out
         # hypergraph tokens: [cls | per frame: actions + act_token, relations + rel_token]
         per = self.n_act + self.n_rel
@@ -492,19 +529,31 @@ class Engine:
                    self.n_rel * H)
         ops.colsum_accum(d_act_hg, st.g("hgq_encoder.act_token").view(-1))
         ops.colsum_accum(d_rel_hg, st.g("hgq_encoder.rel_token").view(-1))
-        # classifier heads add their share to the decoder outputs
-        d_rel_out = self._head_bwd(self.class_embed, ctx["rel_head"], d_rel_logits)
-        d_act_out = self._head_bwd(self.action_embed, ctx["act_head"], d_act_logits)
-        self._acc(d_rel_out, d_rel_hg)
-        self._acc(d_act_out, d_act_hg)
         kv_mem = ctx["kv_mem"]
         dkv_mem = torch.empty_like(kv_mem)
+        self._fork(self.s1, self.s2)
+        # side stream 1: language layers → embeddings
+        with self._on(self.s1):
+            d_lang = d_lang_l
+            for i in reversed(range(self.nl)):
+                d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
+            ids, seg, pre, mean, rstd, _ = ctx["emb"]
+            E = self.emb
+            de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
+            ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
+                     ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
+        # side stream 2: action head + decoder; main: relation head + decoder (disjoint parameters and dK/dV slices)
+        with self._on(self.s2):
+            d_act_out = self._head_bwd(self.action_embed, ctx["act_head"], d_act_logits)
+            self._acc(d_act_out, d_act_hg)
+            dq_a = self._decoder_bwd(self.act_dec, ctx["act_dec"], d_act_out, kv_mem, dkv_mem, self.nd, B, nq_a,
+                                     self.n_act)
+            self._hg_embed_bwd(self.act_q, ctx["act_q"], dq_a, B, nq_a)
+        d_rel_out = self._head_bwd(self.class_embed, ctx["rel_head"], d_rel_logits)
+        self._acc(d_rel_out, d_rel_hg)
         dq_r = self._decoder_bwd(self.rel_dec, ctx["rel_dec"], d_rel_out, kv_mem, dkv_mem, 0, B, nq_r, self.n_rel)
-        dq_a = self._decoder_bwd(self.act_dec, ctx["act_dec"], d_act_out, kv_mem, dkv_mem, self.nd, B, nq_a,
-                                 self.n_act)
-        self._dbg = dict(dq_r=dq_r, dq_a=dq_a, d_rel_out=d_rel_out, d_act_out=d_act_out)
         self._hg_embed_bwd(self.rel_q, ctx["rel_q"], dq_r, B, nq_r)
-        self._hg_embed_bwd(self.act_q, ctx["act_q"], dq_a, B, nq_a)
+        self._join(self.s2)
         # hoisted K/V projection backward: one dgrad over all 10 layers, one wgrad per layer
         mem = ctx["visn_r"]
         d_mem = ops.gemm(dkv_mem, self.kv_w, b_t=True)
@@ -516,13 +565,5 @@ class Engine:
         for i in reversed(range(self.nr)):
             d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None,
                                     need_dx=(i > 0 or need_dvisn))
-        # language layers → embeddings
-        d_lang = d_lang_l
-        for i in reversed(range(self.nl)):
-            d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
-        ids, seg, pre, mean, rstd, _ = ctx["emb"]
-        E = self.emb
-        de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
-        ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
-                 ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
+        self._join(self.s1)
         return d_visn

@@ -91,6 +91,9 @@ class HotPathTrainer:
         self.exp_avg = self.exp_avg_sq = None
         self.n_ans = n_answers
         self.scal = torch.zeros(16, device=self.device, dtype=torch.float32)   # loss sums / grad sumsq
+        self.lr_dev = torch.zeros(1, device=self.device, dtype=torch.float32)   # device-resident lr (graph-safe)
+        self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else None
+        self.graph = None
 
     # ------------------------------------------------------------------ weights
     def init_weights(self, seed=9595):
@@ -160,13 +163,20 @@ class HotPathTrainer:
             self.exp_avg = torch.zeros_like(self.store.master)
             self.exp_avg_sq = torch.zeros_like(self.store.master)
 
-    def optimizer_step(self):
+    def current_lr(self):
+        if self.t_total != -1:
+            return self.lr * warmup_linear(self.step_count / self.t_total, self.warmup)
+        return self.lr
+
+    def _push_lr(self):
+        """lr of this step → device scalar (async copy from pinned memory; outside any captured graph)."""
+        self.lr_host[0] = self.current_lr()
+        self.lr_dev.copy_(self.lr_host, non_blocking=True)
+
+    def optimizer_step(self, lr_on_device=False):
         st = self.store
         self._ensure_opt_state()
-        if self.t_total != -1:
-            lr = self.lr * warmup_linear(self.step_count / self.t_total, self.warmup)
-        else:
-            lr = self.lr
+        lr = self.current_lr()
         sumsq = self.scal[9:10]
         sumsq.zero_()
         n_live = st.n_live
@@ -174,10 +184,12 @@ class HotPathTrainer:
                  ops.ptr(sumsq), ops.stream(), work=("hbm", 4.0 * n_live))
         ops.call("shg_bert_adam_step", ops.ptr(st.master), ops.ptr(st.grad), ops.ptr(self.exp_avg),
                  ops.ptr(self.exp_avg_sq), ops.ptr(st.shadow), st.n_matrix, ops.ptr(st.seg_start),
-                 ops.ptr(st.seg_prefix), st.n_seg, n_live, ops.ptr(sumsq), self.max_norm, lr, self.b1, self.b2,
+                 ops.ptr(st.seg_prefix), st.n_seg, n_live, ops.ptr(sumsq), self.max_norm, lr,
+                 ops.ptr(self.lr_dev) if lr_on_device else None, self.b1, self.b2,
                  self.eps, self.wd, 1.0 / self.world_size, 1, ops.stream(), work=("hbm", 34.0 * n_live))
         self.engine.refresh_derived()
-        self.step_count += 1
+        if not lr_on_device:
+            self.step_count += 1
 
     def all_reduce_grads(self):
         """The step's only collective: sum the flat live-gradient range over ranks (NCCL over NVLink); the
@@ -185,17 +197,76 @@ class HotPathTrainer:
         all_reduce_live_grads(self.store, self.world_size, self.pg)
 
     # ------------------------------------------------------------------ steps
-    def train_step(self, inp, batch):
+    def train_step(self, inp, batch, lr_on_device=False):
         out, ctx = self.engine.forward(inp, train=True)
         scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, batch)
         self.engine.backward(ctx, d_hg, d_rel, d_act)
         self.all_reduce_grads()
-        self.optimizer_step()
+        self.optimizer_step(lr_on_device)
         return out, scal
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    def capture(self, inp, batch, warmup=3):
+        """Capture one whole training step (≈830 launches on three streams, the NCCL all-reduce included) into a
+        CUDA graph over STATIC input buffers.  The eager path is launch-bound on the host (≈17 ms of Python/ctypes
+        enqueue per step vs ≈18 ms of GPU work); the replay is one launch.  lr is read from device memory so the
+        warm-up schedule keeps working; new batches are copied into the static buffers before each replay."""
+        self._ensure_opt_state()
+        from . import _lib
+        l0 = _lib.launch_count
+        self.train_step(inp, batch)
+        self.launches_per_step = _lib.launch_count - l0
+        self.static_inp = {k: v.clone() for k, v in inp.items()}
+        self.static_batch = {k: v.clone() for k, v in batch.items()}
+        self._push_lr()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # warm allocator, TMA-descriptor cache, cuFuncSetAttribute
+                self.train_step(self.static_inp, self.static_batch, lr_on_device=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.graph_opt = None
+        if self.world_size == 1:
+            with torch.cuda.graph(self.graph):
+                self.static_out, self.static_scal = self.train_step(self.static_inp, self.static_batch,
+                                                                    lr_on_device=True)
+        else:
+            # data-parallel: [forward + loss + backward] | NCCL all-reduce (eager, torch.distributed) | [optimiser]
+            with torch.cuda.graph(self.graph):
+                out, ctx = self.engine.forward(self.static_inp, train=True)
+                scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, self.static_batch)
+                self.engine.backward(ctx, d_hg, d_rel, d_act)
+                self.static_out, self.static_scal = out, scal
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                self.optimizer_step(lr_on_device=True)
+        return self.graph
+
+    def train_step_graph(self, inp=None, batch=None):
+        """Replay the captured step; optional new inputs (device or pinned-host tensors) are copied in first.
+        CSR label buffers must keep the captured sizes (pad the label vector, offsets carry the real extents)."""
+        if inp is not None:
+            for k, v in inp.items():
+                self.static_inp[k].copy_(v, non_blocking=True)
+        if batch is not None:
+            for k, v in batch.items():
+                self.static_batch[k].copy_(v, non_blocking=True)
+        self._push_lr()
+        self.graph.replay()
+        if self.graph_opt is not None:
+            self.all_reduce_grads()
+            self.graph_opt.replay()
+        self.step_count += 1
+        return self.static_out, self.static_scal
 
     def train_step_host(self, host_inp, host_batch):
         """The call a user of the path makes with HOST (pinned) buffers: H2D copies of the step's inputs, the
         step, and a D2H read of the loss sums.  Returns the loss dict."""
+        if self.graph is not None:
+            _, scal = self.train_step_graph(host_inp, host_batch)
+            return self.losses_from_scalars(scal)
         inp = {k: v.to(self.device, non_blocking=True) for k, v in host_inp.items()}
         batch = {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
         _, scal = self.train_step(inp, batch)
