@@ -35,7 +35,7 @@ class AttnArgs(ctypes.Structure):
                 ("o", c_vp), ("ldo", c_i64), ("lse", c_vp),
                 ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
                 ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
-                ("q_per_frame", c_int), ("k_per_frame", c_int)]
+                ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64)]
 
 
 class AttnBwdArgs(ctypes.Structure):
@@ -44,7 +44,7 @@ class AttnBwdArgs(ctypes.Structure):
                 ("dq", c_vp), ("lddq", c_i64), ("dk", c_vp), ("lddk", c_i64), ("dv", c_vp), ("lddv", c_i64),
                 ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
                 ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
-                ("q_per_frame", c_int), ("k_per_frame", c_int)]
+                ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64)]
 
 
 # name -> argtypes (all return int).  Must list every symbol include/shgvqa.h declares.

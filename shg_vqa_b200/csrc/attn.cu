@@ -17,6 +17,8 @@ constexpr int kAttnThreads = 256;
 struct AttnParams {
     __nv_bfloat16* o;
     int64_t ldo;
+    float* o_f32;           // optional fp32 copy of O (consumed by the backward's delta)
+    int64_t ldof;
     float* lse;
     const float* key_mask;  // [batch, lk] additive, or null
     int batch, heads, lq, lk;
@@ -139,18 +141,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         float pv[32];
         if (c + 32 <= k_lim) {          // whole chunk visible: no per-element predicate
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 32; ++i)
                 pv[i] = ex2_approx(HAS_KMASK ? fmaf(__uint_as_float(raw[i]), c1, s_kmask[c + i] - mx)
                                              : fmaf(__uint_as_float(raw[i]), c1, -mx));
-                sum += pv[i];
-            }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float t = HAS_KMASK ? fmaf(__uint_as_float(raw[i]), c1, s_kmask[c + i] - mx)
                                           : fmaf(__uint_as_float(raw[i]), c1, -mx);
                 pv[i] = c + i < k_lim ? ex2_approx(t) : 0.f;
-                sum += pv[i];
             }
         }
         uint8_t* blk = sP + (c >> 6) * 16384 + row * 128;
@@ -160,6 +159,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             uint4 u;
             u.x = pack_bf16x2(pv[8 * j], pv[8 * j + 1]), u.y = pack_bf16x2(pv[8 * j + 2], pv[8 * j + 3]);
             u.z = pack_bf16x2(pv[8 * j + 4], pv[8 * j + 5]), u.w = pack_bf16x2(pv[8 * j + 6], pv[8 * j + 7]);
+            // The row is normalised by the sum of the ROUNDED probabilities the tensor core consumes, so that the
+            // stored O is an exact convex combination of V rows (sum_j P_ij = 1): the backward's
+            // delta = rowsum(dO o O_f32) then cancels against dP to second order (see attn_bwd_dq_kernel).
+            sum += (__uint_as_float(u.x << 16) + __uint_as_float(u.x & 0xffff0000u)) +
+                   (__uint_as_float(u.y << 16) + __uint_as_float(u.y & 0xffff0000u)) +
+                   (__uint_as_float(u.z << 16) + __uint_as_float(u.z & 0xffff0000u)) +
+                   (__uint_as_float(u.w << 16) + __uint_as_float(u.w & 0xffff0000u));
             *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) = u;
         }
     }
@@ -199,6 +205,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 u.w = pack_bf16x2(__uint_as_float(raw[i + 6]) * inv, __uint_as_float(raw[i + 7]) * inv);
                 *reinterpret_cast<uint4*>(dst + i) = u;
             }
+            if (p.o_f32) {
+                float* df = p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(df + i) =
+                        make_float4(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv,
+                                    __uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
+            }
         }
     }
     // natural-log log-sum-exp of the scaled, masked scores
@@ -226,6 +240,8 @@ constexpr int kBwdThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnBwdParams {
+    const float* o_f32;        // fp32 forward output [batch*lq, ldof] or null (then delta comes from a pre-sweep)
+    int64_t ldof;
     const __nv_bfloat16* o;    // forward output  [batch*lq, ldo]
     const __nv_bfloat16* d_o;  // its gradient    [batch*lq, lddo]
     int64_t ldo, lddo;
@@ -268,10 +284,11 @@ __global__ void __launch_bounds__(kBwdThreads)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
                    const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
                    const AttnBwdParams p) {
-    // Two sweeps over the key chunks.  Sweep 1 only accumulates, per query row, sum(p) and sum(p * dP) in fp32 and
-    // forms delta = sum(p dP) / sum(p) from the SAME p and dP that build dS in sweep 2.  The textbook
-    // delta = rowsum(dO o O) reads the bf16-rounded O; when the value rows of a head are nearly identical (the
-    // decoder states of this model are) dP - delta cancels to ~1e-3 of dP and that rounding dominates dQ/dK.
+    // delta_i = sum_j P_ij dP_ij must be consistent with the dP that build dS to fp32 accuracy: when the value rows of
+    // a head are nearly identical (the decoder states of this model are) dP - delta cancels to ~1e-3 of dP, and the
+    // textbook delta = rowsum(dO o O) on the bf16-rounded O is then pure rounding noise.  Two exact routes:
+    //   * o_f32 given (the forward's fp32 copy of O): delta = rowsum(dO o O_f32), one sweep over the key chunks;
+    //   * otherwise: a pre-sweep accumulates sum(p) and sum(p * dP) per row, delta = their ratio (2 sweeps).
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                       // 16 KB
@@ -290,7 +307,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_kc = (p.lk + 127) / 128;
-    const int n_it = 2 * n_kc;
+    const int n_pre = p.o_f32 ? 0 : n_kc;      // iterations of the delta pre-sweep
+    const int n_it = n_pre + n_kc;
 
     if (tid == 0) {
         mbar_init(bar_q, 1);
@@ -320,7 +338,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         tc_commit(bar_s);
     };
     auto load_kv = [&](int jj) {
-        const int j = jj < n_kc ? jj : jj - n_kc;
+        const int j = jj < n_pre ? jj : jj - n_pre;
         mbar_expect_tx(bar_kv + (jj & 1), 32768);
         tma_load_3d(sK + (jj & 1) * 16384, &tma_k, bar_kv + (jj & 1), h * kHeadDim, j * 128, b);
         tma_load_3d(sV + (jj & 1) * 16384, &tma_v, bar_kv + (jj & 1), h * kHeadDim, j * 128, b);
@@ -331,7 +349,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         tma_load_3d(sQ, &tma_q, bar_q, h * kHeadDim, q0, b);
         tma_load_3d(sdO, &tma_do, bar_q, h * kHeadDim, q0, b);
         load_kv(0);
-        load_kv(1);
+        if (n_it > 1) load_kv(1);
         mbar_wait(bar_q, 0);
         mbar_wait(bar_kv, 0);
         tc_fence_after();
@@ -354,10 +372,35 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         __syncthreads();
     }
 
+    if (p.o_f32) {
+        // delta = rowsum(dO o O_f32): each of the row's two threads takes 32 of the 64 head columns
+        float part = 0.f;
+        if (q < p.lq) {
+            const float4* po = reinterpret_cast<const float4*>(p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + half * 32);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)b * p.lq + q) * p.lddo + h * kHeadDim + half * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 g = __ldg(pd + i);
+                const float4 o0 = __ldg(po + 2 * i), o1 = __ldg(po + 2 * i + 1);
+                float2 y;
+                y = unpack_bf16x2(g.x), part = fmaf(o0.x, y.x, fmaf(o0.y, y.y, part));
+                y = unpack_bf16x2(g.y), part = fmaf(o0.z, y.x, fmaf(o0.w, y.y, part));
+                y = unpack_bf16x2(g.z), part = fmaf(o1.x, y.x, fmaf(o1.y, y.y, part));
+                y = unpack_bf16x2(g.w), part = fmaf(o1.z, y.x, fmaf(o1.w, y.y, part));
+            }
+        }
+        s_part[half * 128 + row] = part;
+        __syncthreads();
+        const float my_delta = s_part[row] + s_part[128 + row];
+        neg_delta_scaled = -my_delta * p.scale;
+        if (half == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
+        __syncthreads();
+    }
+
     for (int jj = 0; jj < n_it; ++jj) {
-        const bool sweep2 = jj >= n_kc;
-        const int j = sweep2 ? jj - n_kc : jj;      // key chunk
-        const int j2 = jj - n_kc;                   // index within sweep 2
+        const bool sweep2 = jj >= n_pre;
+        const int j = sweep2 ? jj - n_pre : jj;     // key chunk
+        const int j2 = jj - n_pre;                  // index within the main sweep
         mbar_wait(bar_s, jj & 1);
         tc_fence_after();
         if (sweep2 && j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
@@ -391,8 +434,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         if (sweep2) fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (jj == n_kc - 1) {
-            // end of sweep 1: combine the two half-row partials
+        if (jj == n_pre - 1) {
+            // end of the pre-sweep: combine the two half-row partials
             s_part[(half * 128 + row) * 2] = acc_p;
             s_part[(half * 128 + row) * 2 + 1] = acc_pd;
             __syncthreads();
@@ -647,6 +690,9 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
                 "shg_attn_fwd: output must be 16-byte aligned with ld %% 8 == 0");
     AttnParams p;
     p.o = (__nv_bfloat16*)a->o, p.ldo = a->ldo, p.lse = a->lse, p.key_mask = a->key_mask;
+    p.o_f32 = a->o_f32, p.ldof = a->ldof;
+    SHG_REQUIRE(!a->o_f32 || (a->ldof % 4 == 0 && (reinterpret_cast<uintptr_t>(a->o_f32) & 15) == 0), SHG_ESHAPE,
+                "shg_attn_fwd: o_f32 must be 16-byte aligned with ld %% 4 == 0");
     p.batch = a->batch, p.heads = a->heads, p.lq = a->lq, p.lk = a->lk;
     p.lk16 = (a->lk + 15) / 16 * 16, p.lk32 = (a->lk + 31) / 32 * 32;
     p.n_kbox = (p.lk16 + 63) / 64;
@@ -689,6 +735,9 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
                 SHG_ESHAPE, "shg_attn_bwd: leading dimensions must be multiples of 8");
     AttnBwdParams p;
     p.o = (const __nv_bfloat16*)a->o, p.d_o = (const __nv_bfloat16*)a->d_o, p.ldo = a->ldo, p.lddo = a->lddo;
+    p.o_f32 = a->o_f32, p.ldof = a->ldof;
+    SHG_REQUIRE(!a->o_f32 || (a->ldof % 4 == 0 && (reinterpret_cast<uintptr_t>(a->o_f32) & 15) == 0), SHG_ESHAPE,
+                "shg_attn_bwd: o_f32 must be 16-byte aligned with ld %% 4 == 0");
     p.lse = a->lse, p.delta = a->delta;
     p.dq = (__nv_bfloat16*)a->dq, p.dk = (__nv_bfloat16*)a->dk, p.dv = (__nv_bfloat16*)a->dv;
     p.lddq = a->lddq, p.lddk = a->lddk, p.lddv = a->lddv;

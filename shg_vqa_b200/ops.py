@@ -70,6 +70,7 @@ def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, 
     if out is None:
         out = torch.empty(batch * lq, heads * 64, device=q.device, dtype=BF16)
     lse = torch.empty(batch, heads, lq, device=q.device, dtype=torch.float32) if save_lse else None
+    o32 = torch.empty(batch * lq, heads * 64, device=q.device, dtype=torch.float32) if save_lse else None
     a = AttnArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), _ld(q), ptr(k), _ld(k), ptr(v), _ld(v)
     a.o, a.ldo, a.lse = ptr(out), _ld(out), ptr(lse)
@@ -79,14 +80,19 @@ def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, 
         assert key_mask.dtype == torch.float32 and key_mask.is_contiguous() and key_mask.shape == (batch, lk)
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
+    a.o_f32, a.ldof = ptr(o32), heads * 64
     call("shg_attn_fwd", a, stream(), work=("tensor", 4.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
-    return out, lse
+    return out, (lse, o32) if save_lse else None
 
 
 def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, scale=0.125, key_mask=None,
                   frames=None):
-    """Writes dq/dk/dv (bf16 views with the same head layout as q/k/v)."""
+    """Writes dq/dk/dv (bf16 views with the same head layout as q/k/v).  `lse` is what attention_fwd returned
+    with save_lse: (log-sum-exp, fp32 O); a bare lse tensor selects the two-sweep delta."""
     require_device(q)
+    o32 = None
+    if isinstance(lse, tuple):
+        lse, o32 = lse
     delta = torch.empty_like(lse)
     a = AttnBwdArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), _ld(q), ptr(k), _ld(k), ptr(v), _ld(v)
@@ -97,6 +103,7 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     a.mask_mode = 1 if key_mask is not None else (2 if frames is not None else 0)
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
+    a.o_f32, a.ldof = ptr(o32), (o32.stride(0) if o32 is not None else 0)
     call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
 
 
@@ -110,7 +117,7 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0
     rstd = torch.empty_like(mean) if save_stats else None
     call("shg_layernorm_fwd", ptr(x), ptr(residual), ptr(gamma), ptr(beta), eps, ptr(y), ptr(y2), ptr(addend),
          addend_rows, ptr(mean), ptr(rstd), rows, n, stream(),
-         work=("hbm", 2.0 * rows * n * (2 + (residual is not None) + 2 * (addend is not None))))
+         work=("hbm", 2.0 * rows * n * (2 + (residual is not None) + 2 * (addend is not None)), "%dx%d" % (rows, n)))
     return y, y2, mean, rstd
 
 
@@ -120,14 +127,14 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dy2=None, residual=No
     dx = torch.empty_like(x)
     call("shg_layernorm_bwd", ptr(dy), ptr(dy2), ptr(x), ptr(residual), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx),
          ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, stream(),
-         work=("hbm", 2.0 * rows * n * (3 + (dy2 is not None) + (residual is not None))))
+         work=("hbm", 2.0 * rows * n * (3 + (dy2 is not None) + (residual is not None)), "%dx%d" % (rows, n)))
     return dx
 
 
 def colsum_accum(x, out):
     require_device(x)
     rows, n = x.shape
-    call("shg_colsum_accum", ptr(x), _ld(x), rows, n, ptr(out), stream(), work=("hbm", 2.0 * rows * n))
+    call("shg_colsum_accum", ptr(x), _ld(x), rows, n, ptr(out), stream(), work=("hbm", 2.0 * rows * n, "%dx%d" % (rows, n)))
 
 
 def add_rows(x, add):

@@ -325,7 +325,8 @@ def test_attention_fwd_all_path_shapes(ops, lq, lk, mode):
     ref, ref_lse = _attn_ref(q, k, v, b, lq, lk, 0.125, add)
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item(), err
-    assert torch.allclose(lse, ref_lse, atol=2e-2, rtol=1e-3)
+    assert torch.allclose(lse[0], ref_lse, atol=2e-2, rtol=1e-3)
+    assert (lse[1] - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()      # fp32 copy of O
 
 
 @pytest.mark.parametrize("lq,lk,mode", [(40, 40, "key"), (393, 393, "none"), (40, 393, "none"), (393, 40, "key"),
@@ -358,6 +359,11 @@ def test_attention_bwd_all_path_shapes(ops, lq, lk, mode):
     dk_buf = torch.zeros(b * lk, 2304, device=_dev(), dtype=torch.bfloat16)
     ops.attention_bwd(q, k, v, out, d_o, lse, dq_buf[:, :768], dk_buf[:, 768:1536], dk_buf[:, 1536:], b, lq, lk,
                       key_mask=key_mask, frames=frames)
+    # the two-sweep variant (no fp32 O) must agree
+    dq2 = torch.zeros(b * lq, 768, device=_dev(), dtype=torch.bfloat16)
+    dk2 = torch.zeros(b * lk, 768, device=_dev(), dtype=torch.bfloat16)
+    dv2 = torch.zeros(b * lk, 768, device=_dev(), dtype=torch.bfloat16)
+    ops.attention_bwd(q, k, v, out, d_o, lse[0], dq2, dk2, dv2, b, lq, lk, key_mask=key_mask, frames=frames)
     qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
     ref, _ = _attn_ref(qf, kf, vf, b, lq, lk, 0.125, add)
     ref.backward(d_o.float())
@@ -366,6 +372,8 @@ def test_attention_bwd_all_path_shapes(ops, lq, lk, mode):
         err = (got.float() - want).abs().max().item()
         assert err <= 3e-2 * want.abs().max().item() + 1e-6, (name, err, want.abs().max().item())
     assert float(dq_buf[:, 768:].abs().max()) == 0.0 and float(dk_buf[:, :768].abs().max()) == 0.0
+    for got, want in ((dq2, qf.grad), (dk2, kf.grad), (dv2, vf.grad)):
+        assert (got.float() - want).abs().max().item() <= 3e-2 * want.abs().max().item() + 1e-6
 
 
 @pytest.mark.parametrize("bn", [128, 256])
