@@ -152,7 +152,7 @@ def canonical_key(key):
 
 def _is_matrix(key, shape):
     """Tensors that get a bf16 shadow (tensor-core operands)."""
-    return len(shape) == 2 and shape[0] >= 64 and "embeddings" not in key and "pe.weight" not in key \
+    return len(shape) == 2 and shape[1] >= 64 and "embeddings" not in key and "pe.weight" not in key \
         and "box_fc" not in key
 
 

@@ -229,3 +229,65 @@ def test_compat_model_forward_from_backbone_features(oracle_weights, inputs_b2, 
         assert float((mine.float().cpu() - ref).abs().max()) <= 3e-2 * float(ref.abs().max()), name
     assert len(attn) == 5
     assert list(model.state_dict()) == list(oracle_weights)
+
+
+def test_vqa_eval_forward_config4(oracle_weights, inputs_b2):
+    """Config 4 (--taskVQA eval: LXRT stack + pooler + answer head only, no decoders / matcher) against the golden
+    logits of the unmodified reference built with --taskVQA (tests/golden/vqa_b2.npz)."""
+    import os
+    from oracle import shg_oracle as so
+    from shg_vqa_b200.compat import AGQAHotPath
+    dev = torch.device("cuda:0")
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vqa_b2.npz"))
+    model = AGQAHotPath(171, task="vqa")
+    sd = {k: v for k, v in oracle_weights.items() if k in model.key_shapes}
+    assert len(sd) == 324
+    model.load_state_dict(sd, strict=True)
+    i = {k: v.to(dev) for k, v in inputs_b2.items() if torch.is_tensor(v)}
+    logit, attn = model(i["feat"], i["boxes"], i["input_ids"], i["input_mask"], i["segment_ids"])
+    ref = torch.from_numpy(gold["logit"])
+    assert float((logit.float().cpu() - ref).abs().max()) <= 3e-2 * float(ref.abs().max())
+
+
+def test_star_shaped_decoder_matcher_stress_config5():
+    """Config 5: STAR class counts (564 relation / 112 action classes, 4 answers), bs64, every frame full
+    (1024 8x8 + 1024 3x3 assignment problems): forward + device matching vs the oracle on the same weights;
+    assignments compared on the path's own logits fed to the oracle's CPU matcher (bit-exact)."""
+    from oracle import shg_oracle as so
+    from shg_vqa_b200.params import build_key_shapes
+    from shg_vqa_b200.synthetic import make_inputs
+    from shg_vqa_b200.trainer import HotPathTrainer, csr_targets
+    dev = torch.device("cuda:0")
+    tr = HotPathTrainer(dev, n_answers=4, n_rel_cls=564, n_act_cls=112)
+    ks = {k: [list(s), d] for k, (s, d) in tr.key_shapes.items() if ".visn_fc.conv" not in k}
+    w = so.make_state_dict(ks, seed=5)
+    tr.load_state_dict(w, strict=False)
+    B = 64
+    raw = make_inputs(B, seed=77, n_rel_cls=564, n_act_cls=112, n_ans=4, full_frames=True, with_feat=False,
+                      visn_tokens=True)
+    inp = {k: raw[k].to(dev) for k in ("input_ids", "input_mask", "segment_ids", "rel_segment_ids", "act_segment_ids")}
+    inp["visn_tokens"] = raw["visn_tokens"].reshape(-1, 768).to(torch.bfloat16).to(dev)
+    batch = {"target": raw["target"].to(dev)}
+    batch["rel_labels"], batch["rel_off"] = csr_targets(raw["rel_labels"], dev)
+    batch["act_labels"], batch["act_off"] = csr_targets(raw["act_labels"], dev)
+    out, ctx = tr.engine.forward(inp, train=True)
+    scal, d_hg, d_rel, d_act, matches = tr.loss_and_grads(out, batch)
+    tr.engine.backward(ctx, d_hg, d_rel, d_act)
+    torch.cuda.synchronize()
+    assert out["rel_logits"].shape == (B * 128, 564) and out["act_logits"].shape == (B * 48, 112)
+    assert out["hg_logit"].shape == (B, 4)
+    for fam, q_f, m in (("rel", 8, matches[0]), ("act", 3, matches[1])):
+        lg = out[fam + "_logits"].float().cpu().reshape(B, 16 * q_f, -1)
+        ref = so.hungarian_match(lg, raw[fam + "_labels"])
+        rows, cols, n = m["rows"].cpu().numpy(), m["cols"].cpu().numpy(), m["n_match"].cpu().numpy()
+        assert (n == q_f).all() and (m["status"].cpu().numpy() == 0).all()
+        same = sum(np.array_equal(rows[f], r.numpy()) and np.array_equal(cols[f], c.numpy())
+                   for f, (r, c) in enumerate(ref))
+        assert same >= 0.995 * len(ref), "%s: %d / %d" % (fam, same, len(ref))
+    losses = tr.losses_from_scalars(scal)
+    assert np.isfinite(losses["total"]) and float(tr.store.grad[tr.store.live_extent].abs().max()) > 0
+    # oracle forward on 2 of the 64 clips: logits agree within the bf16 tolerance
+    sub = {k: (v[:2] if torch.is_tensor(v) else v) for k, v in raw.items()}
+    o = so.agqa_forward(w, sub)
+    mine = out["rel_logits"].float().cpu().reshape(B, 128, 564)[:2]
+    assert float((mine - o["rel_logits"]).abs().max()) <= 3e-2 * float(o["rel_logits"].abs().max())
