@@ -56,6 +56,10 @@ class Engine:
         self.use_streams = self.dev.type == "cuda"
         self.s1 = torch.cuda.Stream(self.dev) if self.use_streams else None
         self.s2 = torch.cuda.Stream(self.dev) if self.use_streams else None
+        # weight/bias-gradient products are off the critical path (nothing reads them before the optimiser): they
+        # are queued on their own stream and fill the SMs the dependent chain of small launches leaves idle
+        self.sw = torch.cuda.Stream(self.dev) if self.use_streams else None
+        self._keep = []          # operands of in-flight wgrads stay referenced until the final join
 
     def _fork(self, *streams):
         """streams start after everything queued so far on the current stream."""
@@ -195,11 +199,29 @@ class Engine:
         ops.to_bf16(st.p("hgq_encoder.cls_token").view(-1), out=self.tok[o:o + H])
 
     # ------------------------------------------------------------------ primitive fwd/bwd helpers
-    @staticmethod
-    def _wgrad(lin, dy, x, bias=True):
-        ops.gemm(dy, x, a_t=True, b_t=True, out=lin.gw, accumulate=True)
-        if bias:
-            ops.colsum_accum(dy, lin.gb)
+    def _wgrad(self, lin, dy, x, bias=True):
+        """dW += dy^T x (split-K fp32 atomics into the flat gradient buffer), db += colsum(dy) — on the wgrad
+        stream, ordered after whatever produced dy on the current stream."""
+        if not self.use_streams:
+            ops.gemm(dy, x, a_t=True, b_t=True, out=lin.gw, accumulate=True)
+            if bias:
+                ops.colsum_accum(dy, lin.gb)
+            return
+        self.sw.wait_event(torch.cuda.current_stream().record_event())
+        self._keep.append((dy, x))
+        with torch.cuda.stream(self.sw):
+            ops.gemm(dy, x, a_t=True, b_t=True, out=lin.gw, accumulate=True)
+            if bias:
+                ops.colsum_accum(dy, lin.gb)
+
+    def _bias_grad(self, dy, gb):
+        if not self.use_streams:
+            ops.colsum_accum(dy, gb)
+            return
+        self.sw.wait_event(torch.cuda.current_stream().record_event())
+        self._keep.append((dy,))
+        with torch.cuda.stream(self.sw):
+            ops.colsum_accum(dy, gb)
 
     def _ffn_fwd(self, f1, f2, ln, a, save, act="gelu", eps=EPS_BERT, addend=None):
         pre = torch.empty(a.shape[0], f1.w.shape[0], device=self.dev, dtype=BF16) if (save and act == "gelu") else None
@@ -326,7 +348,7 @@ class Engine:
             self._trace.append(("dtgt_p", dtgt_p.float().cpu(), dqk.float().cpu()))
         if first:
             # tgt is the constant zero tensor (tasks/agqa_model.py:235): only the bias of the value projection learns
-            ops.colsum_accum(dv, D["sa_v"].gb)
+            self._bias_grad(dv, D["sa_v"].gb)
             self._acc(dqpos, dtgt_p)
             return None, None
         self._wgrad(D["sa_v"], dv, tgt)
@@ -565,5 +587,6 @@ class Engine:
         for i in reversed(range(self.nr)):
             d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None,
                                     need_dx=(i > 0 or need_dvisn))
-        self._join(self.s1)
+        self._join(self.s1, self.sw)
+        self._keep.clear()
         return d_visn
