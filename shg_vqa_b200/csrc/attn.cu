@@ -233,10 +233,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 //                                                                                dK  = scale * dS^T . Q
 // with dS = P o (dP - delta), dP = dO . V^T, delta = rowsum(dO o O).  Per chunk: two tcgen05 products into
 // TMEM (S and dP, or their transposes), 256 threads turn them into bf16 P / dS tiles in 128B-swizzled shared
-// memory (thread = one row, half the columns), and those tiles feed the accumulating products as K-major A
+// memory (thread = one row, a quarter of the columns), and those tiles feed the accumulating products as K-major A
 // operands while the TMA-loaded K / Q / dO tiles are consumed as MN-major B operands in place.
 // =====================================================================================================
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;   // 16 warps: four threads per tile row, one 32-column chunk each
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -296,8 +296,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     uint8_t* sK = smem + 32768;               // 2 x 16 KB
     uint8_t* sV = smem + 65536;               // 2 x 16 KB
     uint8_t* sdS = smem + 98304;              // 2 x 32 KB
-    float* s_part = reinterpret_cast<float*>(smem + 163840);   // [2 halves][128 rows][2], then [448] key mask
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 512 + 448);
+    float* s_part = reinterpret_cast<float*>(smem + 163840);   // [4 quarters][128 rows][2], then [448] key mask
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024 + 448);
     uint64_t* bar_q = bars;          // Q + dO landed
     uint64_t* bar_kv = bars + 1;     // [2]
     uint64_t* bar_s = bars + 3;      // S and dP of the current chunk complete
@@ -357,7 +357,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     }
     __syncwarp();
 
-    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane, quad = warp >> 2;   // quad: which 32-column chunk of the 128
     const int q = q0 + row;
     const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
     const float* kmask = p.mask_mode == 1 ? p.key_mask + (size_t)b * p.lk : nullptr;
@@ -366,20 +366,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const float my_lse = q < p.lq ? p.lse[((size_t)b * p.heads + h) * p.lq + q] * kLog2e : INFINITY;
     float acc_p = 0.f, acc_pd = 0.f, neg_delta_scaled = 0.f;
     // additive key mask of this batch element, pre-scaled by log2(e), staged once in shared memory
-    float* s_kmask = s_part + 512;
+    float* s_kmask = s_part + 1024;
     if (kmask) {
         for (int k = tid; k < p.lk; k += kBwdThreads) s_kmask[k] = kmask[k] * kLog2e;
         __syncthreads();
     }
 
     if (p.o_f32) {
-        // delta = rowsum(dO o O_f32): each of the row's two threads takes 32 of the 64 head columns
+        // delta = rowsum(dO o O_f32): each of the row's four threads takes 16 of the 64 head columns
         float part = 0.f;
         if (q < p.lq) {
-            const float4* po = reinterpret_cast<const float4*>(p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + half * 32);
-            const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)b * p.lq + q) * p.lddo + h * kHeadDim + half * 32);
+            const float4* po = reinterpret_cast<const float4*>(p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + quad * 16);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)b * p.lq + q) * p.lddo + h * kHeadDim + quad * 16);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 const uint4 g = __ldg(pd + i);
                 const float4 o0 = __ldg(po + 2 * i), o1 = __ldg(po + 2 * i + 1);
                 float2 y;
@@ -389,11 +389,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 y = unpack_bf16x2(g.w), part = fmaf(o1.z, y.x, fmaf(o1.w, y.y, part));
             }
         }
-        s_part[half * 128 + row] = part;
+        s_part[quad * 128 + row] = part;
         __syncthreads();
-        const float my_delta = s_part[row] + s_part[128 + row];
+        const float my_delta = (s_part[row] + s_part[128 + row]) + (s_part[256 + row] + s_part[384 + row]);
         neg_delta_scaled = -my_delta * p.scale;
-        if (half == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
+        if (quad == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
         __syncthreads();
     }
 
@@ -405,9 +405,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         tc_fence_after();
         if (sweep2 && j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
         uint8_t* tile = sdS + (j2 & 1) * 32768;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = half * 64 + cc * 32;
+        {
+            const int c = quad * 32;
             uint32_t rs[32], rp[32];
             tmem_ld32(t_s + t_row + c, rs);
             tmem_ld32(t_dp + t_row + c, rp);
@@ -436,14 +435,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         __syncthreads();
         if (jj == n_pre - 1) {
             // end of the pre-sweep: combine the two half-row partials
-            s_part[(half * 128 + row) * 2] = acc_p;
-            s_part[(half * 128 + row) * 2 + 1] = acc_pd;
+            s_part[(quad * 128 + row) * 2] = acc_p;
+            s_part[(quad * 128 + row) * 2 + 1] = acc_pd;
             __syncthreads();
-            const float z = s_part[row * 2] + s_part[(128 + row) * 2];
-            const float pd = s_part[row * 2 + 1] + s_part[(128 + row) * 2 + 1];
+            float z = 0.f, pd = 0.f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) z += s_part[(g * 128 + row) * 2], pd += s_part[(g * 128 + row) * 2 + 1];
             const float my_delta = z > 0.f ? pd / z : 0.f;
             neg_delta_scaled = -my_delta * p.scale;
-            if (half == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
+            if (quad == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
         }
         if (tid == 0) {
             tc_fence_after();
@@ -471,13 +471,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     mbar_wait(bar_dq + ((n_kc - 1) & 1), ((n_kc - 1) >> 1) & 1);
     tc_fence_after();
     {
-        uint32_t raw[32];
-        tmem_ld32(t_dq + t_row + half * 32, raw);
+        uint32_t raw[16];
+        tmem_ld16(t_dq + t_row + quad * 16, raw);
         tmem_ld_wait();
         if (q < p.lq) {
-            __nv_bfloat16* dst = p.dq + ((size_t)b * p.lq + q) * p.lddq + h * kHeadDim + half * 32;
+            __nv_bfloat16* dst = p.dq + ((size_t)b * p.lq + q) * p.lddq + h * kHeadDim + quad * 16;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
+            for (int i = 0; i < 16; i += 8) {
                 uint4 u;
                 u.x = pack_bf16x2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
                 u.y = pack_bf16x2(__uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
@@ -556,7 +556,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         const int qq = i * 128 + (tid & 127);
         const size_t base = ((size_t)b * p.heads + h) * p.lq;
         if (tid < 128) s_lse[(i & 1) * 128 + tid] = qq < p.lq ? p.lse[base + qq] * kLog2e : INFINITY;
-        else s_delta[(i & 1) * 128 + (tid - 128)] = qq < p.lq ? p.delta[base + qq] * p.scale : 0.f;   // pre-scaled
+        else if (tid < 256) s_delta[(i & 1) * 128 + (tid - 128)] = qq < p.lq ? p.delta[base + qq] * p.scale : 0.f;   // pre-scaled
     };
 
     if (tid == 0) {
@@ -573,7 +573,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     load_vec(0);
     __syncthreads();
 
-    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane, quad = warp >> 2;
     const int key = k0 + row;
     const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
     const float c1 = p.scale * kLog2e;
@@ -589,9 +589,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         if (i >= 1) mbar_wait(bar_acc, (i - 1) & 1);   // sPt / sdSt free again
         const float* lse_i = s_lse + (i & 1) * 128;
         const float* del_i = s_delta + (i & 1) * 128;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = half * 64 + cc * 32;
+        {
+            const int c = quad * 32;
             uint32_t rs[32], rp[32];
             tmem_ld32(t_s + t_row + c, rs);
             tmem_ld32(t_dp + t_row + c, rp);
@@ -638,12 +637,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     mbar_wait(bar_acc, (n_qc - 1) & 1);
     tc_fence_after();
     {
-        // warps 0-3 write dK, warps 4-7 write dV (64 columns each)
-        const uint32_t t_src = (half == 0 ? t_dk : t_dv) + t_row;
-        __nv_bfloat16* base = half == 0 ? p.dk : p.dv;
-        const int64_t ld = half == 0 ? p.lddk : p.lddv;
-#pragma unroll
-        for (int c = 0; c < kHeadDim; c += 32) {
+        // warp quads 0,1 write the two halves of dK, quads 2,3 those of dV (32 columns each)
+        const uint32_t t_src = (quad < 2 ? t_dk : t_dv) + t_row;
+        __nv_bfloat16* base = quad < 2 ? p.dk : p.dv;
+        const int64_t ld = quad < 2 ? p.lddk : p.lddv;
+        {
+            const int c = (quad & 1) * 32;
             uint32_t raw[32];
             tmem_ld32(t_src + c, raw);
             tmem_ld_wait();
@@ -748,7 +747,7 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     const CUtensorMap* tk = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, 128);
     const CUtensorMap* tv = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, 128);
     if (!tq || !tdo || !tk || !tv) return SHG_ECUDA;
-    const size_t smem = 163840 + 2048 + 1792 + 128 + 1024;   // tiles + per-row vectors + key mask + barriers + slack
+    const size_t smem = 163840 + 4096 + 1792 + 128 + 1024;   // tiles + per-row vectors + key mask + barriers + slack
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
