@@ -529,6 +529,14 @@ class Engine:
     def backward(self, ctx, d_hg_logit, d_rel_logits, d_act_logits, need_dvisn=False):
         """Gradients of the --taskHGQA loss (hg answer loss + relation CE + action CE, tasks/agqaHGQA.py:344-378)
         accumulated into the flat gradient buffer.  d_* are bf16 [rows, n_cls] views with ld % 8 == 0."""
+        self.backward_late_params(ctx, d_hg_logit, d_rel_logits, d_act_logits)
+        return self.backward_early_params(ctx, need_dvisn)
+
+    def backward_late_params(self, ctx, d_hg_logit, d_rel_logits, d_act_logits):
+        """First half of the backward: answer head, CrossEncoder, classifier heads, both decoders, query embeddings
+        and the hoisted K/V weights.  On return (all side streams joined) the gradients of every parameter that
+        sits AFTER the LXRT encoder in the flat layout are final — the data-parallel trainer starts their
+        all-reduce here, overlapped with backward_early_params."""
         B = ctx["B"]
         nl, nv, ng, nq_r, nq_a = ctx["dims"]
         kmask = ctx["kmask"]
@@ -540,7 +548,7 @@ class Engine:
         self._pool_bwd(self.hg_pooler, ctx["hg_pool"], d_pool, d_xg, ng, d_xl, nl, B)
         for s in reversed(ctx["HGX"]):
             d_xl, d_xg = self._cross_bwd(self.hgx_layer, s, d_xl, d_xg, B, nl, ng, kmask, ctx["hg_kmask"])
-        d_lang_l = d_xl
+        ctx["d_lang_l"] = d_xl
         # hypergraph assembly backward: cls / type-token gradients and the decoder-output gradients
         st = self.st
         ops.colsum_accum(d_xg.view(B, ng * H)[:, :H], st.g("hgq_encoder.cls_token").view(-1))
@@ -553,17 +561,8 @@ class Engine:
         ops.colsum_accum(d_rel_hg, st.g("hgq_encoder.rel_token").view(-1))
         kv_mem = ctx["kv_mem"]
         dkv_mem = torch.empty_like(kv_mem)
-        self._fork(self.s1, self.s2)
-        # side stream 1: language layers → embeddings
-        with self._on(self.s1):
-            d_lang = d_lang_l
-            for i in reversed(range(self.nl)):
-                d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
-            ids, seg, pre, mean, rstd, _ = ctx["emb"]
-            E = self.emb
-            de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
-            ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
-                     ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
+        ctx["dkv_mem"] = dkv_mem
+        self._fork(self.s2)
         # side stream 2: action head + decoder; main: relation head + decoder (disjoint parameters and dK/dV slices)
         with self._on(self.s2):
             d_act_out = self._head_bwd(self.action_embed, ctx["act_head"], d_act_logits)
@@ -576,14 +575,30 @@ class Engine:
         dq_r = self._decoder_bwd(self.rel_dec, ctx["rel_dec"], d_rel_out, kv_mem, dkv_mem, 0, B, nq_r, self.n_rel)
         self._hg_embed_bwd(self.rel_q, ctx["rel_q"], dq_r, B, nq_r)
         self._join(self.s2)
-        # hoisted K/V projection backward: one dgrad over all 10 layers, one wgrad per layer
+        # hoisted K/V projection: one wgrad per decoder layer (their parameters belong to this half)
         mem = ctx["visn_r"]
-        d_mem = ops.gemm(dkv_mem, self.kv_w, b_t=True)
         for i, D in enumerate(self._dec_layers()):
             c = i * 2 * H
             self._wgrad(D["ca_kv"], dkv_mem[:, c:c + 2 * H], mem)
-        # relation layers
-        d_visn = d_mem
+        self._join(self.sw)
+
+    def backward_early_params(self, ctx, need_dvisn=False):
+        """Second half: the hoisted K/V dgrad, relation layers (main stream), language layers and embeddings
+        (side stream)."""
+        B = ctx["B"]
+        nl, nv, ng, nq_r, nq_a = ctx["dims"]
+        kmask = ctx["kmask"]
+        self._fork(self.s1)
+        with self._on(self.s1):
+            d_lang = ctx["d_lang_l"]
+            for i in reversed(range(self.nl)):
+                d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
+            ids, seg, pre, mean, rstd, _ = ctx["emb"]
+            E = self.emb
+            de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
+            ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
+                     ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
+        d_visn = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True)
         for i in reversed(range(self.nr)):
             d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None,
                                     need_dx=(i > 0 or need_dvisn))

@@ -203,6 +203,14 @@ class ParamStore:
             if self.device.type == "cuda" else None
         self.int_buffers = {k: torch.arange(s[-1], device=self.device).expand(s).clone()
                             for k, (s, d) in key_shapes.items() if d == "int64"}
+        # data-parallel buckets over the live span.  "late" = tensors whose gradients are final after the first half
+        # of the backward (everything that is not the LXRT encoder's language/relation layers and embeddings):
+        # the live matrices from the first such key to the end of the matrix region.  The rest of the live span
+        # ("early" parameters: language/relation layers, and every vector/table) is reduced at the end.
+        late_mats = [k for k in mats if is_live(k) and not k.startswith("lxrt_encoder.")]
+        self.bucket_late = slice(self.offsets[late_mats[0]][0], self.n_matrix) if late_mats else slice(0, 0)
+        self.bucket_early_a = slice(self.live_begin, self.bucket_late.start if late_mats else self.live_begin)
+        self.bucket_early_b = slice(self.n_matrix if late_mats else self.live_begin, self.live_end)
         # optimiser segment table (one contiguous live span)
         self.n_seg = 1
         self.seg_start = torch.tensor([self.live_begin], dtype=torch.int64, device=self.device)

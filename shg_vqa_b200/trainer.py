@@ -233,12 +233,16 @@ class HotPathTrainer:
                 self.static_out, self.static_scal = self.train_step(self.static_inp, self.static_batch,
                                                                     lr_on_device=True)
         else:
-            # data-parallel: [forward + loss + backward] | NCCL all-reduce (eager, torch.distributed) | [optimiser]
+            # data-parallel: [forward + loss + first half of backward] | async NCCL all-reduce of the gradients that
+            # are already final | [second half of backward] | all-reduce of the rest | [optimiser]
             with torch.cuda.graph(self.graph):
                 out, ctx = self.engine.forward(self.static_inp, train=True)
                 scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, self.static_batch)
-                self.engine.backward(ctx, d_hg, d_rel, d_act)
+                self.engine.backward_late_params(ctx, d_hg, d_rel, d_act)
                 self.static_out, self.static_scal = out, scal
+            self.graph_bwd2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_bwd2, pool=self.graph.pool()):
+                self.engine.backward_early_params(ctx)
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
                 self.optimizer_step(lr_on_device=True)
@@ -256,7 +260,13 @@ class HotPathTrainer:
         self._push_lr()
         self.graph.replay()
         if self.graph_opt is not None:
-            self.all_reduce_grads()
+            import torch.distributed as dist
+            st = self.store
+            w1 = dist.all_reduce(st.grad[st.bucket_late], group=self.pg, async_op=True)   # overlaps graph_bwd2
+            self.graph_bwd2.replay()
+            w2 = dist.all_reduce(st.grad[st.bucket_early_a], group=self.pg, async_op=True)
+            w3 = dist.all_reduce(st.grad[st.bucket_early_b], group=self.pg, async_op=True)
+            w1.wait(), w2.wait(), w3.wait()
             self.graph_opt.replay()
         self.step_count += 1
         return self.static_out, self.static_scal
