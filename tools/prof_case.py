@@ -13,6 +13,18 @@ if what == "attn":
     kv = torch.randn(B * lk, 2304, device=dev).to(torch.bfloat16)
     for _ in range(3):
         ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk)
+elif what == "attn_bwd":
+    lq = int(sys.argv[2]) if len(sys.argv) > 2 else 393
+    lk = int(sys.argv[3]) if len(sys.argv) > 3 else 393
+    q = torch.randn(B * lq, 2304, device=dev).to(torch.bfloat16)
+    kv = torch.randn(B * lk, 2304, device=dev).to(torch.bfloat16)
+    d_o = torch.randn(B * lq, 768, device=dev).to(torch.bfloat16)
+    dq = torch.empty(B * lq, 768, device=dev, dtype=torch.bfloat16)
+    dk = torch.empty(B * lk, 768, device=dev, dtype=torch.bfloat16)
+    dv = torch.empty(B * lk, 768, device=dev, dtype=torch.bfloat16)
+    out, lse = ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, save_lse=True)
+    for _ in range(3):
+        ops.attention_bwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], out, d_o, lse, dq, dk, dv, B, lq, lk)
 elif what == "gemm":
     m, n, k = [int(v) for v in sys.argv[2:5]] if len(sys.argv) > 4 else (B * 393, 3072, 768)
     a = torch.randn(m, k, device=dev).to(torch.bfloat16)
