@@ -598,12 +598,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             float pr[32], ds[32];
             const bool all_visible = key_ok && i * 128 + c >= q_first;   // queries beyond lq carry lse = +inf -> p = 0
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float x = fmaf(__uint_as_float(rs[e]), c1, kbias - lse_i[c + e]);
-                float pe = ex2_approx(x);
-                if (!all_visible) pe = (key_ok && i * 128 + c + e >= q_first) ? pe : 0.f;
-                pr[e] = pe;
-                ds[e] = pe * fmaf(__uint_as_float(rp[e]), p.scale, -del_i[c + e]);
+            for (int e = 0; e < 32; e += 4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(lse_i + c + e);
+                const float4 d4 = *reinterpret_cast<const float4*>(del_i + c + e);
+                const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float x = fmaf(__uint_as_float(rs[e + t]), c1, kbias - lv[t]);
+                    float pe = ex2_approx(x);
+                    if (!all_visible) pe = (key_ok && i * 128 + c + e + t >= q_first) ? pe : 0.f;
+                    pr[e + t] = pe;
+                    ds[e + t] = pe * fmaf(__uint_as_float(rp[e + t]), p.scale, -dv4[t]);
+                }
             }
             store_tile_chunk32(sPt, row, c, pr);
             store_tile_chunk32(sdSt, row, c, ds);
