@@ -109,7 +109,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    tr = HotPathTrainer(dev, world_size=world, t_total=100000, warmup=0.1, lr=1e-5)
+    # train mode as the reference runs it (model.train()): dropout live at every site of the path
+    tr = HotPathTrainer(dev, world_size=world, t_total=100000, warmup=0.1, lr=1e-5, dropout=not args.no_dropout,
+                        dropout_seed=20261018, rank=rank)
     tr.init_weights(seed=9595)                      # identical replicas: same seed on every rank
     h_inp, h_batch = make_batch(1234 + rank, pin=True)
     inp = {k: v.to(dev) for k, v in h_inp.items()}
@@ -202,7 +204,8 @@ def run_ours(args):
         "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": clips, "per_gpu_batch": BATCH_PER_GPU,
-                   "parallelism": "dp%d" % world, "launch": "eager" if args.eager else "cuda-graph replay",
+                   "parallelism": "dp%d" % world, "dropout": "off" if args.no_dropout else
+                   "train mode: hidden/attention-prob 0.1, decoders 0.15, fused counter-based masks", "launch": "eager" if args.eager else "cuda-graph replay",
                    "l2": "no flush needed: each step streams ~5 GB of parameters/moments/activations (>> 126 MB L2)",
                    "hot_path_tflop_per_step_per_gpu": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3, 2)},
         "e2e": {"value": round(clips / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d),
@@ -294,6 +297,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropout", action="store_true", help="eval-style step (p = 0) for A/B timing")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -100,7 +100,11 @@ typedef struct {
     void* preact;
     int act;
     const void* mul_aux;   /* bf16 [M,N], ld = ldd: backward through an activation, applied after act/bias */
-    int mul_mode;          /* SHG_MUL_GELU_GRAD: d *= gelu'(mul_aux) ; SHG_MUL_RELU_MASK: d = mul_aux > 0 ? d : 0 */
+    int mul_mode;          /* SHG_MUL_GELU_GRAD: d *= gelu'(mul_aux) ; SHG_MUL_RELU_MASK: d = mul_aux > 0 ? d*mul_scale : 0 */
+    float mul_scale;       /* 0 = 1; 1/(1-p) when mul_aux is a ReLU output that also went through dropout */
+    float dropout_p;       /* training-mode nn.Dropout on the projection output (after act, before residual) */
+    uint32_t dropout_salt; /* call-site id; the mask is a pure function of (*dropout_seed, salt, row*N + col) */
+    const uint32_t* dropout_seed;   /* device scalar; NULL = dropout off */
     int flags;
     int splits;        /* 0 = choose (split-K only with SHG_GEMM_ACCUMULATE); > 1 requires SHG_GEMM_ACCUMULATE */
     int block_n;       /* 0 = choose; else 64|128|192|256, optionally | 1024 to force CTA-pair (256-row) tiles
@@ -129,6 +133,10 @@ typedef struct {
     const float* key_mask;
     int q_per_frame, k_per_frame;
     float* o_f32; int64_t ldof;   /* optional fp32 copy of o [batch*lq, ldof] for the backward's delta (may be NULL) */
+    /* training-mode dropout on the attention probabilities (lxrt/modeling_capsbert.py:381,402 p = 0.1;
+     * nn.MultiheadAttention(dropout=0.15), lxrt/transformer.py:192-193): o = (dropout(softmax(s)) v); the mask is a
+     * pure function of (*dropout_seed, dropout_salt, batch, head, query, key).  dropout_seed NULL = off. */
+    float dropout_p; uint32_t dropout_salt; const uint32_t* dropout_seed;
 } shg_attn_args;
 int shg_attn_fwd(const shg_attn_args* args, void* stream);
 
@@ -154,6 +162,8 @@ typedef struct {
     int q_per_frame, k_per_frame;
     const float* o_f32; int64_t ldof;   /* fp32 o from the forward: delta = rowsum(d_o * o_f32) in one sweep; NULL:
                                            delta from an extra sweep over the keys (same accuracy, ~40 % more work) */
+    float dropout_p; uint32_t dropout_salt; const uint32_t* dropout_seed;   /* same triple as the forward call;
+                                           requires o_f32 (delta must come from the dropped-out forward output) */
 } shg_attn_bwd_args;
 int shg_attn_bwd(const shg_attn_bwd_args* args, void* stream);
 
@@ -170,9 +180,14 @@ int shg_layernorm_fwd(const void* x, const void* residual, const float* gamma, c
 /* Backward of the above.  g = dy (+ dy2, the gradient arriving over the residual branch); x (+ residual) is the
  * forward input; dx bf16; dgamma/dbeta fp32 [n] are ACCUMULATED; dxsum (fp32 [n], may be NULL) accumulates the
  * column sums of dx = the bias gradient of the Linear that produced x. */
+/* Training-mode dropout hooks (seed: device scalar, NULL = off): in_p/in_salt — the forward output went through
+ * nn.Dropout (embeddings), so dy is masked first; out_p/out_salt + dx_drop — the forward input was
+ * dropout(dense_out) + residual, so dx_drop (bf16, = dx * mask/(1-p)) is the gradient the projection sees and
+ * dxsum accumulates it, while dx stays the residual-branch gradient. */
 int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* residual, const float* gamma,
                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
-                      int rows, int n, void* stream);
+                      int rows, int n, void* dx_drop, float out_p, uint32_t out_salt, float in_p, uint32_t in_salt,
+                      const uint32_t* seed, void* stream);
 
 /* out[n] += column sums of the bf16 matrix x [rows, n] (ld elements per row, ld % 8 == 0): bias gradients. */
 int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, void* stream);
@@ -183,7 +198,8 @@ int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, voi
  * the saved tensors for the backward (may be NULL). */
 int shg_embed_ln_fwd(const float* word, const int64_t* word_ids, const float* pos, const float* type,
                      const int64_t* type_ids, const float* gamma, const float* beta, float eps, void* y, void* pre,
-                     float* mean, float* rstd, int rows, int seq_len, int n, void* stream);
+                     float* mean, float* rstd, int rows, int seq_len, int n, float drop_p, uint32_t drop_salt,
+                     const uint32_t* seed, void* stream);
 /* Scatter-add of the gradient wrt the pre-LN sum (bf16 [rows,n]) into the fp32 table gradients;
  * *_pad = padding_idx whose row receives no gradient (nn.Embedding(padding_idx=0)), or -1. */
 int shg_embed_scatter_bwd(const void* de, const int64_t* word_ids, const int64_t* type_ids, float* dword,

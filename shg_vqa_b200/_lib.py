@@ -26,7 +26,8 @@ class GemmArgs(ctypes.Structure):
                 ("m", c_int), ("n", c_int), ("k", c_int),
                 ("bias", c_vp), ("residual", c_vp), ("ldr", c_i64),
                 ("preact", c_vp), ("act", c_int),
-                ("mul_aux", c_vp), ("mul_mode", c_int),
+                ("mul_aux", c_vp), ("mul_mode", c_int), ("mul_scale", c_f32),
+                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp),
                 ("flags", c_int), ("splits", c_int), ("block_n", c_int)]
 
 
@@ -35,7 +36,8 @@ class AttnArgs(ctypes.Structure):
                 ("o", c_vp), ("ldo", c_i64), ("lse", c_vp),
                 ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
                 ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
-                ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64)]
+                ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64),
+                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp)]
 
 
 class AttnBwdArgs(ctypes.Structure):
@@ -44,7 +46,8 @@ class AttnBwdArgs(ctypes.Structure):
                 ("dq", c_vp), ("lddq", c_i64), ("dk", c_vp), ("lddk", c_i64), ("dv", c_vp), ("lddv", c_i64),
                 ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
                 ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
-                ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64)]
+                ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64),
+                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp)]
 
 
 # name -> argtypes (all return int).  Must list every symbol include/shgvqa.h declares.
@@ -60,10 +63,11 @@ SIGNATURES = {
     "shg_attn_fwd": [ctypes.POINTER(AttnArgs), c_vp],
     "shg_attn_bwd": [ctypes.POINTER(AttnBwdArgs), c_vp],
     "shg_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp],
-    "shg_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp],
+    "shg_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_f32,
+                          ctypes.c_uint32, c_f32, ctypes.c_uint32, c_vp, c_vp],
     "shg_colsum_accum": [c_vp, c_i64, c_int, c_int, c_vp, c_vp],
     "shg_embed_ln_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_int, c_int,
-                         c_int, c_vp],
+                         c_int, c_f32, ctypes.c_uint32, c_vp, c_vp],
     "shg_embed_scatter_bwd": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "shg_add_rows": [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp],
     "shg_act_bwd": [c_vp, c_vp, c_vp, c_i64, c_int, c_vp],

@@ -28,10 +28,17 @@ struct AttnParams {
     int tmem_cols, o_col;
     float scale;
     int mask_mode, q_per_frame, k_per_frame;
+    DropCfg drop;           // dropout on the probabilities (training mode)
 };
 
+// Dropout on the probabilities: element (b, h, q, k) of a call site is pair (row_pair0(b,h,q) + k/2), lane k & 1 of
+// the counter-based mask in shg_common.cuh; the forward and both backward passes index it the same way.
+__device__ __forceinline__ uint32_t attn_row_pair0(int b, int heads, int h, int lq, int q, int lk) {
+    return (uint32_t)(((size_t)b * heads + h) * lq + q) * (uint32_t)(((lk + 31) & ~31) >> 1);
+}
+
 // 256 threads: thread (row, half) owns query row `row` of the tile and one half of the key chunks.
-template <bool HAS_KMASK>
+template <bool HAS_KMASK, bool DROP>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -133,6 +140,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     if (mx == -INFINITY) mx = 0.f;
     __syncthreads();             // s_red is reused for the sums below
     float sum = 0.f;
+    uint32_t dkey = 0, dth = 0, row_pair0 = 0;
+    if (DROP) {
+        dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
+        row_pair0 = attn_row_pair0(b, p.heads, h, p.lq, q, p.lk);
+    }
     for (int ch = ch0; ch < ch1; ++ch) {
         const int c = ch << 5;
         uint32_t raw[32];
@@ -166,6 +178,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                    (__uint_as_float(u.y << 16) + __uint_as_float(u.y & 0xffff0000u)) +
                    (__uint_as_float(u.z << 16) + __uint_as_float(u.z & 0xffff0000u)) +
                    (__uint_as_float(u.w << 16) + __uint_as_float(u.w & 0xffff0000u));
+            if (DROP) {
+                // softmax is normalised over ALL keys; the dropped ones are zeroed only in the P.V operand and
+                // the survivors' 1/(1-p) is folded into the final row scaling
+                const uint32_t pb = row_pair0 + ((c + 8 * j) >> 1);
+                u.x &= drop_pair_mask(dkey, pb, dth), u.y &= drop_pair_mask(dkey, pb + 1, dth);
+                u.z &= drop_pair_mask(dkey, pb + 2, dth), u.w &= drop_pair_mask(dkey, pb + 3, dth);
+            }
             *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) = u;
         }
     }
@@ -189,7 +208,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     __syncwarp();
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    const float inv = 1.0f / sum;
+    const float inv = DROP ? 1.0f / (sum * (1.0f - p.drop.p)) : 1.0f / sum;
     {
         uint32_t raw[32];
         tmem_ld32(t_row + p.o_col + half * 32, raw);
@@ -255,6 +274,7 @@ struct AttnBwdParams {
     int batch, heads, lq, lk;
     float scale;
     int mask_mode, q_per_frame, k_per_frame;
+    DropCfg drop;
 };
 
 // 32 consecutive bf16 of row `row` at column c (multiple of 32) of a [128 x 128] K-major tile made of two
@@ -280,6 +300,7 @@ __device__ __forceinline__ uint64_t rows_b_desc(uint32_t tile, int ks) {
     return make_smem_desc(tile + ks * 2048, 8192, 1024);
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
                    const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
@@ -365,6 +386,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const float c1 = p.scale * kLog2e;
     const float my_lse = q < p.lq ? p.lse[((size_t)b * p.heads + h) * p.lq + q] * kLog2e : INFINITY;
     float acc_p = 0.f, acc_pd = 0.f, neg_delta_scaled = 0.f;
+    uint32_t dkey = 0, dth = 0, row_pair0 = 0;
+    float inv_keep = 1.f;
+    if (DROP) {
+        dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
+        row_pair0 = attn_row_pair0(b, p.heads, h, p.lq, q, p.lk), inv_keep = 1.f / (1.f - p.drop.p);
+    }
     // additive key mask of this batch element, pre-scaled by log2(e), staged once in shared memory
     float* s_kmask = s_part + 1024;
     if (kmask) {
@@ -412,6 +439,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             tmem_ld32(t_dp + t_row + c, rp);
             tmem_ld_wait();
             float ds[32];
+            uint32_t dmask = 0;
             const int key0 = j * 128 + c;
             const bool all_visible = key0 + 32 <= k_lim;      // no per-element predicate needed
 #pragma unroll
@@ -420,7 +448,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 if (kmask) x += s_kmask[min(key0 + i, p.lk - 1)];
                 float pr = ex2_approx(x);
                 if (!all_visible) pr = key0 + i < k_lim ? pr : 0.f;
-                const float dp = __uint_as_float(rp[i]);
+                float dp = __uint_as_float(rp[i]);
+                if (DROP) {
+                    // o = dropout(P) V: the gradient reaches P_ij only through a kept entry, scaled by 1/(1-p)
+                    if ((i & 1) == 0) dmask = drop_pair_mask(dkey, row_pair0 + ((key0 + i) >> 1), dth);
+                    dp = (dmask & ((i & 1) ? 0xffff0000u : 0x0000ffffu)) ? dp * inv_keep : 0.f;
+                }
                 if (!sweep2) {
                     acc_p += pr;
                     acc_pd = fmaf(pr, dp, acc_pd);
@@ -495,6 +528,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
                     const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
@@ -581,6 +615,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     // block-causal: this key is visible to queries of frame >= its own frame, i.e. q >= q_first
     const int q_first = p.mask_mode == 2 ? (key / p.k_per_frame) * p.q_per_frame : 0;
     const bool key_ok = key < p.lk;
+    uint32_t dkey = 0, dth = 0, lane_mask = 0, pair_stride = 0, col_pair0 = 0;
+    float inv_keep = 1.f;
+    if (DROP) {
+        dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
+        inv_keep = 1.f / (1.f - p.drop.p);
+        lane_mask = (key & 1) ? 0xffff0000u : 0x0000ffffu;
+        pair_stride = attn_row_pair0(0, p.heads, 0, p.lq, 1, p.lk);                 // pairs per query row
+        col_pair0 = attn_row_pair0(b, p.heads, h, p.lq, 0, p.lk) + (uint32_t)(key >> 1);
+    }
 
     for (int i = 0; i < n_qc; ++i) {
         if (i + 1 < n_qc) load_vec(i + 1);          // other buffer; consumed after the next __syncthreads
@@ -607,8 +650,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                     const float x = fmaf(__uint_as_float(rs[e + t]), c1, kbias - lv[t]);
                     float pe = ex2_approx(x);
                     if (!all_visible) pe = (key_ok && i * 128 + c + e + t >= q_first) ? pe : 0.f;
-                    pr[e + t] = pe;
-                    ds[e + t] = pe * fmaf(__uint_as_float(rp[e + t]), p.scale, -dv4[t]);
+                    float dp = __uint_as_float(rp[e + t]), pd = pe;
+                    if (DROP) {
+                        const uint32_t qq = (uint32_t)(i * 128 + c + e + t);
+                        const bool keep = drop_pair_mask(dkey, col_pair0 + qq * pair_stride, dth) & lane_mask;
+                        dp = keep ? dp * inv_keep : 0.f;
+                        pd = keep ? pe * inv_keep : 0.f;          // dV = dropout(P)^T dO
+                    }
+                    pr[e + t] = pd;
+                    ds[e + t] = pe * fmaf(dp, p.scale, -dv4[t]);
                 }
             }
             store_tile_chunk32(sPt, row, c, pr);
@@ -708,6 +758,8 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     const int need = p.o_col + kHeadDim;
     p.tmem_cols = need <= 128 ? 128 : (need <= 256 ? 256 : 512);
     p.scale = a->scale, p.mask_mode = a->mask_mode, p.q_per_frame = a->q_per_frame, p.k_per_frame = a->k_per_frame;
+    p.drop.p = a->dropout_seed ? a->dropout_p : 0.f, p.drop.salt = a->dropout_salt, p.drop.seed = a->dropout_seed;
+    SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_attn_fwd: dropout_p=%f", (double)p.drop.p);
     const size_t smem = (size_t)p.v_off + p.n_kbox * 8192 + (448 + 256) * 4 + 64 + 1024;
     SHG_REQUIRE(smem <= 227 * 1024, SHG_ESHAPE, "shg_attn_fwd: %zu B of shared memory needed", smem);
 
@@ -717,15 +769,22 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     if (!tq || !tk || !tv) return SHG_ECUDA;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     dim3 grid((a->lq + 127) / 128, a->heads, a->batch);
-    if (a->mask_mode == 1)
-        attn_fwd_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(*tq, *tk, *tv, p);
-    else
-        attn_fwd_kernel<false><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(*tq, *tk, *tv, p);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool drop = p.drop.p > 0.f;
+    if (a->mask_mode == 1) {
+        if (drop) attn_fwd_kernel<true, true><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
+        else attn_fwd_kernel<true, false><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
+    } else {
+        if (drop) attn_fwd_kernel<false, true><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
+        else attn_fwd_kernel<false, false><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
+    }
     return check_launch("shg_attn_fwd");
 }
 
@@ -748,6 +807,9 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     p.lddq = a->lddq, p.lddk = a->lddk, p.lddv = a->lddv;
     p.key_mask = a->key_mask, p.batch = a->batch, p.heads = a->heads, p.lq = a->lq, p.lk = a->lk;
     p.scale = a->scale, p.mask_mode = a->mask_mode, p.q_per_frame = a->q_per_frame, p.k_per_frame = a->k_per_frame;
+    p.drop.p = a->dropout_seed ? a->dropout_p : 0.f, p.drop.salt = a->dropout_salt, p.drop.seed = a->dropout_seed;
+    SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_attn_bwd: dropout_p=%f", (double)p.drop.p);
+    const bool drop = p.drop.p > 0.f;
     const CUtensorMap* tq = head_tmap(a->q, a->ldq, a->heads, a->lq, a->batch, 128);
     const CUtensorMap* tdo = head_tmap(a->d_o, a->lddo, a->heads, a->lq, a->batch, 128);
     const CUtensorMap* tk = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, 128);
@@ -756,14 +818,19 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     const size_t smem = 163840 + 4096 + 1792 + 128 + 1024;   // tiles + per-row vectors + key mask + barriers + slack
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    attn_bwd_dq_kernel<<<dim3((a->lq + 127) / 128, a->heads, a->batch), kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    const dim3 gq((a->lq + 127) / 128, a->heads, a->batch), gk((a->lk + 127) / 128, a->heads, a->batch);
+    if (drop) attn_bwd_dq_kernel<true><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    else attn_bwd_dq_kernel<false><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
     int rc = check_launch("shg_attn_bwd(dq)");
     if (rc) return rc;
-    attn_bwd_dkv_kernel<<<dim3((a->lk + 127) / 128, a->heads, a->batch), kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    if (drop) attn_bwd_dkv_kernel<true><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    else attn_bwd_dkv_kernel<false><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
     return check_launch("shg_attn_bwd(dkv)");
 }

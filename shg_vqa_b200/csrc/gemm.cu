@@ -30,6 +30,8 @@ struct GemmParams {
     __nv_bfloat16* preact;
     const __nv_bfloat16* mul_aux;
     int mul_mode;
+    float mul_scale;
+    DropCfg drop;
     int act, out_f32, accumulate;
     int splits, block_n, n_stages;
     int m_tiles, n_tiles, kb_total, kb_per_split;
@@ -150,7 +152,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                         for (int i = 0; i < 32; ++i) acc[i] *= gelu_erf_grad(av[i]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] = av[i] > 0.f ? acc[i] : 0.f;
+                        for (int i = 0; i < 32; ++i) acc[i] = av[i] > 0.f ? acc[i] * p.mul_scale : 0.f;
+                    }
+                }
+                if (p.drop.p > 0.f) {
+                    // nn.Dropout on the projection output, before the residual add (BertAttOutput / BertOutput /
+                    // decoder dropout1-3 and the decoder FFN's inner dropout)
+                    const uint32_t key = drop_key(__ldg(p.drop.seed), p.drop.salt), th = drop_thresh(p.drop.p);
+                    const float inv_keep = 1.0f / (1.0f - p.drop.p);
+                    const uint64_t base = (uint64_t)row * (uint64_t)p.n + col0;     // col0 is even
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const uint32_t kb = drop_pair(key, (uint32_t)((base + i) >> 1), th);
+                        acc[i] = (kb & 1u) ? acc[i] * inv_keep : 0.f;
+                        acc[i + 1] = (kb & 2u) ? acc[i + 1] * inv_keep : 0.f;
                     }
                 }
                 if (p.residual) {
@@ -583,6 +598,10 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     p.bias = a->bias, p.residual = (const __nv_bfloat16*)a->residual, p.ldr = a->ldr;
     p.preact = (__nv_bfloat16*)a->preact, p.act = a->act;
     p.mul_aux = (const __nv_bfloat16*)a->mul_aux, p.mul_mode = a->mul_aux ? a->mul_mode : 0;
+    p.mul_scale = a->mul_scale != 0.f ? a->mul_scale : 1.0f;
+    p.drop.p = a->dropout_seed ? a->dropout_p : 0.f, p.drop.salt = a->dropout_salt, p.drop.seed = a->dropout_seed;
+    SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_gemm: dropout_p=%f", (double)p.drop.p);
+    SHG_REQUIRE(p.drop.p == 0.f || (a->n % 2 == 0 && !accumulate), SHG_ESHAPE, "shg_gemm: dropout needs even N and a plain store");
     p.out_f32 = (a->flags & SHG_GEMM_OUT_F32) || accumulate, p.accumulate = accumulate;
     p.m_tiles = (a->m + BM - 1) / BM;
     // block_n: 0 = choose everything; low bits = tile width; | 1024 forces CTA-pair tiles (256 x bn), | 2048 forbids them

@@ -32,6 +32,16 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// v[0..8) *= keep/(1-p) for the 8 consecutive elements starting at (even) flat index idx
+__device__ __forceinline__ void drop8(float (&v)[8], uint32_t key, uint32_t th, float inv_keep, uint64_t idx) {
+#pragma unroll
+    for (int t = 0; t < 8; t += 2) {
+        const uint32_t kb = drop_pair(key, (uint32_t)((idx + t) >> 1), th);
+        v[t] = (kb & 1u) ? v[t] * inv_keep : 0.f;
+        v[t + 1] = (kb & 2u) ? v[t + 1] * inv_keep : 0.f;
+    }
+}
+
 // CH = 16-byte chunks of 8 elements per lane: n = 256 * CH  (768 -> 3, 1536 -> 6)
 template <int CH>
 __device__ __forceinline__ void row_stats(const float (&v)[CH][8], float inv_n, float eps, float& mean, float& rstd) {
@@ -106,9 +116,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ dxsum, int rows) {
+                     float* __restrict__ dbeta, float* __restrict__ dxsum, int rows,
+                     __nv_bfloat16* __restrict__ dx_drop, DropCfg out_drop, DropCfg in_drop) {
     constexpr int N = 256 * CH;
     __shared__ float red[kRowWarps][256 + 8];
+    uint32_t okey = 0, oth = 0, ikey = 0, ith = 0;
+    float oinv = 1.f, iinv = 1.f;
+    if (out_drop.p > 0.f) okey = drop_key(__ldg(out_drop.seed), out_drop.salt), oth = drop_thresh(out_drop.p), oinv = 1.f / (1.f - out_drop.p);
+    if (in_drop.p > 0.f) ikey = drop_key(__ldg(in_drop.seed), in_drop.salt), ith = drop_thresh(in_drop.p), iinv = 1.f / (1.f - in_drop.p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float ag[CH][8], ab[CH][8], ax[CH][8];
 #pragma unroll
@@ -133,6 +148,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g[j][i] += t[i];
             }
+            if (in_drop.p > 0.f) drop8(g[j], ikey, ith, iinv, (uint64_t)row * N + c);   // y = dropout(LN(x))
             load8(x + (size_t)row * N + c, xh[j]);
             if (residual) {
                 float t[8];
@@ -156,11 +172,15 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         for (int j = 0; j < CH; ++j) {
             float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                o[i] = rstd * (g[j][i] * gm[j][i] - s1 - xh[j][i] * s2);
-                ax[j][i] += o[i];
-            }
+            for (int i = 0; i < 8; ++i) o[i] = rstd * (g[j][i] * gm[j][i] - s1 - xh[j][i] * s2);
             store8(dx + (size_t)row * N + (j * 32 + lane) * 8, o);
+            if (out_drop.p > 0.f) {
+                // x = dropout(dense_out) + residual: the projection sees the masked, rescaled gradient
+                drop8(o, okey, oth, oinv, (uint64_t)row * N + (j * 32 + lane) * 8);
+                store8(dx_drop + (size_t)row * N + (j * 32 + lane) * 8, o);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ax[j][i] += o[i];
         }
     }
     // block reduction of the three column accumulators (one 256-column chunk at a time), then one atomic per
@@ -224,7 +244,7 @@ embed_ln_fwd_kernel(const float* __restrict__ word, const int64_t* __restrict__ 
                     const int64_t* __restrict__ type_ids, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
                     __nv_bfloat16* __restrict__ pre_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                    int rows, int seq_len) {
+                    int rows, int seq_len, DropCfg drop) {
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -269,6 +289,9 @@ embed_ln_fwd_kernel(const float* __restrict__ word, const int64_t* __restrict__ 
         load8(beta + c, b);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+        if (drop.p > 0.f)
+            drop8(o, drop_key(__ldg(drop.seed), drop.salt), drop_thresh(drop.p), 1.f / (1.f - drop.p),
+                  (uint64_t)row * N + c);
         store8(y + (size_t)row * N + c, o);
     }
 }
@@ -434,8 +457,10 @@ int shg_layernorm_fwd(const void* x, const void* residual, const float* gamma, c
 
 int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* residual, const float* gamma,
                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
-                      int rows, int n, void* stream) {
+                      int rows, int n, void* dx_drop, float out_p, uint32_t out_salt, float in_p, uint32_t in_salt,
+                      const uint32_t* seed, void* stream) {
     using namespace shg;
+    DropCfg od{(seed && dx_drop) ? out_p : 0.f, out_salt, seed}, id{seed ? in_p : 0.f, in_salt, seed};
     SHG_REQUIRE(n == 768 || n == 1536, SHG_ESHAPE, "shg_layernorm_bwd: width %d (768 or 1536 supported)", n);
     if (rows <= 0) return SHG_OK;
     int blocks = (rows + kRowWarps - 1) / kRowWarps;
@@ -444,11 +469,13 @@ int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void
     if (n == 768)
         layernorm_bwd_kernel<3><<<blocks, kRowThreads, 0, s>>>(
             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
-            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows);
+            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
+            (__nv_bfloat16*)dx_drop, od, id);
     else
         layernorm_bwd_kernel<6><<<blocks, kRowThreads, 0, s>>>(
             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
-            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows);
+            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
+            (__nv_bfloat16*)dx_drop, od, id);
     return check_launch("shg_layernorm_bwd");
 }
 
@@ -469,7 +496,8 @@ int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, voi
 
 int shg_embed_ln_fwd(const float* word, const int64_t* word_ids, const float* pos, const float* type,
                      const int64_t* type_ids, const float* gamma, const float* beta, float eps, void* y, void* pre,
-                     float* mean, float* rstd, int rows, int seq_len, int n, void* stream) {
+                     float* mean, float* rstd, int rows, int seq_len, int n, float drop_p, uint32_t drop_salt,
+                     const uint32_t* seed, void* stream) {
     using namespace shg;
     SHG_REQUIRE(n == 768, SHG_ESHAPE, "shg_embed_ln_fwd: width %d (768 supported)", n);
     SHG_REQUIRE((mean == nullptr) == (rstd == nullptr), SHG_EINVAL, "shg_embed_ln_fwd: mean and rstd go together");
@@ -477,7 +505,7 @@ int shg_embed_ln_fwd(const float* word, const int64_t* word_ids, const float* po
     const int blocks = (rows + kRowWarps - 1) / kRowWarps;
     embed_ln_fwd_kernel<3><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
         word, word_ids, pos, type, type_ids, gamma, beta, eps, (__nv_bfloat16*)y, (__nv_bfloat16*)pre, mean, rstd,
-        rows, seq_len);
+        rows, seq_len, DropCfg{seed ? drop_p : 0.f, drop_salt, seed});
     return check_launch("shg_embed_ln_fwd");
 }
 

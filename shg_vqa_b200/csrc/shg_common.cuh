@@ -264,6 +264,41 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return fmaf(x * 0.39894228040143267794f, e, phi_cdf);
 }
 
+// ---------------------------------------------------------------- dropout (training mode)
+// Counter-based Bernoulli mask: element `idx` of call site `salt` at step seed `seed` is kept iff a 16-bit slice of
+// a 32-bit integer hash of (seed, salt, idx >> 1) is >= p * 65536.  Forward and backward kernels regenerate the
+// same mask from the same three numbers — nothing is stored.  (The reference draws from torch's Philox stream,
+// nn.Dropout at lxrt/modeling_capsbert.py:311,339,381,429,483 and lxrt/transformer.py:196-204; the streams cannot
+// match, the distribution does: iid keep probability 1-p, survivors scaled by 1/(1-p).)
+struct DropCfg {
+    float p;                 // 0 = off
+    uint32_t salt;
+    const uint32_t* seed;    // device scalar, advanced every step outside the CUDA graph
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t salt) { return mix32(seed ^ (salt * 0x9E3779B9u)); }
+__device__ __forceinline__ uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+// keep-bits of the element pair (2*pair, 2*pair+1): bit 0 / bit 1
+__device__ __forceinline__ uint32_t drop_pair(uint32_t key, uint32_t pair, uint32_t thresh) {
+    const uint32_t h = mix32(key + pair * 0x85ebca6bu);
+    return ((h & 0xffffu) >= thresh ? 1u : 0u) | ((h >> 16) >= thresh ? 2u : 0u);
+}
+// AND-mask for a packed bf16x2 of that pair (dropped lanes zeroed)
+__device__ __forceinline__ uint32_t drop_pair_mask(uint32_t key, uint32_t pair, uint32_t thresh) {
+    const uint32_t h = mix32(key + pair * 0x85ebca6bu);
+    return ((h & 0xffffu) >= thresh ? 0x0000ffffu : 0u) | ((h >> 16) >= thresh ? 0xffff0000u : 0u);
+}
+__device__ __forceinline__ bool drop_keep(uint32_t key, uint64_t idx, uint32_t thresh) {
+    return (drop_pair(key, (uint32_t)(idx >> 1), thresh) >> (idx & 1)) & 1u;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -51,6 +51,13 @@ class Engine:
         self.nl, self.nr, self.nx, self.nd = l_layers, r_layers, x_layers, d_layers
         self.dev = store.device
         self._build_handles()
+        # training-mode dropout (reference probabilities: hidden / attention-prob 0.1, lxrt/modeling_capsbert.py:216-217;
+        # decoders and action-query embedding 0.15, param.py:152-153; relation-query embedding 0.1, :302).  Off by
+        # default: parity is stated for eval()/p=0 semantics; the trainer switches it on for training runs.
+        self.dropout_on = False
+        self.p_hidden, self.p_attn, self.p_dec, self.p_emb, self.p_relq, self.p_actq = 0.1, 0.1, 0.15, 0.1, 0.1, 0.15
+        self.drop_seed = torch.zeros(1, device=self.dev, dtype=torch.int32) if self.dev.type == "cuda" else None
+        self._salt, self._training = 0, False
         # Independent sub-graphs run on side streams so that the small-M launches (40-token language side,
         # 48-query action decoder) fill SMs the 148-CTA persistent kernels of the visual side leave idle.
         self.use_streams = self.dev.type == "cuda"
@@ -198,6 +205,14 @@ class Engine:
         o = (self.n_act + self.n_rel) * H
         ops.to_bf16(st.p("hgq_encoder.cls_token").view(-1), out=self.tok[o:o + H])
 
+    def _drop(self, p, active=True):
+        """(p, fresh call-site salt, seed) for a dropout site of this forward, or None.  Sites are live in every
+        train-mode forward — also in the forward-only LXRT cross layers, as in the reference's model.train()."""
+        if not (active and self._training and self.dropout_on and p > 0):
+            return None
+        self._salt += 1
+        return (p, self._salt, self.drop_seed)
+
     # ------------------------------------------------------------------ primitive fwd/bwd helpers
     def _wgrad(self, lin, dy, x, bias=True):
         """dW += dy^T x (split-K fp32 atomics into the flat gradient buffer), db += colsum(dy) — on the wgrad
@@ -223,43 +238,54 @@ class Engine:
         with torch.cuda.stream(self.sw):
             ops.colsum_accum(dy, gb)
 
-    def _ffn_fwd(self, f1, f2, ln, a, save, act="gelu", eps=EPS_BERT, addend=None):
+    def _ffn_fwd(self, f1, f2, ln, a, save, act="gelu", eps=EPS_BERT, addend=None, p_out=0.0, p_inner=0.0):
         pre = torch.empty(a.shape[0], f1.w.shape[0], device=self.dev, dtype=BF16) if (save and act == "gelu") else None
-        h = ops.gemm(a, f1.w, bias=f1.b, act=act, preact=pre)
-        s2 = ops.gemm(h, f2.w, bias=f2.b, residual=a)
+        d_in, d_out = self._drop(p_inner), self._drop(p_out)
+        h = ops.gemm(a, f1.w, bias=f1.b, act=act, preact=pre, drop=d_in)
+        s2 = ops.gemm(h, f2.w, bias=f2.b, residual=a, drop=d_out)
         y, y2, m, r = ops.layernorm_fwd(s2, ln.g, ln.b, eps, addend=addend, save_stats=save)
-        return y, y2, (a, pre, h, s2, m, r)
+        return y, y2, (a, pre, h, s2, m, r, d_in, d_out)
+
+    def _ln_bwd_split(self, dy, x, ln, m, r, drop, dy2=None, dxsum=None):
+        """LayerNorm backward of x = dropout(dense) + residual → (gradient for the residual branch, gradient for
+        the projection); identical tensors when the site had no dropout."""
+        res = ops.layernorm_bwd(dy, x, ln.g, m, r, ln.gg, ln.gb, dy2=dy2, dxsum=dxsum, out_drop=drop)
+        return res if drop is not None else (res, res)
 
     def _ffn_bwd(self, f1, f2, ln, saved, dy, dy2=None, act="gelu"):
-        a, pre, h, s2, m, r = saved
-        ds2 = ops.layernorm_bwd(dy, s2, ln.g, m, r, ln.gg, ln.gb, dy2=dy2, dxsum=f2.gb)
-        self._wgrad(f2, ds2, h, bias=False)
+        a, pre, h, s2, m, r, d_in, d_out = saved
+        ds2, ds2d = self._ln_bwd_split(dy, s2, ln, m, r, d_out, dy2=dy2, dxsum=f2.gb)
+        self._wgrad(f2, ds2d, h, bias=False)
         if act == "gelu":
-            dpre = ops.gemm(ds2, f2.w, b_t=True, mul_aux=pre, mul_mode="gelu_grad")
+            dpre = ops.gemm(ds2d, f2.w, b_t=True, mul_aux=pre, mul_mode="gelu_grad")
         else:
-            dpre = ops.gemm(ds2, f2.w, b_t=True, mul_aux=h, mul_mode="relu_mask")
+            # h went through ReLU and (decoders) dropout: h > 0 marks "active and kept"
+            dpre = ops.gemm(ds2d, f2.w, b_t=True, mul_aux=h, mul_mode="relu_mask",
+                            mul_scale=1.0 / (1.0 - d_in[0]) if d_in is not None else 1.0)
         self._wgrad(f1, dpre, a)
         return ops.gemm(dpre, f1.w, b_t=True, residual=ds2)      # d a  (FFN path + residual path)
 
     # ------------------------------------------------------------------ BertLayer (L, R)
     def _bert_fwd(self, L, x, B, n, key_mask, save):
         qkv = ops.gemm(x, L["qkv"].w, bias=L["qkv"].b)
+        da = self._drop(self.p_attn)
         ctx, lse = ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, n, n, key_mask=key_mask,
-                                     save_lse=save)
-        s1 = ops.gemm(ctx, L["o"].w, bias=L["o"].b, residual=x)
+                                     save_lse=save, drop=da)
+        d1 = self._drop(self.p_hidden)
+        s1 = ops.gemm(ctx, L["o"].w, bias=L["o"].b, residual=x, drop=d1)
         a, _, m1, r1 = ops.layernorm_fwd(s1, L["ln1"].g, L["ln1"].b, EPS_BERT, save_stats=save)
-        y, _, ffn = self._ffn_fwd(L["f1"], L["f2"], L["ln2"], a, save)
-        return y, (x, qkv, ctx, lse, s1, m1, r1, ffn)
+        y, _, ffn = self._ffn_fwd(L["f1"], L["f2"], L["ln2"], a, save, p_out=self.p_hidden)
+        return y, (x, qkv, ctx, lse, s1, m1, r1, ffn, d1, da)
 
     def _bert_bwd(self, L, saved, dy, B, n, key_mask, need_dx=True):
-        x, qkv, ctx, lse, s1, m1, r1, ffn = saved
+        x, qkv, ctx, lse, s1, m1, r1, ffn, d1, d_att = saved
         da = self._ffn_bwd(L["f1"], L["f2"], L["ln2"], ffn, dy)
-        ds1 = ops.layernorm_bwd(da, s1, L["ln1"].g, m1, r1, L["ln1"].gg, L["ln1"].gb, dxsum=L["o"].gb)
-        self._wgrad(L["o"], ds1, ctx, bias=False)
-        dctx = ops.gemm(ds1, L["o"].w, b_t=True)
+        ds1, ds1d = self._ln_bwd_split(da, s1, L["ln1"], m1, r1, d1, dxsum=L["o"].gb)
+        self._wgrad(L["o"], ds1d, ctx, bias=False)
+        dctx = ops.gemm(ds1d, L["o"].w, b_t=True)
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, dctx, lse, dqkv[:, :H], dqkv[:, H:2 * H],
-                          dqkv[:, 2 * H:], B, n, n, key_mask=key_mask)
+                          dqkv[:, 2 * H:], B, n, n, key_mask=key_mask, drop=d_att)
         self._wgrad(L["qkv"], dqkv, x)
         if not need_dx:
             return None
@@ -271,33 +297,39 @@ class Engine:
         qkv_l = ops.gemm(lang, q.w, bias=q.b)
         qkv_v = ops.gemm(visn, q.w, bias=q.b)
         # one attention block, both directions (lxrt/modeling_capsbert.py:643-644)
+        dal, dav = self._drop(self.p_attn), self._drop(self.p_attn)
         ctx_l, lse_l = ops.attention_fwd(qkv_l[:, :H], qkv_v[:, H:2 * H], qkv_v[:, 2 * H:], B, nl, nv,
-                                         key_mask=visn_kmask, save_lse=save)
+                                         key_mask=visn_kmask, save_lse=save, drop=dal)
         ctx_v, lse_v = ops.attention_fwd(qkv_v[:, :H], qkv_l[:, H:2 * H], qkv_l[:, 2 * H:], B, nv, nl,
-                                         key_mask=lang_kmask, save_lse=save)
-        s_l = ops.gemm(ctx_l, X["o"].w, bias=X["o"].b, residual=lang)
-        s_v = ops.gemm(ctx_v, X["o"].w, bias=X["o"].b, residual=visn)
+                                         key_mask=lang_kmask, save_lse=save, drop=dav)
+        dl, dv_ = self._drop(self.p_hidden), self._drop(self.p_hidden)
+        s_l = ops.gemm(ctx_l, X["o"].w, bias=X["o"].b, residual=lang, drop=dl)
+        s_v = ops.gemm(ctx_v, X["o"].w, bias=X["o"].b, residual=visn, drop=dv_)
         a_l, _, ml, rl = ops.layernorm_fwd(s_l, X["lno"].g, X["lno"].b, EPS_BERT, save_stats=save)
         a_v, _, mv, rv = ops.layernorm_fwd(s_v, X["lno"].g, X["lno"].b, EPS_BERT, save_stats=save)
-        y_l, _, ffn_l = self._ffn_fwd(X["lf1"], X["lf2"], X["lln"], a_l, save)
-        y_v, _, ffn_v = self._ffn_fwd(X["vf1"], X["vf2"], X["vln"], a_v, save)
-        return y_l, y_v, (lang, visn, qkv_l, qkv_v, ctx_l, lse_l, ctx_v, lse_v, s_l, ml, rl, s_v, mv, rv, ffn_l, ffn_v)
+        y_l, _, ffn_l = self._ffn_fwd(X["lf1"], X["lf2"], X["lln"], a_l, save, p_out=self.p_hidden)
+        y_v, _, ffn_v = self._ffn_fwd(X["vf1"], X["vf2"], X["vln"], a_v, save, p_out=self.p_hidden)
+        return y_l, y_v, (lang, visn, qkv_l, qkv_v, ctx_l, lse_l, ctx_v, lse_v, s_l, ml, rl, s_v, mv, rv, ffn_l, ffn_v,
+                          dl, dv_, dal, dav)
 
     def _cross_bwd(self, X, saved, dy_l, dy_v, B, nl, nv, lang_kmask, visn_kmask):
-        lang, visn, qkv_l, qkv_v, ctx_l, lse_l, ctx_v, lse_v, s_l, ml, rl, s_v, mv, rv, ffn_l, ffn_v = saved
+        (lang, visn, qkv_l, qkv_v, ctx_l, lse_l, ctx_v, lse_v, s_l, ml, rl, s_v, mv, rv, ffn_l, ffn_v,
+         dl, dv_, dal, dav) = saved
         da_l = self._ffn_bwd(X["lf1"], X["lf2"], X["lln"], ffn_l, dy_l)
         da_v = self._ffn_bwd(X["vf1"], X["vf2"], X["vln"], ffn_v, dy_v)
-        ds_l = ops.layernorm_bwd(da_l, s_l, X["lno"].g, ml, rl, X["lno"].gg, X["lno"].gb, dxsum=X["o"].gb)
-        ds_v = ops.layernorm_bwd(da_v, s_v, X["lno"].g, mv, rv, X["lno"].gg, X["lno"].gb, dxsum=X["o"].gb)
-        self._wgrad(X["o"], ds_l, ctx_l, bias=False)
-        self._wgrad(X["o"], ds_v, ctx_v, bias=False)
-        dctx_l = ops.gemm(ds_l, X["o"].w, b_t=True)
-        dctx_v = ops.gemm(ds_v, X["o"].w, b_t=True)
+        ds_l, ds_ld = self._ln_bwd_split(da_l, s_l, X["lno"], ml, rl, dl, dxsum=X["o"].gb)
+        ds_v, ds_vd = self._ln_bwd_split(da_v, s_v, X["lno"], mv, rv, dv_, dxsum=X["o"].gb)
+        self._wgrad(X["o"], ds_ld, ctx_l, bias=False)
+        self._wgrad(X["o"], ds_vd, ctx_v, bias=False)
+        dctx_l = ops.gemm(ds_ld, X["o"].w, b_t=True)
+        dctx_v = ops.gemm(ds_vd, X["o"].w, b_t=True)
         dqkv_l, dqkv_v = torch.empty_like(qkv_l), torch.empty_like(qkv_v)
         ops.attention_bwd(qkv_l[:, :H], qkv_v[:, H:2 * H], qkv_v[:, 2 * H:], ctx_l, dctx_l, lse_l,
-                          dqkv_l[:, :H], dqkv_v[:, H:2 * H], dqkv_v[:, 2 * H:], B, nl, nv, key_mask=visn_kmask)
+                          dqkv_l[:, :H], dqkv_v[:, H:2 * H], dqkv_v[:, 2 * H:], B, nl, nv, key_mask=visn_kmask,
+                          drop=dal)
         ops.attention_bwd(qkv_v[:, :H], qkv_l[:, H:2 * H], qkv_l[:, 2 * H:], ctx_v, dctx_v, lse_v,
-                          dqkv_v[:, :H], dqkv_l[:, H:2 * H], dqkv_l[:, 2 * H:], B, nv, nl, key_mask=lang_kmask)
+                          dqkv_v[:, :H], dqkv_l[:, H:2 * H], dqkv_l[:, 2 * H:], B, nv, nl, key_mask=lang_kmask,
+                          drop=dav)
         self._wgrad(X["qkv"], dqkv_l, lang)
         self._wgrad(X["qkv"], dqkv_v, visn)
         d_lang = ops.gemm(dqkv_l, X["qkv"].w, b_t=True, residual=ds_l)
@@ -308,37 +340,42 @@ class Engine:
     def _dec_fwd(self, D, tgt, tgt_p, qpos, k_mem, v_mem, B, nq, per, save, first):
         qk = ops.gemm(tgt_p, D["sa_qk"].w, bias=D["sa_qk"].b)
         v = ops.gemm(tgt, D["sa_v"].w, bias=D["sa_v"].b)
-        sa, lse1 = ops.attention_fwd(qk[:, :H], qk[:, H:], v, B, nq, nq, frames=(per, per), save_lse=save)
-        s1 = ops.gemm(sa, D["sa_o"].w, bias=D["sa_o"].b, residual=tgt)
+        da1, da2 = self._drop(self.p_dec), self._drop(self.p_dec)
+        sa, lse1 = ops.attention_fwd(qk[:, :H], qk[:, H:], v, B, nq, nq, frames=(per, per), save_lse=save, drop=da1)
+        d1, d2 = self._drop(self.p_dec), self._drop(self.p_dec)
+        s1 = ops.gemm(sa, D["sa_o"].w, bias=D["sa_o"].b, residual=tgt, drop=d1)
         t1, t1p, m1, r1 = ops.layernorm_fwd(s1, D["n1"].g, D["n1"].b, EPS_DETR, addend=qpos, save_stats=save)
         cq = ops.gemm(t1p, D["ca_q"].w, bias=D["ca_q"].b)
-        ca, lse2 = ops.attention_fwd(cq, k_mem, v_mem, B, nq, 393, save_lse=save)
-        s2 = ops.gemm(ca, D["ca_o"].w, bias=D["ca_o"].b, residual=t1)
+        ca, lse2 = ops.attention_fwd(cq, k_mem, v_mem, B, nq, 393, save_lse=save, drop=da2)
+        s2 = ops.gemm(ca, D["ca_o"].w, bias=D["ca_o"].b, residual=t1, drop=d2)
         t2, _, m2, r2 = ops.layernorm_fwd(s2, D["n2"].g, D["n2"].b, EPS_DETR, save_stats=save)
-        t3, t3p, ffn = self._ffn_fwd(D["l1"], D["l2"], D["n3"], t2, save, act="relu", eps=EPS_DETR, addend=qpos)
-        return t3, t3p, (tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, ffn, first)
+        t3, t3p, ffn = self._ffn_fwd(D["l1"], D["l2"], D["n3"], t2, save, act="relu", eps=EPS_DETR, addend=qpos,
+                                     p_out=self.p_dec, p_inner=self.p_dec)
+        return t3, t3p, (tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, ffn, first, d1, d2,
+                         da1, da2)
 
     def _dec_bwd(self, D, saved, dt3, dt3p, dqpos, k_mem, v_mem, dk_mem, dv_mem, B, nq, per):
-        tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, ffn, first = saved
+        (tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, ffn, first, d1, d2,
+         da1, da2) = saved
         if dt3p is not None:
             self._acc(dqpos, dt3p)
         dt2 = self._ffn_bwd(D["l1"], D["l2"], D["n3"], ffn, dt3, dy2=dt3p, act="relu")
-        ds2 = ops.layernorm_bwd(dt2, s2, D["n2"].g, m2, r2, D["n2"].gg, D["n2"].gb, dxsum=D["ca_o"].gb)
-        self._wgrad(D["ca_o"], ds2, ca, bias=False)
-        dca = ops.gemm(ds2, D["ca_o"].w, b_t=True)
+        ds2, ds2d = self._ln_bwd_split(dt2, s2, D["n2"], m2, r2, d2, dxsum=D["ca_o"].gb)
+        self._wgrad(D["ca_o"], ds2d, ca, bias=False)
+        dca = ops.gemm(ds2d, D["ca_o"].w, b_t=True)
         dcq = torch.empty_like(cq)
-        ops.attention_bwd(cq, k_mem, v_mem, ca, dca, lse2, dcq, dk_mem, dv_mem, B, nq, 393)
+        ops.attention_bwd(cq, k_mem, v_mem, ca, dca, lse2, dcq, dk_mem, dv_mem, B, nq, 393, drop=da2)
         self._wgrad(D["ca_q"], dcq, t1p)
         dt1p = ops.gemm(dcq, D["ca_q"].w, b_t=True)
         if getattr(self, "_trace", None) is not None:
             self._trace.append(("dt1p", dt1p.float().cpu(), dcq.float().cpu()))
         self._acc(dqpos, dt1p)
-        ds1 = ops.layernorm_bwd(ds2, s1, D["n1"].g, m1, r1, D["n1"].gg, D["n1"].gb, dy2=dt1p, dxsum=D["sa_o"].gb)
-        self._wgrad(D["sa_o"], ds1, sa, bias=False)
-        dsa = ops.gemm(ds1, D["sa_o"].w, b_t=True)
+        ds1, ds1d = self._ln_bwd_split(ds2, s1, D["n1"], m1, r1, d1, dy2=dt1p, dxsum=D["sa_o"].gb)
+        self._wgrad(D["sa_o"], ds1d, sa, bias=False)
+        dsa = ops.gemm(ds1d, D["sa_o"].w, b_t=True)
         dqk, dv = torch.empty_like(qk), torch.empty_like(v)
         ops.attention_bwd(qk[:, :H], qk[:, H:], v, sa, dsa, lse1, dqk[:, :H], dqk[:, H:], dv, B, nq, nq,
-                          frames=(per, per))
+                          frames=(per, per), drop=da1)
         if getattr(self, "_trace", None) is not None:
             self._trace_self = getattr(self, "_trace_self", [])
             self._trace_self.append(tuple(t.float().cpu() for t in (qk, v, dsa, dqk, dv, sa)))
@@ -416,20 +453,22 @@ class Engine:
         ops.copy3d(dcat, d_first, B, 1, H, 2 * H, 0, n_first * H, 0, accumulate=True)
         ops.copy3d(dcat[:, H:], d_second, B, 1, H, 2 * H, 0, n_second * H, 0, accumulate=True)
 
-    def _hg_embed_fwd(self, E, seg_ids, B, nq, save):
+    def _hg_embed_fwd(self, E, seg_ids, B, nq, save, p_drop=0.0):
         rows = B * nq
         y = torch.empty(rows, H, device=self.dev, dtype=BF16)
         pre = torch.empty_like(y) if save else None
         mean = torch.empty(rows, device=self.dev, dtype=torch.float32) if save else None
         rstd = torch.empty_like(mean) if save else None
+        d = self._drop(p_drop)
         ops.call("shg_embed_ln_fwd", ops.ptr(E["word"]), None, None, ops.ptr(E["type"]), ops.ptr(seg_ids),
                  ops.ptr(E["ln"].g), ops.ptr(E["ln"].b), EPS_BERT, ops.ptr(y), ops.ptr(pre), ops.ptr(mean),
-                 ops.ptr(rstd), rows, nq, H, ops.stream())
-        return y, (seg_ids, pre, mean, rstd)
+                 ops.ptr(rstd), rows, nq, H, d[0] if d else 0.0, d[1] if d else 0, ops.ptr(d[2]) if d else None,
+                 ops.stream())
+        return y, (seg_ids, pre, mean, rstd, d)
 
     def _hg_embed_bwd(self, E, saved, dq, B, nq):
-        seg_ids, pre, mean, rstd = saved
-        de = ops.layernorm_bwd(dq, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
+        seg_ids, pre, mean, rstd, d = saved
+        de = ops.layernorm_bwd(dq, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb, in_drop=d)
         # word table is used whole (no lookup → no padding mask); frame-id table is nn.Embedding(padding_idx=0)
         ops.call("shg_embed_scatter_bwd", ops.ptr(de), None, ops.ptr(seg_ids), ops.ptr(E["gword"]), -1, None, -1,
                  ops.ptr(E["gtype"]), 0, B * nq, nq, H, ops.stream())
@@ -448,10 +487,13 @@ class Engine:
         mean = torch.empty(B * nl, device=self.dev, dtype=torch.float32) if save else None
         rstd = torch.empty_like(mean) if save else None
         E = self.emb
+        self._salt, self._training = 0, bool(train)
+        d_emb = self._drop(self.p_emb)
         ops.call("shg_embed_ln_fwd", ops.ptr(E["word"]), ops.ptr(ids), ops.ptr(E["pos"]), ops.ptr(E["type"]),
                  ops.ptr(seg), ops.ptr(E["ln"].g), ops.ptr(E["ln"].b), EPS_BERT, ops.ptr(lang), ops.ptr(pre),
-                 ops.ptr(mean), ops.ptr(rstd), B * nl, nl, H, ops.stream())
-        ctx["emb"] = (ids, seg, pre, mean, rstd, nl)
+                 ops.ptr(mean), ops.ptr(rstd), B * nl, nl, H, d_emb[0] if d_emb else 0.0, d_emb[1] if d_emb else 0,
+                 ops.ptr(d_emb[2]) if d_emb else None, ops.stream())
+        ctx["emb"] = (ids, seg, pre, mean, rstd, nl, d_emb)
         # additive key mask (1-mask)*-10000 (lxrt/modeling_capsbert.py:1826-1834); the visual mask is all zeros (:1836)
         kmask = ((1.0 - inp["input_mask"].to(torch.float32)) * -10000.0).contiguous()
         ctx["kmask"] = kmask
@@ -491,11 +533,13 @@ class Engine:
         if not hgqa:
             return out, ctx
         nq_r, nq_a = self.T * self.n_rel, self.T * self.n_act
-        rel_q, ctx["rel_q"] = self._hg_embed_fwd(self.rel_q, inp["rel_segment_ids"].reshape(-1), B, nq_r, save)
+        rel_q, ctx["rel_q"] = self._hg_embed_fwd(self.rel_q, inp["rel_segment_ids"].reshape(-1), B, nq_r, save,
+                                                 self.p_relq)
         rel_out, ctx["rel_dec"] = self._decoder_fwd(self.rel_dec, rel_q, kv_mem, 0, B, nq_r, self.n_rel, save)
         out["rel_logits"], ctx["rel_head"] = self._head_fwd(self.class_embed, rel_out, save)
         with self._on(self.s2):
-            act_q, ctx["act_q"] = self._hg_embed_fwd(self.act_q, inp["act_segment_ids"].reshape(-1), B, nq_a, save)
+            act_q, ctx["act_q"] = self._hg_embed_fwd(self.act_q, inp["act_segment_ids"].reshape(-1), B, nq_a, save,
+                                                     self.p_actq)
             act_out, ctx["act_dec"] = self._decoder_fwd(self.act_dec, act_q, kv_mem, self.nd, B, nq_a, self.n_act,
                                                         save)
             out["act_logits"], ctx["act_head"] = self._head_fwd(self.action_embed, act_out, save)
@@ -593,9 +637,9 @@ class Engine:
             d_lang = ctx["d_lang_l"]
             for i in reversed(range(self.nl)):
                 d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
-            ids, seg, pre, mean, rstd, _ = ctx["emb"]
+            ids, seg, pre, mean, rstd, _, d_emb = ctx["emb"]
             E = self.emb
-            de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb)
+            de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb, in_drop=d_emb)
             ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
                      ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
         d_visn = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True)

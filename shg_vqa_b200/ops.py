@@ -23,7 +23,8 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, preact=None, mul_aux=None,
-         mul_mode=None, out=None, out_f32=False, accumulate=False, splits=0, block_n=0):
+         mul_mode=None, mul_scale=1.0, drop=None, out=None, out_f32=False, accumulate=False, splits=0, block_n=0):
+    # drop = (p, salt, seed_tensor) enables training-mode dropout on the output (before the residual add)
     """D = epilogue(A . B^T).  a: [M,K] (or stored [K,M] with a_t), b: [N,K] (or stored [K,N] with b_t); bf16."""
     require_device(a)
     assert a.dtype == BF16 and b.dtype == BF16
@@ -55,15 +56,22 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
     args.act = ACT[act]
     if mul_aux is not None:
         assert mul_aux.dtype == BF16 and _ld(mul_aux) == _ld(out) and mul_aux.shape == out.shape
-    args.mul_aux, args.mul_mode = ptr(mul_aux), MUL[mul_mode]
+    args.mul_aux, args.mul_mode, args.mul_scale = ptr(mul_aux), MUL[mul_mode], mul_scale
+    if drop is not None and drop[0] > 0:
+        args.dropout_p, args.dropout_salt, args.dropout_seed = drop[0], drop[1], ptr(drop[2])
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
     args.splits, args.block_n = splits, (block_n | _PAIR_FLAG if block_n == 0 and _PAIR_FLAG else block_n)
     call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k, "%dx%dx%d %s%s%s" % (m, n, k, "T" if a_t else "N", "T" if b_t else "N", " acc" if accumulate else "")))
     return out
 
 
+def _set_drop(a, drop):
+    if drop is not None and drop[0] > 0:
+        a.dropout_p, a.dropout_salt, a.dropout_seed = drop[0], drop[1], ptr(drop[2])
+
+
 def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, frames=None, out=None,
-                  save_lse=False):
+                  save_lse=False, drop=None):
     """q [batch*lq, >=heads*64], k/v [batch*lk, ...] bf16 views (row stride = ld, unit column stride).
     key_mask: fp32 [batch, lk] additive.  frames=(q_per_frame, k_per_frame) selects the block-causal mask."""
     require_device(q)
@@ -81,12 +89,13 @@ def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, 
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
     a.o_f32, a.ldof = ptr(o32), heads * 64
+    _set_drop(a, drop)
     call("shg_attn_fwd", a, stream(), work=("tensor", 4.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
     return out, (lse, o32) if save_lse else None
 
 
 def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, scale=0.125, key_mask=None,
-                  frames=None):
+                  frames=None, drop=None):
     """Writes dq/dk/dv (bf16 views with the same head layout as q/k/v).  `lse` is what attention_fwd returned
     with save_lse: (log-sum-exp, fp32 O); a bare lse tensor selects the two-sweep delta."""
     require_device(q)
@@ -104,6 +113,7 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     a.key_mask = ptr(key_mask)
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
     a.o_f32, a.ldof = ptr(o32), (o32.stride(0) if o32 is not None else 0)
+    _set_drop(a, drop)
     call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
 
 
@@ -121,14 +131,21 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0
     return y, y2, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dy2=None, residual=None, dxsum=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dy2=None, residual=None, dxsum=None, out_drop=None,
+                  in_drop=None):
+    """out_drop / in_drop = (p, salt, seed_tensor).  With out_drop returns (dx, dx_drop)."""
     require_device(dy)
     rows, n = x.shape
     dx = torch.empty_like(x)
+    od = out_drop if (out_drop is not None and out_drop[0] > 0) else None
+    idr = in_drop if (in_drop is not None and in_drop[0] > 0) else None
+    dxd = torch.empty_like(x) if od is not None else None
+    seed = od[2] if od is not None else (idr[2] if idr is not None else None)
     call("shg_layernorm_bwd", ptr(dy), ptr(dy2), ptr(x), ptr(residual), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx),
-         ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, stream(),
+         ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, ptr(dxd), od[0] if od else 0.0, od[1] if od else 0,
+         idr[0] if idr else 0.0, idr[1] if idr else 0, ptr(seed), stream(),
          work=("hbm", 2.0 * rows * n * (3 + (dy2 is not None) + (residual is not None)), "%dx%d" % (rows, n)))
-    return dx
+    return (dx, dxd) if od is not None else dx
 
 
 def colsum_accum(x, out):

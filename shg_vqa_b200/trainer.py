@@ -78,7 +78,7 @@ def shard_seed(base_seed, rank):
 class HotPathTrainer:
     def __init__(self, device, task="hgqa", n_answers=171, n_rel_cls=457, n_act_cls=158, lr=1e-5, t_total=-1,
                  warmup=0.1, weight_decay=0.01, max_grad_norm=5.0, eos_coef=0.1, world_size=1, process_group=None,
-                 live=live_in_hgqa_training):
+                 live=live_in_hgqa_training, dropout=False, dropout_seed=0, rank=0):
         self.device = torch.device(device)
         self.key_shapes = build_key_shapes(task, n_answers, n_rel_cls, n_act_cls)
         self.store = ParamStore(self.key_shapes, self.device, live=live)
@@ -94,6 +94,12 @@ class HotPathTrainer:
         self.lr_dev = torch.zeros(1, device=self.device, dtype=torch.float32)   # device-resident lr (graph-safe)
         self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else None
         self.graph = None
+        # training-mode dropout (the reference trains with model.train(): hidden/attention 0.1, decoders 0.15).
+        # Masks are counter-based functions of (step seed, call site, element); the seed lives on the device and
+        # is advanced at the start of every step (inside the captured graph too), and differs per rank.
+        self.engine.dropout_on = bool(dropout)
+        if self.engine.drop_seed is not None:
+            self.engine.drop_seed.fill_((dropout_seed + 1000003 * rank) & 0x7fffffff)
 
     # ------------------------------------------------------------------ weights
     def init_weights(self, seed=9595):
@@ -197,7 +203,12 @@ class HotPathTrainer:
         all_reduce_live_grads(self.store, self.world_size, self.pg)
 
     # ------------------------------------------------------------------ steps
+    def _advance_seed(self):
+        if self.engine.dropout_on:
+            self.engine.drop_seed.add_(1)
+
     def train_step(self, inp, batch, lr_on_device=False):
+        self._advance_seed()
         out, ctx = self.engine.forward(inp, train=True)
         scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, batch)
         self.engine.backward(ctx, d_hg, d_rel, d_act)
@@ -236,6 +247,7 @@ class HotPathTrainer:
             # data-parallel: [forward + loss + first half of backward] | async NCCL all-reduce of the gradients that
             # are already final | [second half of backward] | all-reduce of the rest | [optimiser]
             with torch.cuda.graph(self.graph):
+                self._advance_seed()
                 out, ctx = self.engine.forward(self.static_inp, train=True)
                 scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, self.static_batch)
                 self.engine.backward_late_params(ctx, d_hg, d_rel, d_act)
