@@ -12,7 +12,7 @@
 namespace shg {
 
 constexpr int kHeadDim = 64;
-constexpr int kAttnThreads = 256;
+constexpr int kAttnThreads = 512;   // 16 warps: four threads per query row, each a quarter of the key chunks
 
 struct AttnParams {
     __nv_bfloat16* o;
@@ -37,7 +37,8 @@ __device__ __forceinline__ uint32_t attn_row_pair0(int b, int heads, int h, int 
     return (uint32_t)(((size_t)b * heads + h) * lq + q) * (uint32_t)(((lk + 31) & ~31) >> 1);
 }
 
-// 256 threads: thread (row, half) owns query row `row` of the tile and one half of the key chunks.
+// 512 threads: thread (row, quad) owns query row `row` of the tile and one quarter of the key chunks (16 warps keep
+// four in flight per scheduler: the softmax is latency-bound — tcgen05.ld, ex2, pack, st.shared chains).
 template <bool HAS_KMASK, bool DROP>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -49,8 +50,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     uint8_t* sP = smem;                 // aliases Q/K once S is complete: blocks of 128 x 128 B
     uint8_t* sV = smem + p.v_off;
     float* s_kmask = reinterpret_cast<float*>(sV + p.n_kbox * 8192);   // [448] additive key mask * log2(e)
-    float* s_red = s_kmask + 448;                                       // [2][128] row max, then row sum
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 256);
+    float* s_red = s_kmask + 448;                                       // [4][128] row max, then row sum
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 512);
     uint64_t* bar_qk = bars;
     uint64_t* bar_v = bars + 1;
     uint64_t* bar_s = bars + 2;
@@ -102,14 +103,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     __syncwarp();
 
     // ---------------------------------------------------------------- softmax in the log2 domain
-    const int row = (warp & 3) * 32 + lane, half = warp >> 2;   // warp w may touch TMEM lanes [32(w%4), +32)
+    const int row = (warp & 3) * 32 + lane, quad = warp >> 2;   // warp w may touch TMEM lanes [32(w%4), +32)
     const int q = q0 + row;
     const uint32_t t_row = tmem + (uint32_t((warp & 3) * 32) << 16);
     // keys < k_lim are visible to this row (block-causal: frames <= the query's frame)
     const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
     const float c1 = p.scale * 1.4426950408889634f;
     const int n_ch = p.lk32 >> 5;
-    const int ch0 = half == 0 ? 0 : (n_ch + 1) >> 1, ch1 = half == 0 ? (n_ch + 1) >> 1 : n_ch;
+    // warps whose 32 query rows lie beyond lq (last tile of 393 = 3 x 128 + 9) skip the softmax: their P rows only
+    // feed O rows that are never stored
+    const bool rows_live = q0 + (warp & 3) * 32 < p.lq;
+    const int ch0 = (n_ch * quad) >> 2, ch1 = rows_live ? (n_ch * (quad + 1)) >> 2 : ch0;
 
     mbar_wait(bar_s, 0);
     tc_fence_after();
@@ -134,9 +138,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
     }
     if (!HAS_KMASK) mx *= c1;    // scale > 0: the max commutes with the scaling
-    s_red[half * 128 + row] = mx;
+    s_red[quad * 128 + row] = mx;
     __syncthreads();
-    mx = fmaxf(s_red[row], s_red[128 + row]);
+    mx = fmaxf(fmaxf(s_red[row], s_red[128 + row]), fmaxf(s_red[256 + row], s_red[384 + row]));
     if (mx == -INFINITY) mx = 0.f;
     __syncthreads();             // s_red is reused for the sums below
     float sum = 0.f;
@@ -188,11 +192,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) = u;
         }
     }
-    s_red[half * 128 + row] = sum;
+    s_red[quad * 128 + row] = sum;
     fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core's async proxy
     tc_fence_before();
     __syncthreads();
-    sum = s_red[row] + s_red[128 + row];
+    sum = (s_red[row] + s_red[128 + row]) + (s_red[256 + row] + s_red[384 + row]);
 
     if (tid == 0) {
         tc_fence_after();
@@ -209,14 +213,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const float inv = DROP ? 1.0f / (sum * (1.0f - p.drop.p)) : 1.0f / sum;
-    {
-        uint32_t raw[32];
-        tmem_ld32(t_row + p.o_col + half * 32, raw);
+    if (rows_live) {
+        uint32_t raw[16];
+        tmem_ld16(t_row + p.o_col + quad * 16, raw);
         tmem_ld_wait();
         if (q < p.lq) {
-            __nv_bfloat16* dst = p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim + half * 32;
+            __nv_bfloat16* dst = p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim + quad * 16;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
+            for (int i = 0; i < 16; i += 8) {
                 uint4 u;
                 u.x = pack_bf16x2(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
                 u.y = pack_bf16x2(__uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
@@ -225,9 +229,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 *reinterpret_cast<uint4*>(dst + i) = u;
             }
             if (p.o_f32) {
-                float* df = p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + half * 32;
+                float* df = p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + quad * 16;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
+                for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4*>(df + i) =
                         make_float4(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv,
                                     __uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
@@ -235,7 +239,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
     }
     // natural-log log-sum-exp of the scaled, masked scores
-    if (p.lse && half == 0 && q < p.lq)
+    if (p.lse && quad == 0 && q < p.lq)
         p.lse[((size_t)b * p.heads + h) * p.lq + q] = (mx + log2f(sum)) * 0.6931471805599453f;
     tc_fence_before();
     __syncthreads();
@@ -255,7 +259,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 // memory (thread = one row, a quarter of the columns), and those tiles feed the accumulating products as K-major A
 // operands while the TMA-loaded K / Q / dO tiles are consumed as MN-major B operands in place.
 // =====================================================================================================
-constexpr int kBwdThreads = 512;   // 16 warps: four threads per tile row, one 32-column chunk each
+constexpr int kBwdThreads = 512;
+constexpr int kBwdTileBytes = 196608;   // operand / P / dS tiles of either backward kernel (3-stage streamed operands)   // 16 warps: four threads per tile row, one 32-column chunk each
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -291,6 +296,16 @@ __device__ __forceinline__ void store_tile_chunk32(uint8_t* tile, int row, int c
     }
 }
 
+// same, from values already packed as bf16 pairs (pk[i] = elements 2i, 2i+1)
+__device__ __forceinline__ void store_tile_chunk32_packed(uint8_t* tile, int row, int c, const uint32_t (&pk)[16]) {
+    uint8_t* blk = tile + (c >> 6) * 16384 + row * 128;
+    const int j0 = (c & 32) ? 4 : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+}
+
 // K-major A descriptor for k-step ks (16 columns) of such a tile; MN-major B descriptor for rows [16ks,16ks+16)
 // of a [128 x 64] TMA tile.
 __device__ __forceinline__ uint64_t tile_a_desc(uint32_t tile, int ks) {
@@ -298,6 +313,68 @@ __device__ __forceinline__ uint64_t tile_a_desc(uint32_t tile, int ks) {
 }
 __device__ __forceinline__ uint64_t rows_b_desc(uint32_t tile, int ks) {
     return make_smem_desc(tile + ks * 2048, 8192, 1024);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-thread math of one 32-column group, specialised at compile time so that the common case (no key mask,
+// every column visible) is 4 issue slots per element: FFMA, MUFU.EX2, FFMA, FMUL (+ the bf16 pack).
+// ---------------------------------------------------------------------------------------------------------
+// dq pass: ds_e = p_e * (dP_e * scale - delta * scale),  p_e = 2^(s_e * c1 [+ kmask_e] - lse)
+template <bool KMASK, bool DROP, bool VIS>
+__device__ __forceinline__ void dq_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&ds)[16],
+                                              float c1, float neg_lse, const float* km, int n_vis, float scale_keep,
+                                              float nds, uint32_t dkey, uint32_t pair0, uint32_t dth) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        uint32_t dmask = 0xffffffffu;
+        if (DROP) dmask = drop_pair_mask(dkey, pair0 + (i >> 1), dth);
+        float v2[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int e = i + t;
+            float x = fmaf(__uint_as_float(rs[e]), c1, neg_lse);
+            if (KMASK) x += km[e];
+            const float pr = ex2_approx(x);
+            // o = dropout(P) V: the gradient reaches P_ij only through a kept entry, scaled by 1/(1-p) (in scale_keep)
+            float g = fmaf(__uint_as_float(rp[e]), scale_keep, nds);
+            if (DROP) g = (dmask & (t ? 0xffff0000u : 0x0000ffffu)) ? g : nds;
+            const float v = pr * g;
+            v2[t] = (VIS || e < n_vis) ? v : 0.f;
+        }
+        ds[i >> 1] = pack_bf16x2(v2[0], v2[1]);
+    }
+}
+
+// dkv pass (thread = key row, 32 queries): p_e as above with per-query lse, pd_e = dropout(p)_e (-> dV), ds_e (-> dK)
+template <bool DROP, bool VIS>
+__device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&pr)[16],
+                                               uint32_t (&ds)[16], float c1, float kbias, const float* lse, const float* del,
+                                               int e_first, float scale_keep, float inv_keep, uint32_t dkey,
+                                               uint32_t pair0, uint32_t pair_stride, uint32_t dth, uint32_t lane_mask) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(lse + e);
+        const float4 d4 = *reinterpret_cast<const float4*>(del + e);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv4[4] = {d4.x, d4.y, d4.z, d4.w};
+        float po[4], so[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float x = fmaf(__uint_as_float(rs[e + t]), c1, kbias - lv[t]);
+            float pe = ex2_approx(x);
+            if (!VIS) pe = (e + t >= e_first) ? pe : 0.f;
+            float g = fmaf(__uint_as_float(rp[e + t]), scale_keep, -dv4[t]), pd = pe;
+            if (DROP) {
+                const bool keep = drop_pair_mask(dkey, pair0 + (uint32_t)(e + t) * pair_stride, dth) & lane_mask;
+                g = keep ? g : -dv4[t];
+                pd = keep ? pe * inv_keep : 0.f;          // dV = dropout(P)^T dO
+            }
+            po[t] = pd;
+            so[t] = pe * g;
+        }
+        pr[e >> 1] = pack_bf16x2(po[0], po[1]), pr[(e >> 1) + 1] = pack_bf16x2(po[2], po[3]);
+        ds[e >> 1] = pack_bf16x2(so[0], so[1]), ds[(e >> 1) + 1] = pack_bf16x2(so[2], so[3]);
+    }
 }
 
 template <bool DROP>
@@ -314,16 +391,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                       // 16 KB
     uint8_t* sdO = smem + 16384;              // 16 KB
-    uint8_t* sK = smem + 32768;               // 2 x 16 KB
-    uint8_t* sV = smem + 65536;               // 2 x 16 KB
-    uint8_t* sdS = smem + 98304;              // 2 x 32 KB
-    float* s_part = reinterpret_cast<float*>(smem + 163840);   // [4 quarters][128 rows][2], then [448] key mask
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024 + 448);
+    uint8_t* sK = smem + 32768;               // 3 x 16 KB
+    uint8_t* sV = smem + 81920;               // 3 x 16 KB
+    uint8_t* sdS = smem + 131072;             // 2 x 32 KB
+    float* s_part = reinterpret_cast<float*>(smem + kBwdTileBytes);   // [4 quarters][128 rows][2], then [512] key mask
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024 + 512);
     uint64_t* bar_q = bars;          // Q + dO landed
-    uint64_t* bar_kv = bars + 1;     // [2]
-    uint64_t* bar_s = bars + 3;      // S and dP of the current chunk complete
-    uint64_t* bar_dq = bars + 4;     // [2] dQ product retired (frees its dS tile and K/V buffer)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* bar_kv = bars + 1;     // [3]
+    uint64_t* bar_s = bars + 4;      // S and dP of the current chunk complete
+    uint64_t* bar_dq = bars + 5;     // [2] dQ product retired (frees its dS tile and K/V buffer)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -333,7 +410,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 
     if (tid == 0) {
         mbar_init(bar_q, 1);
-        mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1);
+        mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1), mbar_init(bar_kv + 2, 1);
         mbar_init(bar_s, 1);
         mbar_init(bar_dq, 1), mbar_init(bar_dq + 1, 1);
         fence_barrier_init();
@@ -344,12 +421,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 256;
-    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
+    // keys of chunk j that exist, rounded up to the MMA granule: the products of the last chunk are only that wide
+    auto chunk_n16 = [&](int j) { return (min(128, p.lk - j * 128) + 15) & ~15; };
 
-    auto issue_s = [&](int jj) {   // S = Q K_j^T ; dP = dO V_j^T   (operands of iteration jj sit in buffer jj & 1)
+    auto issue_s = [&](int jj) {   // S = Q K_j^T ; dP = dO V_j^T   (operands of iteration jj sit in buffer jj % 3)
         const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
-        const uint32_t bk = smem_u32(sK + (jj & 1) * 16384), bv = smem_u32(sV + (jj & 1) * 16384);
+        const uint32_t bk = smem_u32(sK + (jj % 3) * 16384), bv = smem_u32(sV + (jj % 3) * 16384);
+        const uint32_t idesc_s = make_idesc_bf16(128, chunk_n16(jj < n_pre ? jj : jj - n_pre), 0, 0);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
             umma_bf16(t_s, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(bk + ks * 32, 16, 1024), idesc_s, ks > 0);
@@ -359,10 +438,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         tc_commit(bar_s);
     };
     auto load_kv = [&](int jj) {
-        const int j = jj < n_pre ? jj : jj - n_pre;
-        mbar_expect_tx(bar_kv + (jj & 1), 32768);
-        tma_load_3d(sK + (jj & 1) * 16384, &tma_k, bar_kv + (jj & 1), h * kHeadDim, j * 128, b);
-        tma_load_3d(sV + (jj & 1) * 16384, &tma_v, bar_kv + (jj & 1), h * kHeadDim, j * 128, b);
+        const int j = jj < n_pre ? jj : jj - n_pre, st = jj % 3;
+        mbar_expect_tx(bar_kv + st, 32768);
+        tma_load_3d(sK + st * 16384, &tma_k, bar_kv + st, h * kHeadDim, j * 128, b);
+        tma_load_3d(sV + st * 16384, &tma_v, bar_kv + st, h * kHeadDim, j * 128, b);
     };
 
     if (tid == 0) {
@@ -371,6 +450,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         tma_load_3d(sdO, &tma_do, bar_q, h * kHeadDim, q0, b);
         load_kv(0);
         if (n_it > 1) load_kv(1);
+        if (n_it > 2) load_kv(2);
         mbar_wait(bar_q, 0);
         mbar_wait(bar_kv, 0);
         tc_fence_after();
@@ -395,7 +475,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     // additive key mask of this batch element, pre-scaled by log2(e), staged once in shared memory
     float* s_kmask = s_part + 1024;
     if (kmask) {
-        for (int k = tid; k < p.lk; k += kBwdThreads) s_kmask[k] = kmask[k] * kLog2e;
+        for (int k = tid; k < 512; k += kBwdThreads) s_kmask[k] = k < p.lk ? kmask[k] * kLog2e : 0.f;
         __syncthreads();
     }
 
@@ -424,50 +504,77 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         __syncthreads();
     }
 
+    // Per key chunk: S/dP (TMEM) -> registers -> [the next chunk's S/dP products are issued here, so the tensor core
+    // works through them while the threads do the exponentials] -> dS tile -> dQ += dS K.
+    // Warps whose 32 query rows lie beyond lq (the last query tile: 393 = 3 x 128 + 9) and column groups beyond the
+    // chunk's keys do no math at all: their dS entries feed only dQ rows that are never stored / k-steps never issued.
+    const bool rows_live = q0 + (warp & 3) * 32 < p.lq;
+    const float scale_keep = p.scale * inv_keep;
     for (int jj = 0; jj < n_it; ++jj) {
         const bool sweep2 = jj >= n_pre;
         const int j = sweep2 ? jj - n_pre : jj;     // key chunk
         const int j2 = jj - n_pre;                  // index within the main sweep
+        const int n16 = chunk_n16(j);
+        const int c = quad * 32;
+        const bool live = rows_live && c < n16;     // warp-uniform
         mbar_wait(bar_s, jj & 1);
         tc_fence_after();
-        if (sweep2 && j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
-        uint8_t* tile = sdS + (j2 & 1) * 32768;
-        {
-            const int c = quad * 32;
-            uint32_t rs[32], rp[32];
+        uint32_t rs[32], rp[32];
+        if (live) {
             tmem_ld32(t_s + t_row + c, rs);
             tmem_ld32(t_dp + t_row + c, rp);
             tmem_ld_wait();
-            float ds[32];
-            uint32_t dmask = 0;
+        }
+        tc_fence_before();
+        __syncthreads();                            // every thread holds its S/dP values: the TMEM tiles are free
+        if (tid == 0) {
+            tc_fence_after();
+            if (jj + 1 < n_it) {
+                mbar_wait(bar_kv + (jj + 1) % 3, ((jj + 1) / 3) & 1);
+                tc_fence_after();
+                issue_s(jj + 1);
+            }
+            if (jj >= 1 && jj + 2 < n_it) {
+                // buffer (jj - 1) % 3 is free once its last reader retired: the S/dP products (bar_s, observed one
+                // iteration ago) in the pre-sweep, the dQ product in the main sweep
+                if (jj - 1 >= n_pre) mbar_wait(bar_dq + ((jj - 1 - n_pre) & 1), ((jj - 1 - n_pre) >> 1) & 1);
+                load_kv(jj + 2);
+            }
+        }
+        uint8_t* tile = sdS + (j2 & 1) * 32768;
+        if (live) {
             const int key0 = j * 128 + c;
-            const bool all_visible = key0 + 32 <= k_lim;      // no per-element predicate needed
+            const int n_vis = k_lim - key0;            // visible columns of this group (may be <= 0 or >= 32)
+            if (!sweep2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float x = fmaf(__uint_as_float(rs[i]), c1, -my_lse);
-                if (kmask) x += s_kmask[min(key0 + i, p.lk - 1)];
-                float pr = ex2_approx(x);
-                if (!all_visible) pr = key0 + i < k_lim ? pr : 0.f;
-                float dp = __uint_as_float(rp[i]);
-                if (DROP) {
-                    // o = dropout(P) V: the gradient reaches P_ij only through a kept entry, scaled by 1/(1-p)
-                    if ((i & 1) == 0) dmask = drop_pair_mask(dkey, row_pair0 + ((key0 + i) >> 1), dth);
-                    dp = (dmask & ((i & 1) ? 0xffff0000u : 0x0000ffffu)) ? dp * inv_keep : 0.f;
-                }
-                if (!sweep2) {
+                for (int i = 0; i < 32; ++i) {
+                    float x = fmaf(__uint_as_float(rs[i]), c1, -my_lse);
+                    if (kmask) x += s_kmask[key0 + i];
+                    const float pr = i < n_vis ? ex2_approx(x) : 0.f;
+                    float dp = __uint_as_float(rp[i]);
+                    if (DROP) dp = drop_keep(dkey, 2ull * row_pair0 + (uint32_t)(key0 + i), dth) ? dp * inv_keep : 0.f;
                     acc_p += pr;
                     acc_pd = fmaf(pr, dp, acc_pd);
-                } else {
-                    ds[i] = pr * fmaf(dp, p.scale, neg_delta_scaled);
                 }
+            } else {
+                uint32_t ds[16];
+                const uint32_t pair0 = row_pair0 + (uint32_t)(key0 >> 1);
+                const float* km = s_kmask + key0;
+                if (__all_sync(0xffffffffu, n_vis >= 32)) {
+                    if (kmask) dq_group_math<true, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
+                    else dq_group_math<false, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
+                } else {
+                    if (kmask) dq_group_math<true, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
+                    else dq_group_math<false, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
+                }
+                if (j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
+                store_tile_chunk32_packed(tile, row, c, ds);
+                fence_proxy_async_smem();
             }
-            if (sweep2) store_tile_chunk32(tile, row, c, ds);
         }
-        if (sweep2) fence_proxy_async_smem();
-        tc_fence_before();
         __syncthreads();
         if (jj == n_pre - 1) {
-            // end of the pre-sweep: combine the two half-row partials
+            // end of the pre-sweep: combine the four quarter-row partials
             s_part[(quad * 128 + row) * 2] = acc_p;
             s_part[(quad * 128 + row) * 2 + 1] = acc_pd;
             __syncthreads();
@@ -478,26 +585,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             neg_delta_scaled = -my_delta * p.scale;
             if (quad == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
         }
-        if (tid == 0) {
+        if (tid == 0 && sweep2) {
             tc_fence_after();
-            if (sweep2) {
-                const uint32_t a = smem_u32(tile), bk = smem_u32(sK + (jj & 1) * 16384);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    umma_bf16(t_dq, tile_a_desc(a, ks), rows_b_desc(bk, ks), idesc_dq, (j2 > 0 || ks > 0) ? 1u : 0u);
-                tc_commit(bar_dq + (j2 & 1));
-            }
-            if (jj + 1 < n_it) {
-                mbar_wait(bar_kv + ((jj + 1) & 1), ((jj + 1) >> 1) & 1);
-                tc_fence_after();
-                issue_s(jj + 1);
-            }
-            if (jj + 2 < n_it) {
-                // buffer jj & 1 is free once its last reader retired: the S/dP products in sweep 1 (bar_s already
-                // observed), the dQ product in sweep 2
-                if (sweep2) mbar_wait(bar_dq + (j2 & 1), (j2 >> 1) & 1);
-                load_kv(jj + 2);
-            }
+            if (j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);
+            const uint32_t a = smem_u32(tile), bk = smem_u32(sK + (jj % 3) * 16384);
+            for (int ks = 0; ks < (n16 >> 4); ++ks)
+                umma_bf16(t_dq, tile_a_desc(a, ks), rows_b_desc(bk, ks), idesc_dq, (j2 > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(bar_dq + (j2 & 1));
         }
         __syncwarp();
     }
@@ -537,18 +631,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;                       // 16 KB
     uint8_t* sV = smem + 16384;               // 16 KB
-    uint8_t* sQ = smem + 32768;               // 2 x 16 KB
-    uint8_t* sdO = smem + 65536;              // 2 x 16 KB
-    uint8_t* sPt = smem + 98304;              // 32 KB   P^T  [128 keys x 128 queries]
-    uint8_t* sdSt = smem + 131072;            // 32 KB   dS^T
-    float* s_lse = reinterpret_cast<float*>(smem + 163840);   // [2][128]
-    float* s_delta = s_lse + 256;                               // [2][128]
+    uint8_t* sQ = smem + 32768;               // 3 x 16 KB
+    uint8_t* sdO = smem + 81920;              // 3 x 16 KB
+    uint8_t* sPt = smem + 131072;             // 32 KB   P^T  [128 keys x 128 queries]
+    uint8_t* sdSt = smem + 163840;            // 32 KB   dS^T
+    float* s_lse = reinterpret_cast<float*>(smem + kBwdTileBytes);   // [2][128]
+    float* s_delta = s_lse + 256;                                      // [2][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
     uint64_t* bar_kv = bars;
-    uint64_t* bar_q = bars + 1;      // [2]
-    uint64_t* bar_s = bars + 3;
-    uint64_t* bar_acc = bars + 4;    // dK/dV products of chunk i retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* bar_q = bars + 1;      // [3]
+    uint64_t* bar_s = bars + 4;
+    uint64_t* bar_acc = bars + 5;    // dK/dV products of chunk i retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -556,7 +650,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 
     if (tid == 0) {
         mbar_init(bar_kv, 1);
-        mbar_init(bar_q, 1), mbar_init(bar_q + 1, 1);
+        mbar_init(bar_q, 1), mbar_init(bar_q + 1, 1), mbar_init(bar_q + 2, 1);
         mbar_init(bar_s, 1);
         mbar_init(bar_acc, 1);
         fence_barrier_init();
@@ -567,12 +661,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_s = tmem, t_dp = tmem + 128, t_dk = tmem + 256, t_dv = tmem + 320;
-    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc_acc = make_idesc_bf16(128, kHeadDim, 0, 1);
+    auto chunk_n16 = [&](int i) { return (min(128, p.lq - i * 128) + 15) & ~15; };   // queries of chunk i, MMA granule
 
     auto issue_s = [&](int i) {   // S^T = K Q_i^T ; dP^T = V dO_i^T
+        const uint32_t idesc_s = make_idesc_bf16(128, chunk_n16(i), 0, 0);
         const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
-        const uint32_t bq = smem_u32(sQ + (i & 1) * 16384), bd = smem_u32(sdO + (i & 1) * 16384);
+        const uint32_t bq = smem_u32(sQ + (i % 3) * 16384), bd = smem_u32(sdO + (i % 3) * 16384);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
             umma_bf16(t_s, make_smem_desc(ak + ks * 32, 16, 1024), make_smem_desc(bq + ks * 32, 16, 1024), idesc_s, ks > 0);
@@ -582,9 +677,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         tc_commit(bar_s);
     };
     auto load_q = [&](int i) {
-        mbar_expect_tx(bar_q + (i & 1), 32768);
-        tma_load_3d(sQ + (i & 1) * 16384, &tma_q, bar_q + (i & 1), h * kHeadDim, i * 128, b);
-        tma_load_3d(sdO + (i & 1) * 16384, &tma_do, bar_q + (i & 1), h * kHeadDim, i * 128, b);
+        const int st = i % 3;
+        mbar_expect_tx(bar_q + st, 32768);
+        tma_load_3d(sQ + st * 16384, &tma_q, bar_q + st, h * kHeadDim, i * 128, b);
+        tma_load_3d(sdO + st * 16384, &tma_do, bar_q + st, h * kHeadDim, i * 128, b);
     };
     auto load_vec = [&](int i) {  // lse / delta of query chunk i -> smem (all 256 threads)
         const int qq = i * 128 + (tid & 127);
@@ -599,6 +695,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         tma_load_3d(sV, &tma_v, bar_kv, h * kHeadDim, k0, b);
         load_q(0);
         if (n_qc > 1) load_q(1);
+        if (n_qc > 2) load_q(2);
         mbar_wait(bar_kv, 0);
         mbar_wait(bar_q, 0);
         tc_fence_after();
@@ -625,68 +722,62 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         col_pair0 = attn_row_pair0(b, p.heads, h, p.lq, 0, p.lk) + (uint32_t)(key >> 1);
     }
 
+    const bool rows_live = k0 + (warp & 3) * 32 < p.lk;     // warps of key rows beyond lk: nothing to do (dK/dV rows unused)
+    const float scale_keep = p.scale * inv_keep;
     for (int i = 0; i < n_qc; ++i) {
         if (i + 1 < n_qc) load_vec(i + 1);          // other buffer; consumed after the next __syncthreads
+        const int n16 = chunk_n16(i);
+        const int c = quad * 32;
+        const bool live = rows_live && c < n16;     // warp-uniform
         mbar_wait(bar_s, i & 1);
         tc_fence_after();
-        if (i >= 1) mbar_wait(bar_acc, (i - 1) & 1);   // sPt / sdSt free again
-        const float* lse_i = s_lse + (i & 1) * 128;
-        const float* del_i = s_delta + (i & 1) * 128;
-        {
-            const int c = quad * 32;
-            uint32_t rs[32], rp[32];
+        uint32_t rs[32], rp[32];
+        if (live) {
             tmem_ld32(t_s + t_row + c, rs);
             tmem_ld32(t_dp + t_row + c, rp);
             tmem_ld_wait();
-            float pr[32], ds[32];
-            const bool all_visible = key_ok && i * 128 + c >= q_first;   // queries beyond lq carry lse = +inf -> p = 0
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-                const float4 l4 = *reinterpret_cast<const float4*>(lse_i + c + e);
-                const float4 d4 = *reinterpret_cast<const float4*>(del_i + c + e);
-                const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv4[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float x = fmaf(__uint_as_float(rs[e + t]), c1, kbias - lv[t]);
-                    float pe = ex2_approx(x);
-                    if (!all_visible) pe = (key_ok && i * 128 + c + e + t >= q_first) ? pe : 0.f;
-                    float dp = __uint_as_float(rp[e + t]), pd = pe;
-                    if (DROP) {
-                        const uint32_t qq = (uint32_t)(i * 128 + c + e + t);
-                        const bool keep = drop_pair_mask(dkey, col_pair0 + qq * pair_stride, dth) & lane_mask;
-                        dp = keep ? dp * inv_keep : 0.f;
-                        pd = keep ? pe * inv_keep : 0.f;          // dV = dropout(P)^T dO
-                    }
-                    pr[e + t] = pd;
-                    ds[e + t] = pe * fmaf(dp, p.scale, -dv4[t]);
-                }
-            }
-            store_tile_chunk32(sPt, row, c, pr);
-            store_tile_chunk32(sdSt, row, c, ds);
         }
-        fence_proxy_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();                            // S^T/dP^T are in registers: their TMEM tiles are free
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t ap = smem_u32(sPt), ads = smem_u32(sdSt);
-            const uint32_t bq = smem_u32(sQ + (i & 1) * 16384), bd = smem_u32(sdO + (i & 1) * 16384);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(t_dv, tile_a_desc(ap, ks), rows_b_desc(bd, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(t_dk, tile_a_desc(ads, ks), rows_b_desc(bq, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-            tc_commit(bar_acc);
-            if (i + 1 < n_qc) {
-                mbar_wait(bar_q + ((i + 1) & 1), ((i + 1) >> 1) & 1);
+            if (i + 1 < n_qc) {                     // next chunk's score products run under this chunk's exponentials
+                mbar_wait(bar_q + (i + 1) % 3, ((i + 1) / 3) & 1);
                 tc_fence_after();
                 issue_s(i + 1);
             }
-            if (i + 2 < n_qc) {
-                mbar_wait(bar_acc, i & 1);
+            if (i >= 1 && i + 2 < n_qc) {
+                mbar_wait(bar_acc, (i - 1) & 1);    // dK/dV of chunk i-1 retired: its Q/dO buffer is free
                 load_q(i + 2);
             }
+        }
+        if (live) {
+            const float* lse_i = s_lse + (i & 1) * 128 + c;
+            const float* del_i = s_delta + (i & 1) * 128 + c;
+            uint32_t pr[16], ds[16];
+            // first query of this group that sees the key (block-causal); queries beyond lq carry lse = +inf -> p = 0
+            const int e_first = key_ok ? q_first - (i * 128 + c) : 32;
+            const uint32_t pair0 = col_pair0 + (uint32_t)(i * 128 + c) * pair_stride;
+            if (__all_sync(0xffffffffu, e_first <= 0))
+                dkv_group_math<DROP, true>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask);
+            else
+                dkv_group_math<DROP, false>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask);
+            if (i >= 1) mbar_wait(bar_acc, (i - 1) & 1);   // sPt / sdSt free again
+            store_tile_chunk32_packed(sPt, row, c, pr);
+            store_tile_chunk32_packed(sdSt, row, c, ds);
+            fence_proxy_async_smem();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            if (i >= 1) mbar_wait(bar_acc, (i - 1) & 1);
+            const uint32_t ap = smem_u32(sPt), ads = smem_u32(sdSt);
+            const uint32_t bq = smem_u32(sQ + (i % 3) * 16384), bd = smem_u32(sdO + (i % 3) * 16384);
+            for (int ks = 0; ks < (n16 >> 4); ++ks)
+                umma_bf16(t_dv, tile_a_desc(ap, ks), rows_b_desc(bd, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < (n16 >> 4); ++ks)
+                umma_bf16(t_dk, tile_a_desc(ads, ks), rows_b_desc(bq, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(bar_acc);
         }
         __syncwarp();
     }
@@ -760,7 +851,7 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     p.scale = a->scale, p.mask_mode = a->mask_mode, p.q_per_frame = a->q_per_frame, p.k_per_frame = a->k_per_frame;
     p.drop.p = a->dropout_seed ? a->dropout_p : 0.f, p.drop.salt = a->dropout_salt, p.drop.seed = a->dropout_seed;
     SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_attn_fwd: dropout_p=%f", (double)p.drop.p);
-    const size_t smem = (size_t)p.v_off + p.n_kbox * 8192 + (448 + 256) * 4 + 64 + 1024;
+    const size_t smem = (size_t)p.v_off + p.n_kbox * 8192 + (448 + 512) * 4 + 64 + 1024;
     SHG_REQUIRE(smem <= 227 * 1024, SHG_ESHAPE, "shg_attn_fwd: %zu B of shared memory needed", smem);
 
     const CUtensorMap* tq = head_tmap(a->q, a->ldq, a->heads, a->lq, a->batch, 128);
@@ -815,7 +906,7 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     const CUtensorMap* tk = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, 128);
     const CUtensorMap* tv = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, 128);
     if (!tq || !tdo || !tk || !tv) return SHG_ECUDA;
-    const size_t smem = 163840 + 4096 + 1792 + 128 + 1024;   // tiles + per-row vectors + key mask + barriers + slack
+    const size_t smem = kBwdTileBytes + 4096 + 2048 + 128 + 1024;   // tiles + per-row vectors + key mask + barriers + slack
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -4,7 +4,7 @@
 //   warp 1      : TMEM allocation (whole warp) + MMA issuer (one lane): tcgen05.mma 128 x block_n x 16,
 //                 fp32 accumulators in TMEM, two accumulator stages so the epilogue of tile t overlaps
 //                 the main loop of tile t+1
-//   warps 2..9  : epilogue — two warps per TMEM lane quarter (alternating 32-column chunks), tcgen05.ld with
+//   warps 2..17 : epilogue — four warps per TMEM lane quarter (16 columns each of a 64-column block), tcgen05.ld with
 //                 thread = one output row; bias staged in smem, residual / activation-derivative operands
 //                 prefetched from HBM ahead of the accumulator wait; bias / pre-activation store /
 //                 GELU|ReLU|tanh / x act'(aux) / residual / bf16|fp32 store or fp32 atomic accumulate (split-K)
@@ -17,7 +17,8 @@ namespace shg {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiSub = 2;          // epilogue warps per TMEM lane quarter
+constexpr int kGemmThreads = 64 + kEpiSub * 128;   // TMA warp + MMA warp + 4 * kEpiSub epilogue warps
 constexpr int kMaxStages = 8;
 
 struct GemmParams {
@@ -33,6 +34,7 @@ struct GemmParams {
     float mul_scale;
     DropCfg drop;
     int act, out_f32, accumulate;
+    int tma_store;          // bf16 D (and preact) leave through smem staging + TMA stores
     int splits, block_n, n_stages;
     int m_tiles, n_tiles, kb_total, kb_per_split;
 };
@@ -46,186 +48,220 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     }
 }
 
-// One output tile's epilogue for one thread (= one output row, every other 32-column chunk starting at grp*32).
-// `wait_accumulator` blocks until the tile's accumulator is complete in TMEM; HBM operands of the first chunk are
-// requested before it.
-template <class WaitFn>
+constexpr int kStageOutBytes = 2 * 16384;   // two [128 x 64] bf16 staging blocks for the TMA-store epilogue
+
+// One output tile's epilogue for one thread (= one output row; warp group `sub` of NSUB takes 64/NSUB columns of
+// every 64-column block).  `wait_accumulator` blocks until the tile's accumulator is complete in TMEM; HBM operands of
+// the first chunk are requested before it.
+//
+// bf16 outputs (D and the optional pre-activation copy) leave through shared memory: the 256 epilogue threads write a
+// [128 x 64] block 128B-swizzled (thread = row: 4 x 16 B, conflict-free), one thread hands it to a TMA store, two
+// blocks in flight.  A warp-level st.global of "thread = row" touches 32 different lines per instruction — at 256
+// columns per tile the LSU, not the tensor core, then sets the tile time; the bulk store moves whole lines and clips
+// the M / N tails itself.  fp32 outputs and split-K accumulation (atomics) keep the direct path.
+template <int NSUB, class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* sb, uint32_t t_row, int row, bool row_ok,
-                                              int n0, int grp, WaitFn wait_accumulator) {
-        const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
-        const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
-        const bool vec_ok_aux = p.mul_aux && (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mul_aux) & 15) == 0);
-        const bool vec_ok_res = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-            // operands of the first chunk that come from HBM: issue before waiting for the accumulator
-            uint4 res[4], aux[4];
-            auto prefetch = [&](int c) {
-                const int col0 = n0 + c;
-                const bool full = col0 + 32 <= p.n;
-                if (row_ok && full && vec_ok_res) {
-                    const uint4* src = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col0);
+                                              int m0, int n0, int sub, int etid, uint8_t* stg, const CUtensorMap* tm_d,
+                                              const CUtensorMap* tm_pre, uint32_t& nblk, WaitFn wait_accumulator) {
+    constexpr int COLS = 64 / NSUB;          // columns per thread and 64-column block (32 or 16)
+    constexpr int NV = COLS / 8;             // 16-byte bf16 vectors per thread and block
+    const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
+    const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
+    // the one bf16 side operand of the tile: the saved activation input/output (backward through an activation) or
+    // the residual — never both on this path (checked on the host)
+    const __nv_bfloat16* side_ptr = p.mul_aux ? p.mul_aux : p.residual;
+    const int64_t ld_side = p.mul_aux ? p.ldd : p.ldr;
+    const bool vec_ok_side = side_ptr && (ld_side % 8 == 0) && ((reinterpret_cast<uintptr_t>(side_ptr) & 15) == 0);
+    const bool staged = p.tma_store != 0;
+    const int r_local = row - m0;
+    // COLS values of this thread's row -> its part of the staging block -> (one thread) bulk store of the block
+    auto staged_store = [&](const float (&v)[COLS], const CUtensorMap* tm, int blk_col0, bool active) {
+        if (etid == 0) bulk_wait_read<1>();              // the store that last used this buffer has read it
+        asm volatile("bar.sync 1, %0;" ::"n"(NSUB * 128) : "memory");
+        uint8_t* buf = stg + (nblk & 1) * 16384;
+        if (active) {
+            uint8_t* dst = buf + r_local * 128;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) res[i] = __ldg(src + i);
-                }
-                if (row_ok && full && vec_ok_aux) {
-                    const uint4* src = reinterpret_cast<const uint4*>(p.mul_aux + (size_t)row * p.ldd + col0);
+            for (int j = 0; j < NV; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]), u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(dst + (((sub * NV + j) ^ (r_local & 7)) << 4)) = u;
+            }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(NSUB * 128) : "memory");
+        if (etid == 0) {
+            tma_store_2d(tm, buf, blk_col0, m0);
+            bulk_commit();
+        }
+        ++nblk;
+    };
+    // side operand of a chunk: requested from HBM ahead of its use (first chunk: before the accumulator wait)
+    uint4 side[NV];
+    auto prefetch = [&](int c) {
+        const int col0 = n0 + c;
+        if (row_ok && col0 + COLS <= p.n && vec_ok_side) {
+            const uint4* src = reinterpret_cast<const uint4*>(side_ptr + (size_t)row * ld_side + col0);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) aux[i] = __ldg(src + i);
-                }
-            };
-            prefetch(grp * 32);
-            wait_accumulator();
-            tc_fence_after();
-            for (int c = grp * 32; c < p.block_n; c += 64) {
-                const int col0 = n0 + c;
-                if (col0 >= p.n) break;  // warp-uniform
-                uint32_t raw[32];
-                __syncwarp();
-                tmem_ld32(t_row + c, raw);
-                tmem_ld_wait();
-                float acc[32];
-                const bool full_chunk = col0 + 32 <= p.n;
+            for (int i = 0; i < NV; ++i) side[i] = __ldg(src + i);
+        }
+    };
+    prefetch(sub * COLS);
+    wait_accumulator();
+    tc_fence_after();
+    for (int blk0 = 0; blk0 < p.block_n; blk0 += 64) {
+        if (n0 + blk0 >= p.n) break;                     // uniform over the epilogue threads
+        const int c = blk0 + sub * COLS;
+        const int col0 = n0 + c;
+        const bool active = c < p.block_n && col0 < p.n;  // warp-uniform
+        if (!active && !staged) break;
+        float acc[COLS];
+        const bool full_chunk = col0 + COLS <= p.n;
+        const bool do_row = row_ok && active;
+        if (active) {
+            uint32_t raw[COLS];
+            __syncwarp();
+            if constexpr (COLS == 32) tmem_ld32(t_row + c, raw);
+            else tmem_ld16(t_row + c, raw);
+            tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(sb + c + i);
-                    acc[i] = __uint_as_float(raw[i]) + b4.x, acc[i + 1] = __uint_as_float(raw[i + 1]) + b4.y;
-                    acc[i + 2] = __uint_as_float(raw[i + 2]) + b4.z, acc[i + 3] = __uint_as_float(raw[i + 3]) + b4.w;
-                }
-                // this chunk's prefetched operands -> registers of their own, then prefetch the next chunk's
-                float rv[32], av[32];
-                const bool have_res = row_ok && full_chunk && vec_ok_res;
-                const bool have_aux = row_ok && full_chunk && vec_ok_aux;
-                if (have_res) {
+            for (int i = 0; i < COLS; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + c + i);
+                acc[i] = __uint_as_float(raw[i]) + b4.x, acc[i + 1] = __uint_as_float(raw[i + 1]) + b4.y;
+                acc[i + 2] = __uint_as_float(raw[i + 2]) + b4.z, acc[i + 3] = __uint_as_float(raw[i + 3]) + b4.w;
+            }
+        }
+        if (p.preact) {
+            if (staged) {
+                staged_store(acc, tm_pre, n0 + blk0, active);
+            } else if (do_row) {
+                __nv_bfloat16* pr = p.preact + (size_t)row * p.ldd + col0;
+                if (full_chunk && vec_ok_bf16) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float2 f;
-                        f = unpack_bf16x2(res[i].x), rv[8 * i] = f.x, rv[8 * i + 1] = f.y;
-                        f = unpack_bf16x2(res[i].y), rv[8 * i + 2] = f.x, rv[8 * i + 3] = f.y;
-                        f = unpack_bf16x2(res[i].z), rv[8 * i + 4] = f.x, rv[8 * i + 5] = f.y;
-                        f = unpack_bf16x2(res[i].w), rv[8 * i + 6] = f.x, rv[8 * i + 7] = f.y;
-                    }
-                }
-                if (have_aux) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float2 f;
-                        f = unpack_bf16x2(aux[i].x), av[8 * i] = f.x, av[8 * i + 1] = f.y;
-                        f = unpack_bf16x2(aux[i].y), av[8 * i + 2] = f.x, av[8 * i + 3] = f.y;
-                        f = unpack_bf16x2(aux[i].z), av[8 * i + 4] = f.x, av[8 * i + 5] = f.y;
-                        f = unpack_bf16x2(aux[i].w), av[8 * i + 6] = f.x, av[8 * i + 7] = f.y;
-                    }
-                }
-                if (c + 64 < p.block_n) prefetch(c + 64);
-                if (row_ok) {
-                if (p.preact) {
-                    __nv_bfloat16* pr = p.preact + (size_t)row * p.ldd + col0;
-                    if (full_chunk && vec_ok_bf16) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 u;
-                            u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
-                            u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
-                            *reinterpret_cast<uint4*>(pr + i) = u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.n) pr[i] = __float2bfloat16(acc[i]);
-                    }
-                }
-                if (p.act == SHG_ACT_GELU_ERF) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] = gelu_erf(acc[i]);
-                } else if (p.act != SHG_ACT_NONE) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] = apply_act(acc[i], p.act);
-                }
-                if (p.mul_mode) {
-                    // backward through an activation: acc *= act'(aux) (aux = saved pre-activation for GELU,
-                    // saved output for ReLU)
-                    if (!have_aux) {
-                        const __nv_bfloat16* ax = p.mul_aux + (size_t)row * p.ldd + col0;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) av[i] = col0 + i < p.n ? __bfloat162float(ax[i]) : 0.f;
-                    }
-                    if (p.mul_mode == SHG_MUL_GELU_GRAD) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] *= gelu_erf_grad(av[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] = av[i] > 0.f ? acc[i] * p.mul_scale : 0.f;
-                    }
-                }
-                if (p.drop.p > 0.f) {
-                    // nn.Dropout on the projection output, before the residual add (BertAttOutput / BertOutput /
-                    // decoder dropout1-3 and the decoder FFN's inner dropout)
-                    const uint32_t key = drop_key(__ldg(p.drop.seed), p.drop.salt), th = drop_thresh(p.drop.p);
-                    const float inv_keep = 1.0f / (1.0f - p.drop.p);
-                    const uint64_t base = (uint64_t)row * (uint64_t)p.n + col0;     // col0 is even
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const uint32_t kb = drop_pair(key, (uint32_t)((base + i) >> 1), th);
-                        acc[i] = (kb & 1u) ? acc[i] * inv_keep : 0.f;
-                        acc[i + 1] = (kb & 2u) ? acc[i + 1] * inv_keep : 0.f;
-                    }
-                }
-                if (p.residual) {
-                    if (!have_res) {
-                        const __nv_bfloat16* rs = p.residual + (size_t)row * p.ldr + col0;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) rv[i] = col0 + i < p.n ? __bfloat162float(rs[i]) : 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] += rv[i];
-                }
-                if (p.accumulate) {
-                    float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
-                    if (full_chunk && vec_ok_f32) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            atomicAdd(reinterpret_cast<float4*>(o + i),
-                                      make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.n) atomicAdd(o + i, acc[i]);
-                    }
-                } else if (p.out_f32) {
-                    float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
-                    if (full_chunk && vec_ok_f32) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(o + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.n) o[i] = acc[i];
+                    for (int i = 0; i < COLS; i += 8) {
+                        uint4 u;
+                        u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
+                        u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
+                        *reinterpret_cast<uint4*>(pr + i) = u;
                     }
                 } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)row * p.ldd + col0;
-                    if (full_chunk && vec_ok_bf16) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 u;
-                            u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
-                            u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
-                            *reinterpret_cast<uint4*>(o + i) = u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.n) o[i] = __float2bfloat16(acc[i]);
-                    }
+                    for (int i = 0; i < COLS; ++i)
+                        if (col0 + i < p.n) pr[i] = __float2bfloat16(acc[i]);
                 }
-                }  // row_ok
             }
+        }
+        if (do_row || (staged && active)) {
+            // activation first: only the accumulators (and the packed side operand) are live here, which leaves the
+            // register allocator room to interleave the 32 independent GELU chains
+            if (p.act == SHG_ACT_GELU_ERF) {
+                gelu_erf_batch(acc);
+            } else if (p.act != SHG_ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < COLS; ++i) acc[i] = apply_act(acc[i], p.act);
+            }
+            float sv[COLS];
+            if (side_ptr) {
+                if (row_ok && full_chunk && vec_ok_side) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        float2 f;
+                        f = unpack_bf16x2(side[i].x), sv[8 * i] = f.x, sv[8 * i + 1] = f.y;
+                        f = unpack_bf16x2(side[i].y), sv[8 * i + 2] = f.x, sv[8 * i + 3] = f.y;
+                        f = unpack_bf16x2(side[i].z), sv[8 * i + 4] = f.x, sv[8 * i + 5] = f.y;
+                        f = unpack_bf16x2(side[i].w), sv[8 * i + 6] = f.x, sv[8 * i + 7] = f.y;
+                    }
+                } else {
+                    const __nv_bfloat16* sp = side_ptr + (size_t)row * ld_side + col0;
+#pragma unroll
+                    for (int i = 0; i < COLS; ++i) sv[i] = (row_ok && col0 + i < p.n) ? __bfloat162float(sp[i]) : 0.f;
+                }
+                if (c + 64 < p.block_n) prefetch(c + 64);
+            }
+            if (p.mul_mode) {
+                // backward through an activation: acc *= act'(aux) (aux = saved pre-activation for GELU,
+                // saved output for ReLU)
+                if (p.mul_mode == SHG_MUL_GELU_GRAD) {
+                    gelu_erf_grad_batch(acc, sv);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < COLS; ++i) acc[i] = sv[i] > 0.f ? acc[i] * p.mul_scale : 0.f;
+                }
+            }
+            if (p.drop.p > 0.f) {
+                // nn.Dropout on the projection output, before the residual add (BertAttOutput / BertOutput /
+                // decoder dropout1-3 and the decoder FFN's inner dropout)
+                const uint32_t key = drop_key(__ldg(p.drop.seed), p.drop.salt), th = drop_thresh(p.drop.p);
+                const float inv_keep = 1.0f / (1.0f - p.drop.p);
+                const uint64_t base = (uint64_t)row * (uint64_t)p.n + col0;     // col0 is even
+#pragma unroll
+                for (int i = 0; i < COLS; i += 2) {
+                    const uint32_t kb = drop_pair(key, (uint32_t)((base + i) >> 1), th);
+                    acc[i] = (kb & 1u) ? acc[i] * inv_keep : 0.f;
+                    acc[i + 1] = (kb & 2u) ? acc[i + 1] * inv_keep : 0.f;
+                }
+            }
+            if (p.residual) {
+#pragma unroll
+                for (int i = 0; i < COLS; ++i) acc[i] += sv[i];
+            }
+        }
+        if (staged) {
+            staged_store(acc, tm_d, n0 + blk0, active);
+        } else if (do_row) {
+            if (p.accumulate) {
+                float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
+                if (full_chunk && vec_ok_f32) {
+#pragma unroll
+                    for (int i = 0; i < COLS; i += 4)
+                        atomicAdd(reinterpret_cast<float4*>(o + i),
+                                  make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < COLS; ++i)
+                        if (col0 + i < p.n) atomicAdd(o + i, acc[i]);
+                }
+            } else if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
+                if (full_chunk && vec_ok_f32) {
+#pragma unroll
+                    for (int i = 0; i < COLS; i += 4)
+                        *reinterpret_cast<float4*>(o + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < COLS; ++i)
+                        if (col0 + i < p.n) o[i] = acc[i];
+                }
+            } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)row * p.ldd + col0;
+                if (full_chunk && vec_ok_bf16) {
+#pragma unroll
+                    for (int i = 0; i < COLS; i += 8) {
+                        uint4 u;
+                        u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
+                        u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
+                        *reinterpret_cast<uint4*>(o + i) = u;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < COLS; ++i)
+                        if (col0 + i < p.n) o[i] = __float2bfloat16(acc[i]);
+                }
+            }
+        }
+    }
 }
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
             const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stg = smem;                               // TMA-store staging (present only when p.tma_store)
+    if (p.tma_store) smem += kStageOutBytes;
     const uint32_t a_bytes = BM * BK * 2;
     const uint32_t b_bytes = p.block_n * BK * 2;
     const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -244,7 +280,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full + s, 1);
-            mbar_init(tmem_empty + s, 8);
+            mbar_init(tmem_empty + s, 4 * kEpiSub);
         }
         fence_barrier_init();
         tma_prefetch_desc(&tma_a);
@@ -335,10 +371,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // ---------------------------------------------------------------- epilogue (warps 2..9)
         // Two warps per TMEM lane quarter, each taking every other 32-column chunk; thread = one output row.
         const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
-        const int grp = (warp - 2) >> 2;       // which half of the chunks
+        const int sub = (warp - 2) >> 2;       // which 16 columns of each 64-column block
         const int etid = (warp - 2) * 32 + lane;
         int as = 0;
-        uint32_t aphase = 0;
+        uint32_t aphase = 0, nblk = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int rem = tile % (p.m_tiles * p.n_tiles);
             const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
@@ -346,10 +382,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const bool row_ok = row < p.m;
             // bias of this tile -> shared memory (zero past N), while the main loop is still running
             float* sb = s_bias + as * 256;
-            sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (etid < 256) sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            epilogue_tile(p, sb, t_row, row, row_ok, n0, grp, [&] { mbar_wait(tmem_full + as, aphase); });
+            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk,
+                          [&] { mbar_wait(tmem_full + as, aphase); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_relaxed(tmem_empty + as);
@@ -358,6 +395,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 aphase ^= 1;
             }
         }
+        if (etid == 0) bulk_wait_read<0>();            // staging must outlive the last bulk store's read
     }
     tc_fence_before();
     __syncthreads();
@@ -376,9 +414,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
              const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stg = smem;
+    if (p.tma_store) smem += kStageOutBytes;
     const uint32_t a_bytes = BM * BK * 2;
     const int half_n = p.block_n / 2;
     const uint32_t b_bytes = half_n * BK * 2;
@@ -400,7 +441,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full + s, 1);     // each CTA's: multicast commit
-            mbar_init(tmem_empty + s, 16);   // leader's: 8 epilogue warps of each CTA
+            mbar_init(tmem_empty + s, 8 * kEpiSub);   // leader's: the epilogue warps of both CTAs
         }
         fence_barrier_init();
         tma_prefetch_desc(&tma_a);
@@ -492,10 +533,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             }
         }
     } else {
-        const int quarter = warp & 3, grp = (warp - 2) >> 2;
+        const int quarter = warp & 3, sub = (warp - 2) >> 2;
         const int etid = (warp - 2) * 32 + lane;
         int as = 0;
-        uint32_t aphase = 0;
+        uint32_t aphase = 0, nblk = 0;
         const uint32_t leader_empty0 = mapa_u32(smem_u32(tmem_empty), 0);
         for (int tile = pair; tile < total_tiles; tile += n_pairs) {
             const int rem = tile % (p.m_tiles * p.n_tiles);
@@ -503,10 +544,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             const int row = m0 + quarter * 32 + lane;
             const bool row_ok = row < p.m;
             float* sb = s_bias + as * 256;
-            sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (etid < 256) sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            epilogue_tile(p, sb, t_row, row, row_ok, n0, grp, [&] { mbar_wait(tmem_full + as, aphase); });
+            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk,
+                          [&] { mbar_wait(tmem_full + as, aphase); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_empty0 + as * 8);
@@ -515,6 +557,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 aphase ^= 1;
             }
         }
+        if (etid == 0) bulk_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -593,6 +636,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     SHG_REQUIRE(splits == 1 || accumulate, SHG_EINVAL, "shg_gemm: splits>1 needs SHG_GEMM_ACCUMULATE");
     SHG_REQUIRE(!accumulate || !(a->preact || a->residual || a->act || a->mul_aux), SHG_EINVAL,
                 "shg_gemm: accumulate mode takes no activation/residual/preact");
+    SHG_REQUIRE(!(a->residual && a->mul_aux), SHG_EINVAL, "shg_gemm: residual and mul_aux are mutually exclusive");
     GemmParams p;
     p.d = a->d, p.ldd = a->ldd, p.m = a->m, p.n = a->n, p.k = a->k;
     p.bias = a->bias, p.residual = (const __nv_bfloat16*)a->residual, p.ldr = a->ldr;
@@ -605,7 +649,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     p.out_f32 = (a->flags & SHG_GEMM_OUT_F32) || accumulate, p.accumulate = accumulate;
     p.m_tiles = (a->m + BM - 1) / BM;
     // block_n: 0 = choose everything; low bits = tile width; | 1024 forces CTA-pair tiles (256 x bn), | 2048 forbids them
-    const int bn_req = a->block_n & 1023;
+    const int bn_req = a->block_n & 1023;            // (| 4096: direct-store epilogue, for A/B comparison)
     bool pair = (a->block_n & 1024) != 0;
     if (!(a->block_n & (1024 | 2048)) && !bn_req) pair = prefer_pair(a->m, a->n, a->k, splits, 0);
     int bn = bn_req ? bn_req : (pair ? pick_pair_block_n(a->m, a->n, splits) : pick_block_n(p.m_tiles * splits, a->n));
@@ -620,10 +664,14 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
     const int stage_bytes = BM * BK * 2 + (pair ? bn / 2 : bn) * BK * 2;
     const int bar_bytes = 1024 + 2048;   // barriers + TMEM slot + bias staging
-    int n_stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
+    // bf16 outputs with TMA-legal geometry leave through staged bulk stores
+    p.tma_store = (!p.out_f32 && a->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
+                   (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0) && !(a->block_n & 4096)) ? 1 : 0;
+    const int out_bytes = p.tma_store ? kStageOutBytes : 0;
+    int n_stages = (227 * 1024 - 1024 - bar_bytes - out_bytes) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
     p.n_stages = n_stages;
-    const size_t smem = (size_t)n_stages * stage_bytes + bar_bytes + 1024;
+    const size_t smem = (size_t)n_stages * stage_bytes + bar_bytes + out_bytes + 1024;
 
     // TMA descriptors over the operands as they lie in HBM
     uint64_t dims[2], strides[1];
@@ -639,6 +687,17 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     strides[0] = (uint64_t)a->ldb * 2;
     tb = get_tmap_bf16(a->b, 2, dims, strides, box);
     if (!tb) return SHG_ECUDA;
+    const CUtensorMap *td = ta, *tpre = ta;          // placeholders when the staged store is off
+    if (p.tma_store) {
+        dims[0] = a->n, dims[1] = a->m, box[0] = 64, box[1] = BM;
+        strides[0] = (uint64_t)a->ldd * 2;
+        td = get_tmap_bf16(a->d, 2, dims, strides, box);
+        if (!td) return SHG_ECUDA;
+        if (a->preact) {
+            tpre = get_tmap_bf16(a->preact, 2, dims, strides, box);
+            if (!tpre) return SHG_ECUDA;
+        }
+    }
 
     const int total = p.m_tiles * p.n_tiles * p.splits;
     int grid = total < kNumSMs ? total : kNumSMs;
@@ -651,7 +710,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm2_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set2 = true;                                                                                  \
         }                                                                                                      \
-        gemm2_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, p);                                   \
+        gemm2_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, *td, *tpre, p);                                  \
     } while (0)
     if (pair) {
         if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);
@@ -668,7 +727,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set = true;                                                                                  \
         }                                                                                                     \
-        gemm_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, p);                                   \
+        gemm_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, *td, *tpre, p);                                  \
     } while (0)
     if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM_LAUNCH(false, false);
     else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM_LAUNCH(false, true);

@@ -93,6 +93,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// TMA store of a [box] tile staged in shared memory (128B-swizzled like the loads); clips at the tensor edge.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -262,6 +276,61 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     float e;
     const float phi_cdf = gelu_phi(x, e);
     return fmaf(x * 0.39894228040143267794f, e, phi_cdf);
+}
+
+// Batched forms for the GEMM epilogues.  Written stage by stage over 8 elements, with the two SFU operations as
+// `asm volatile` so that ptxas keeps the stages apart: left to itself it serialises the per-element chains through
+// three registers (MUFU latency exposed 2x per element, measured +37 us on the 12576x3072x768 FFN projection).
+__device__ __forceinline__ float ex2_approx_v(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx_v(float x) {
+    float y;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// phi[i] = Phi(x[i]); e[i] = exp(-x[i]^2 / 2)
+__device__ __forceinline__ void gelu_phi_x8(const float* x, float* phi, float* e) {
+    float z[8], k[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = fabsf(x[i]) * 0.70710678118654752440f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k[i] = rcp_approx_v(fmaf(0.3275911f, z[i], 1.0f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = ex2_approx_v(z[i] * z[i] * -1.4426950408889634f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float poly = fmaf(1.061405429f, k[i], -1.453152027f);
+        poly = fmaf(poly, k[i], 1.421413741f);
+        poly = fmaf(poly, k[i], -0.284496736f);
+        poly = fmaf(poly, k[i], 0.254829592f);
+        poly *= k[i];
+        const float erf_abs = fmaf(-poly, e[i], 1.0f);
+        phi[i] = fmaf(copysignf(erf_abs, x[i]), 0.5f, 0.5f);
+    }
+}
+template <int N>
+__device__ __forceinline__ void gelu_erf_batch(float (&v)[N]) {
+#pragma unroll
+    for (int b = 0; b < N; b += 8) {
+        float phi[8], e[8];
+        gelu_phi_x8(v + b, phi, e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[b + i] *= phi[i];
+    }
+}
+// acc[i] *= gelu'(x[i])
+template <int N>
+__device__ __forceinline__ void gelu_erf_grad_batch(float (&acc)[N], const float (&x)[N]) {
+#pragma unroll
+    for (int b = 0; b < N; b += 8) {
+        float phi[8], e[8];
+        gelu_phi_x8(x + b, phi, e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[b + i] *= fmaf(x[b + i] * 0.39894228040143267794f, e[i], phi[i]);
+    }
 }
 
 // ---------------------------------------------------------------- dropout (training mode)

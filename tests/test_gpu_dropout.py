@@ -231,4 +231,4 @@ def test_train_step_with_dropout_is_deterministic_and_differs():
     z_s, z_g, _ = one(tr0)
     # (1/(1-p) = 1 + 1 ulp still flips a few bf16 roundings → agreement to bf16 noise, not bitwise)
     assert torch.allclose(z_s[:9], n_s[:9], rtol=2e-3, atol=1e-3)
-    assert (z_g - n_g).abs().max().item() <= 2e-2 * n_g.abs().max().item()
+    assert float((z_g - n_g).norm() / n_g.norm()) <= 5e-2

@@ -30,7 +30,8 @@ elif what == "gemm":
     a = torch.randn(m, k, device=dev).to(torch.bfloat16)
     w = torch.randn(n, k, device=dev).to(torch.bfloat16)
     bias = torch.randn(n, device=dev)
+    act = sys.argv[5] if len(sys.argv) > 5 else None
     for _ in range(3):
-        ops.gemm(a, w, bias=bias)
+        ops.gemm(a, w, bias=bias, act=act)
 torch.cuda.synchronize()
 print("done")
