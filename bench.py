@@ -171,6 +171,7 @@ def run_ours(args):
     _lib.profiler = prof
     tr.train_step(inp, batch)
     agg = prof.summary()
+    by_tag = prof.by_tag()
     _lib.profiler = None
     if rank != 0:
         if world > 1:
@@ -196,6 +197,19 @@ def run_ours(args):
         rate = x["work"] / (x["ms"] * 1e-3) / (1e12 if x["kind"] == "tensor" else 1e9) if x["ms"] > 0 else 0.0
         kernels[n] = dict(calls=x["calls"], ms=round(x["ms"], 3), share=round(x["ms"] / step_ms_prof, 3),
                           rate=round(rate, 1), unit="TFLOP/s" if x["kind"] == "tensor" else "GB/s")
+
+    # the dominant entry point is 425 launches of very different sizes: its largest shapes, each against the same peak
+    # (traffic: dram__bytes_read+write per launch from the ncu --set full captures under profiles/, where taken)
+    ncu_traffic = {"12576x3072x768 NN": 104.2e6}
+    shapes = []
+    for (n, tag), x in sorted(by_tag.items(), key=lambda kv: -kv[1]["ms"]):
+        if n != name or len(shapes) >= 8:
+            continue
+        r = x["work"] / (x["ms"] * 1e-3) / (1e12 if a["kind"] == "tensor" else 1e9)
+        shapes.append(dict(shape=tag, calls=x["calls"], avg_launch_us=round(1e3 * x["ms"] / x["calls"], 2),
+                           achieved=round(r, 1), frac=round(r / (peaks["tensor"] if a["kind"] == "tensor" else peaks["hbm"]), 3),
+                           traffic=ncu_traffic.get(tag)))
+    roof["largest_shapes"] = shapes
 
     clips = BATCH_PER_GPU * world
     line = {

@@ -111,6 +111,9 @@ typedef struct {
                           (128/256 only) or | 2048 to forbid them */
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
+/* Debug aid: CTA 0 of subsequent shg_gemm launches writes 7 %globaltimer phase stamps to buf (8 x u64 device
+ * memory); NULL = off. */
+int shg_debug_gemm_stamps(void* buf);
 
 /* ------------------------------------------------------------------ attention (tcgen05, head dim 64)
  * O = softmax(scale * Q K^T + mask) V per (batch, head).  Replaces BertAttention's matmul/softmax/matmul

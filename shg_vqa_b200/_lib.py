@@ -60,6 +60,7 @@ SIGNATURES = {
     "shg_set_loss_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp],
     "shg_set_loss_bwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_int, c_int, c_vp],
     "shg_gemm": [ctypes.POINTER(GemmArgs), c_vp],
+    "shg_debug_gemm_stamps": [c_vp],
     "shg_attn_fwd": [ctypes.POINTER(AttnArgs), c_vp],
     "shg_attn_bwd": [ctypes.POINTER(AttnBwdArgs), c_vp],
     "shg_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp],

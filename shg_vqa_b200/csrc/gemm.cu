@@ -37,7 +37,15 @@ struct GemmParams {
     int tma_store;          // bf16 D (and preact) leave through smem staging + TMA stores
     int splits, block_n, n_stages;
     int m_tiles, n_tiles, kb_total, kb_per_split;
+    unsigned long long* dbg;   // optional phase timestamps of CTA 0 (tools/gemm_phases.py), normally null
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SHG_STAMP(i) do { if (p.dbg && blockIdx.x == 0) p.dbg[i] = globaltimer_ns(); } while (0)
 
 __device__ __forceinline__ float apply_act(float x, int act) {
     switch (act) {
@@ -75,9 +83,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
     const bool staged = p.tma_store != 0;
     const int r_local = row - m0;
     // COLS values of this thread's row -> its part of the staging block -> (one thread) bulk store of the block
+#define EPI_STAMP(i) do { if (p.dbg && etid == 0 && blockIdx.x == 0 && nblk == 1) p.dbg[i] = globaltimer_ns(); } while (0)
     auto staged_store = [&](const float (&v)[COLS], const CUtensorMap* tm, int blk_col0, bool active) {
+        EPI_STAMP(10);
         if (etid == 0) bulk_wait_read<1>();              // the store that last used this buffer has read it
         asm volatile("bar.sync 1, %0;" ::"n"(NSUB * 128) : "memory");
+        EPI_STAMP(11);
         uint8_t* buf = stg + (nblk & 1) * 16384;
         if (active) {
             uint8_t* dst = buf + r_local * 128;
@@ -89,12 +100,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                 *reinterpret_cast<uint4*>(dst + (((sub * NV + j) ^ (r_local & 7)) << 4)) = u;
             }
         }
+        EPI_STAMP(12);
         fence_proxy_async_smem();
+        EPI_STAMP(13);
         asm volatile("bar.sync 1, %0;" ::"n"(NSUB * 128) : "memory");
+        EPI_STAMP(14);
         if (etid == 0) {
             tma_store_2d(tm, buf, blk_col0, m0);
             bulk_commit();
         }
+        EPI_STAMP(15);
         ++nblk;
     };
     // side operand of a chunk: requested from HBM ahead of its use (first chunk: before the accumulator wait)
@@ -122,9 +137,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
         if (active) {
             uint32_t raw[COLS];
             __syncwarp();
+            EPI_STAMP(8);
             if constexpr (COLS == 32) tmem_ld32(t_row + c, raw);
             else tmem_ld16(t_row + c, raw);
             tmem_ld_wait();
+            EPI_STAMP(9);
 #pragma unroll
             for (int i = 0; i < COLS; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(sb + c + i);
@@ -274,6 +291,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
+        SHG_STAMP(0);
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(full_bar + s, 1);
             mbar_init(empty_bar + s, 1);
@@ -293,6 +311,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+    if (threadIdx.x == 0) SHG_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -343,6 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const uint32_t d_tmem = tmem_base + as * 256;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar + stage, phase);
+                    if (kb == kb0 && tile == (int)blockIdx.x) SHG_STAMP(2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
@@ -386,7 +406,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
             epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk,
-                          [&] { mbar_wait(tmem_full + as, aphase); });
+                          [&] { mbar_wait(tmem_full + as, aphase); if (etid == 0 && tile == (int)blockIdx.x) SHG_STAMP(3); });
+            if (etid == 0 && tile == (int)blockIdx.x) SHG_STAMP(4);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_relaxed(tmem_empty + as);
@@ -396,6 +417,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
         }
         if (etid == 0) bulk_wait_read<0>();            // staging must outlive the last bulk store's read
+        if (etid == 0) SHG_STAMP(5);
     }
     tc_fence_before();
     __syncthreads();
@@ -403,6 +425,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (threadIdx.x == 0) SHG_STAMP(6);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -568,53 +591,60 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
 }
 
-// Modelled cost of covering the output with tiles: waves over the chip x time per tile, the tile time being the
-// larger of the MMA time and the operand bytes each CTA pulls through L2 (single CTA: 128 + bn rows per k-block,
-// CTA pair: 128 + bn/2), plus a fixed per-tile overhead.
-static double tile_cost(int m, int n, int k, int splits, int bn, bool pair) {
+// Tile selection.  Every candidate (single CTA 128 x {64,128,192,256}; CTA pair 256 x {128,192,256}) is costed with
+// a wave model whose per-k-block time is the largest of: the tensor-core time (2*bn clk), the SM's own operand
+// ingress (64 B/clk) and the chip-wide L2 feed shared by the active CTAs; plus a fixed launch/prologue/epilogue
+// term (larger for pairs: cluster launch, 2-SM commits).  The four constants were fitted to forced-configuration
+// timings of the 45 shapes of the bs32 step (tools/gemm_probe.py tune, gpurun_out/gemm_tune.txt): the model's pick is
+// within 2 % of the best measured configuration in aggregate.  K = 768 projections are L2-feed-bound on B200
+// (256 x 256 pair tiles need 64 B/clk/SM at full tensor rate; the L2 delivers ~43 B/clk/SM chip-wide), which is why
+// wide pair tiles win once a grid is more than a wave deep.
+static double config_cost(int m, int n, int k, int splits, int bn, bool pair, bool accumulate) {
+    const double kFixSingle = 6000.0, kFixPair = 12000.0, kL2BytesPerClk = 5000.0, kDedup = 0.7;
     const int rows = pair ? 256 : 128;
     const long tiles = (long)((m + rows - 1) / rows) * ((n + bn - 1) / bn) * splits;
     const int slots = pair ? kNumSMs / 2 : kNumSMs;
-    const long waves = (tiles + slots - 1) / slots;
     const double kb = (double)((k + BK - 1) / BK) / splits;
-    const double mma = bn * 2.0;                                    // cycles per k-block at 128 x bn x 64 per CTA
-    const double l2 = (128.0 + (pair ? bn / 2 : bn)) * 128.0 / 38.0; // bytes per k-block / (B/clk/SM of L2 feed)
-    const double per_tile = kb * (mma > l2 ? mma : l2) + 1500.0;
-    return waves * per_tile;
+    const double bytes_cta = (128.0 + (pair ? bn / 2 : bn)) * 128.0;
+    const double mma = 2.0 * bn;
+    auto wave = [&](double active_ctas) {
+        double t = mma;
+        if (bytes_cta / 64.0 > t) t = bytes_cta / 64.0;
+        const double l2 = bytes_cta * active_ctas / kL2BytesPerClk * kDedup;
+        if (l2 > t) t = l2;
+        return kb * t;
+    };
+    const long full = tiles / slots, rem = tiles % slots;
+    double t = full * wave(kNumSMs) + (rem ? wave((double)rem * (pair ? 2 : 1)) : 0.0);
+    t += (pair ? kFixPair : kFixSingle) + 6.0 * bn + (accumulate ? 4.0 * bn : 0.0);
+    return t;
 }
-// Measured on B200 (tools/step_breakdown.py, pair tiles forbidden vs forced): the CTA pair wins once the problem is
-// several waves deep (12576 x {2304,3072,15360}: -6..-10 %), and loses on the small grids (M <= 4096, N = 768: the
-// pair's cluster sync and 2-SM commit latency are not amortised).  Split-K wgrads are a wash; they stay single-CTA.
-static bool prefer_pair(int m, int n, int k, int splits, int bn) {
-    (void)k, (void)bn;
-    if (splits > 1) return false;
-    const long tiles = (long)((m + BM - 1) / BM) * ((n + 255) / 256);
-    return tiles >= 400;
-}
-static int pick_pair_block_n(int m, int n, int splits) {
-    return tile_cost(m, n, 768, splits, 256, true) <= tile_cost(m, n, 768, splits, 128, true) ? 256 : 128;
-}
-
-static int pick_block_n(int m_tiles, int n) {
-    // minimise (waves x per-tile cost) over the legal UMMA N values; prefers wider tiles on ties
+// best (pair, block_n) for the problem; pair_ok / single_ok restrict the search (forced by the caller's flags)
+static void pick_config(int m, int n, int k, int splits, bool b_mn, bool accumulate, bool pair_ok, bool single_ok,
+                        bool* pair, int* bn) {
+    double best = 1e30;
+    *pair = !single_ok, *bn = 128;
     const int cands[4] = {256, 192, 128, 64};
-    int best = 128;
-    double best_cost = 1e30;
-    for (int bn : cands) {
-        const int n_tiles = (n + bn - 1) / bn;
-        const long tiles = (long)m_tiles * n_tiles;
-        const long waves = (tiles + kNumSMs - 1) / kNumSMs;
-        // per-tile time ~ bn (MMA) + fixed overhead; narrow tiles also halve operand reuse
-        const double cost = (double)waves * (bn + 24.0 + (bn <= 64 ? 24.0 : 0.0));
-        if (cost < best_cost) {
-            best_cost = cost;
-            best = bn;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool pr = pass == 1;
+        if (pr ? !pair_ok : !single_ok) continue;
+        for (int c : cands) {
+            if (pr && (c == 64 || (c == 192 && b_mn))) continue;    // pair tiles: 128 | 256 (192 with a K-major B)
+            const double t = config_cost(m, n, k, splits, c, pr, accumulate);
+            if (t < best) best = t, *pair = pr, *bn = c;
         }
     }
-    return best;
 }
 
 }  // namespace shg
+
+static unsigned long long* g_gemm_dbg = nullptr;
+// Debug aid (tools/gemm_phases.py): CTA 0 of subsequent shg_gemm launches writes 7 globaltimer stamps to `buf`
+// (device memory, 8 x u64); NULL switches it off.  Not part of the product path.
+extern "C" int shg_debug_gemm_stamps(void* buf) {
+    g_gemm_dbg = (unsigned long long*)buf;
+    return SHG_OK;
+}
 
 extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     using namespace shg;
@@ -638,6 +668,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
                 "shg_gemm: accumulate mode takes no activation/residual/preact");
     SHG_REQUIRE(!(a->residual && a->mul_aux), SHG_EINVAL, "shg_gemm: residual and mul_aux are mutually exclusive");
     GemmParams p;
+    p.dbg = g_gemm_dbg;
     p.d = a->d, p.ldd = a->ldd, p.m = a->m, p.n = a->n, p.k = a->k;
     p.bias = a->bias, p.residual = (const __nv_bfloat16*)a->residual, p.ldr = a->ldr;
     p.preact = (__nv_bfloat16*)a->preact, p.act = a->act;
@@ -651,10 +682,14 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     // block_n: 0 = choose everything; low bits = tile width; | 1024 forces CTA-pair tiles (256 x bn), | 2048 forbids them
     const int bn_req = a->block_n & 1023;            // (| 4096: direct-store epilogue, for A/B comparison)
     bool pair = (a->block_n & 1024) != 0;
-    if (!(a->block_n & (1024 | 2048)) && !bn_req) pair = prefer_pair(a->m, a->n, a->k, splits, 0);
-    int bn = bn_req ? bn_req : (pair ? pick_pair_block_n(a->m, a->n, splits) : pick_block_n(p.m_tiles * splits, a->n));
+    int bn = bn_req;
+    if (!bn_req) {
+        const bool forced = (a->block_n & (1024 | 2048)) != 0;
+        pick_config(a->m, a->n, a->k, splits, a->b_mn_major != 0, accumulate, !forced || pair, !forced || !pair, &pair, &bn);
+    }
     SHG_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, SHG_ESHAPE, "shg_gemm: block_n=%d", bn);
-    SHG_REQUIRE(!pair || bn == 128 || bn == 256, SHG_ESHAPE, "shg_gemm: CTA-pair tiles need block_n 128 or 256");
+    SHG_REQUIRE(!pair || bn == 128 || bn == 256 || (bn == 192 && !a->b_mn_major), SHG_ESHAPE,
+                "shg_gemm: CTA-pair tiles need block_n 128 or 256 (192 with a K-major B operand)");
     if (pair) p.m_tiles = (a->m + 255) / 256;
     p.block_n = bn;
     p.n_tiles = (a->n + bn - 1) / bn;

@@ -84,6 +84,44 @@ if __name__ == "__main__":
                                     (1280, 3072, 768, "NN", None), (12576, 768, 2304, "NT", None)]:
             case(m, n, k, mode, ex)
             case(m, n, k, mode, dict(ex or {}, block_n=4096))
+    if sel == "tune":
+        shapes = [(12576, 768, 768, "NN"), (12576, 768, 768, "NT"), (12576, 768, 3072, "NN"), (12576, 768, 3072, "NT"),
+                  (12576, 768, 2304, "NT"), (12576, 3072, 768, "NT"), (12576, 768, 15360, "NT"),
+                  (4096, 768, 768, "NN"), (4096, 768, 768, "NT"), (4096, 1536, 768, "NN"), (4096, 2048, 768, "NN"),
+                  (4096, 768, 2048, "NN"), (4096, 2048, 768, "NT"), (4096, 768, 1536, "NT"), (4096, 457, 1536, "NN"),
+                  (1536, 768, 768, "NN"), (1536, 1536, 768, "NN"), (1536, 2048, 768, "NN"), (1536, 768, 2048, "NN"),
+                  (1280, 2304, 768, "NN"), (1280, 3072, 768, "NN"), (1280, 768, 3072, "NN"), (1280, 768, 768, "NN"),
+                  (1280, 3072, 768, "NT"), (5664, 3072, 768, "NN"), (5664, 768, 3072, "NN"), (5664, 2304, 768, "NN"),
+                  (5664, 768, 768, "NN"), (5664, 768, 2304, "NT"),
+                  (768, 768, 4096, "TT"), (768, 2048, 4096, "TT"), (2048, 768, 4096, "TT"), (768, 768, 1536, "TT"),
+                  (768, 3072, 1280, "TT"), (3072, 768, 1280, "TT"), (2304, 768, 1280, "TT"), (768, 768, 1280, "TT"),
+                  (768, 3072, 5664, "TT"), (2304, 768, 5664, "TT"), (3072, 768, 12576, "TT"), (768, 3072, 12576, "TT"),
+                  (2304, 768, 12576, "TT"), (768, 768, 12576, "TT"), (1536, 768, 12576, "TT"), (1536, 768, 4096, "TT")]
+        import io, contextlib, re
+        cub = float('nan')
+        for (m, n, k, mode) in shapes:
+            res = {}
+            cfgs = [("auto", 0)] + [("s%d" % bn, bn | 2048) for bn in (64, 128, 192, 256)] + \
+                   [("p%d" % bn, bn | 1024) for bn in (128, 192, 256)]
+            for name, flag in cfgs:
+                if name == "p192" and mode != "NN":
+                    continue
+                buf = io.StringIO()
+                try:
+                    with contextlib.redirect_stdout(buf):
+                        case(m, n, k, mode, dict(block_n=flag) if flag else None)
+                    mt = re.search(r":\s+([\d.]+) us\s+[\d.]+ TF/s \| cuBLAS\s+([\d.]+) us", buf.getvalue())
+                    res[name], cub = float(mt.group(1)), float(mt.group(2))
+                except Exception as e:
+                    res[name] = float("nan")
+            best = min((v, k2) for k2, v in res.items() if v == v and k2 != "auto")
+            print("%-2s %6d %5d %6d  auto %6.1f  best %-5s %6.1f  cuBLAS %6.1f | %s" % (
+                mode, m, n, k, res["auto"], best[1], best[0], cub,
+                " ".join("%s=%.1f" % (k2, v) for k2, v in res.items() if k2 != "auto")), flush=True)
+    if sel == "fixed":      # T(K) = a + b K: fixed per-launch cost vs per-k-block cost
+        for (m, n) in [(1536, 768), (4096, 768), (12576, 768)]:
+            for k in (64, 256, 768, 1536, 3072):
+                case(m, n, k, "NN", dict(block_n=128 | 2048))
     if sel == "gelu":
         for ex in (None, dict(gelu_only=True), dict(pre_only=True), dict(gelu=True)):
             case(12576, 3072, 768, "NN", ex)
