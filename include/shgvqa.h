@@ -140,6 +140,8 @@ typedef struct {
      * nn.MultiheadAttention(dropout=0.15), lxrt/transformer.py:192-193): o = (dropout(softmax(s)) v); the mask is a
      * pure function of (*dropout_seed, dropout_salt, batch, head, query, key).  dropout_seed NULL = off. */
     float dropout_p; uint32_t dropout_salt; const uint32_t* dropout_seed;
+    uint32_t* dropout_bits;   /* optional out: the keep mask as bit words [batch, heads, lq, ceil(lk/32)] (bit k%32 of word
+                                 k/32 = key k kept), so that the backward reads 1 bit instead of re-hashing per element */
 } shg_attn_args;
 int shg_attn_fwd(const shg_attn_args* args, void* stream);
 
@@ -165,8 +167,8 @@ typedef struct {
     int q_per_frame, k_per_frame;
     const float* o_f32; int64_t ldof;   /* fp32 o from the forward: delta = rowsum(d_o * o_f32) in one sweep; NULL:
                                            delta from an extra sweep over the keys (same accuracy, ~40 % more work) */
-    float dropout_p; uint32_t dropout_salt; const uint32_t* dropout_seed;   /* same triple as the forward call;
-                                           requires o_f32 (delta must come from the dropped-out forward output) */
+    float dropout_p; uint32_t dropout_salt; const uint32_t* dropout_seed;   /* same triple as the forward call */
+    const uint32_t* dropout_bits;   /* the forward's keep-bit words, or NULL: the mask is regenerated from the triple */
 } shg_attn_bwd_args;
 int shg_attn_bwd(const shg_attn_bwd_args* args, void* stream);
 

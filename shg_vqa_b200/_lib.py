@@ -37,7 +37,8 @@ class AttnArgs(ctypes.Structure):
                 ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
                 ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
                 ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64),
-                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp)]
+                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp),
+                ("dropout_bits", c_vp)]
 
 
 class AttnBwdArgs(ctypes.Structure):
@@ -47,7 +48,8 @@ class AttnBwdArgs(ctypes.Structure):
                 ("batch", c_int), ("heads", c_int), ("lq", c_int), ("lk", c_int),
                 ("scale", c_f32), ("mask_mode", c_int), ("key_mask", c_vp),
                 ("q_per_frame", c_int), ("k_per_frame", c_int), ("o_f32", c_vp), ("ldof", c_i64),
-                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp)]
+                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp),
+                ("dropout_bits", c_vp)]
 
 
 # name -> argtypes (all return int).  Must list every symbol include/shgvqa.h declares.

@@ -29,6 +29,7 @@ struct AttnParams {
     float scale;
     int mask_mode, q_per_frame, k_per_frame;
     DropCfg drop;           // dropout on the probabilities (training mode)
+    uint32_t* drop_bits;    // optional out: keep-bit words [batch, heads, lq, lk32/32]
 };
 
 // Dropout on the probabilities: element (b, h, q, k) of a call site is pair (row_pair0(b,h,q) + k/2), lane k & 1 of
@@ -170,6 +171,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
         uint8_t* blk = sP + (c >> 6) * 16384 + row * 128;
         const int j0 = (c & 32) ? 4 : 0;
+        uint32_t keep_bits = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -186,11 +188,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 // softmax is normalised over ALL keys; the dropped ones are zeroed only in the P.V operand and
                 // the survivors' 1/(1-p) is folded into the final row scaling
                 const uint32_t pb = row_pair0 + ((c + 8 * j) >> 1);
-                u.x &= drop_pair_mask(dkey, pb, dth), u.y &= drop_pair_mask(dkey, pb + 1, dth);
-                u.z &= drop_pair_mask(dkey, pb + 2, dth), u.w &= drop_pair_mask(dkey, pb + 3, dth);
+                const uint32_t k0 = drop_pair(dkey, pb, dth), k1 = drop_pair(dkey, pb + 1, dth);
+                const uint32_t k2 = drop_pair(dkey, pb + 2, dth), k3 = drop_pair(dkey, pb + 3, dth);
+                u.x &= (k0 & 1u) * 0xffffu + (k0 >> 1) * 0xffff0000u, u.y &= (k1 & 1u) * 0xffffu + (k1 >> 1) * 0xffff0000u;
+                u.z &= (k2 & 1u) * 0xffffu + (k2 >> 1) * 0xffff0000u, u.w &= (k3 & 1u) * 0xffffu + (k3 >> 1) * 0xffff0000u;
+                keep_bits |= (k0 | (k1 << 2) | (k2 << 4) | (k3 << 6)) << (8 * j);
             }
             *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) = u;
         }
+        if (DROP && p.drop_bits && q < p.lq)
+            p.drop_bits[(((size_t)b * p.heads + h) * p.lq + q) * (p.lk32 >> 5) + (c >> 5)] = keep_bits;
     }
     s_red[quad * 128 + row] = sum;
     fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core's async proxy
@@ -280,6 +287,7 @@ struct AttnBwdParams {
     float scale;
     int mask_mode, q_per_frame, k_per_frame;
     DropCfg drop;
+    const uint32_t* drop_bits;   // the forward's keep-bit words [batch, heads, lq, lk32/32], or null (re-hash)
 };
 
 // 32 consecutive bf16 of row `row` at column c (multiple of 32) of a [128 x 128] K-major tile made of two
@@ -321,14 +329,15 @@ __device__ __forceinline__ uint64_t rows_b_desc(uint32_t tile, int ks) {
 // every column visible) is 4 issue slots per element: FFMA, MUFU.EX2, FFMA, FMUL (+ the bf16 pack).
 // ---------------------------------------------------------------------------------------------------------
 // dq pass: ds_e = p_e * (dP_e * scale - delta * scale),  p_e = 2^(s_e * c1 [+ kmask_e] - lse)
-template <bool KMASK, bool DROP, bool VIS>
+// DROP: 0 = no dropout, 1 = mask regenerated from the counter hash, 2 = mask read from the forward's keep-bit word
+template <bool KMASK, int DROP, bool VIS>
 __device__ __forceinline__ void dq_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&ds)[16],
                                               float c1, float neg_lse, const float* km, int n_vis, float scale_keep,
-                                              float nds, uint32_t dkey, uint32_t pair0, uint32_t dth) {
+                                              float nds, uint32_t dkey, uint32_t pair0, uint32_t dth, uint32_t bits) {
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
         uint32_t dmask = 0xffffffffu;
-        if (DROP) dmask = drop_pair_mask(dkey, pair0 + (i >> 1), dth);
+        if (DROP == 1) dmask = drop_pair_mask(dkey, pair0 + (i >> 1), dth);
         float v2[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -338,7 +347,8 @@ __device__ __forceinline__ void dq_group_math(const uint32_t (&rs)[32], const ui
             const float pr = ex2_approx(x);
             // o = dropout(P) V: the gradient reaches P_ij only through a kept entry, scaled by 1/(1-p) (in scale_keep)
             float g = fmaf(__uint_as_float(rp[e]), scale_keep, nds);
-            if (DROP) g = (dmask & (t ? 0xffff0000u : 0x0000ffffu)) ? g : nds;
+            if (DROP == 1) g = (dmask & (t ? 0xffff0000u : 0x0000ffffu)) ? g : nds;
+            if (DROP == 2) g = (bits >> e) & 1u ? g : nds;
             const float v = pr * g;
             v2[t] = (VIS || e < n_vis) ? v : 0.f;
         }
@@ -347,15 +357,21 @@ __device__ __forceinline__ void dq_group_math(const uint32_t (&rs)[32], const ui
 }
 
 // dkv pass (thread = key row, 32 queries): p_e as above with per-query lse, pd_e = dropout(p)_e (-> dV), ds_e (-> dK)
-template <bool DROP, bool VIS>
+template <int DROP, bool VIS>
 __device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&pr)[16],
                                                uint32_t (&ds)[16], float c1, float kbias, const float* lse, const float* del,
                                                int e_first, float scale_keep, float inv_keep, uint32_t dkey,
-                                               uint32_t pair0, uint32_t pair_stride, uint32_t dth, uint32_t lane_mask) {
+                                               uint32_t pair0, uint32_t pair_stride, uint32_t dth, uint32_t lane_mask,
+                                               const uint32_t* bits, int bit) {
 #pragma unroll
     for (int e = 0; e < 32; e += 4) {
         const float4 l4 = *reinterpret_cast<const float4*>(lse + e);
         const float4 d4 = *reinterpret_cast<const float4*>(del + e);
+        uint32_t bw[4] = {0, 0, 0, 0};
+        if (DROP == 2) {
+            const uint4 w4 = *reinterpret_cast<const uint4*>(bits + e);     // keep words of queries e..e+3 (this key's word)
+            bw[0] = w4.x, bw[1] = w4.y, bw[2] = w4.z, bw[3] = w4.w;
+        }
         const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv4[4] = {d4.x, d4.y, d4.z, d4.w};
         float po[4], so[4];
 #pragma unroll
@@ -365,7 +381,8 @@ __device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[32], const u
             if (!VIS) pe = (e + t >= e_first) ? pe : 0.f;
             float g = fmaf(__uint_as_float(rp[e + t]), scale_keep, -dv4[t]), pd = pe;
             if (DROP) {
-                const bool keep = drop_pair_mask(dkey, pair0 + (uint32_t)(e + t) * pair_stride, dth) & lane_mask;
+                const bool keep = DROP == 2 ? ((bw[t] >> bit) & 1u) != 0
+                                            : (drop_pair_mask(dkey, pair0 + (uint32_t)(e + t) * pair_stride, dth) & lane_mask) != 0;
                 g = keep ? g : -dv4[t];
                 pd = keep ? pe * inv_keep : 0.f;          // dV = dropout(P)^T dO
             }
@@ -377,7 +394,7 @@ __device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[32], const u
     }
 }
 
-template <bool DROP>
+template <int DROP>
 __global__ void __launch_bounds__(kBwdThreads)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
                    const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
@@ -517,6 +534,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         const int n16 = chunk_n16(j);
         const int c = quad * 32;
         const bool live = rows_live && c < n16;     // warp-uniform
+        uint32_t keep_word = 0;
+        if (DROP == 2 && live && q < p.lq)          // requested ahead of the wait for the score products
+            keep_word = __ldg(p.drop_bits + (((size_t)b * p.heads + h) * p.lq + q) * (size_t)((p.lk + 31) >> 5) + j * 4 + quad);
         mbar_wait(bar_s, jj & 1);
         tc_fence_after();
         uint32_t rs[32], rp[32];
@@ -552,7 +572,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     if (kmask) x += s_kmask[key0 + i];
                     const float pr = i < n_vis ? ex2_approx(x) : 0.f;
                     float dp = __uint_as_float(rp[i]);
-                    if (DROP) dp = drop_keep(dkey, 2ull * row_pair0 + (uint32_t)(key0 + i), dth) ? dp * inv_keep : 0.f;
+                    if (DROP == 1) dp = drop_keep(dkey, 2ull * row_pair0 + (uint32_t)(key0 + i), dth) ? dp * inv_keep : 0.f;
+                    if (DROP == 2) dp = (keep_word >> i) & 1u ? dp * inv_keep : 0.f;
                     acc_p += pr;
                     acc_pd = fmaf(pr, dp, acc_pd);
                 }
@@ -561,11 +582,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 const uint32_t pair0 = row_pair0 + (uint32_t)(key0 >> 1);
                 const float* km = s_kmask + key0;
                 if (__all_sync(0xffffffffu, n_vis >= 32)) {
-                    if (kmask) dq_group_math<true, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
-                    else dq_group_math<false, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
+                    if (kmask) dq_group_math<true, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
+                    else dq_group_math<false, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
                 } else {
-                    if (kmask) dq_group_math<true, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
-                    else dq_group_math<false, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth);
+                    if (kmask) dq_group_math<true, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
+                    else dq_group_math<false, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
                 }
                 if (j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
                 store_tile_chunk32_packed(tile, row, c, ds);
@@ -622,7 +643,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     }
 }
 
-template <bool DROP>
+template <int DROP>
 __global__ void __launch_bounds__(kBwdThreads)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
                     const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
@@ -635,9 +656,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     uint8_t* sdO = smem + 81920;              // 3 x 16 KB
     uint8_t* sPt = smem + 131072;             // 32 KB   P^T  [128 keys x 128 queries]
     uint8_t* sdSt = smem + 163840;            // 32 KB   dS^T
-    float* s_lse = reinterpret_cast<float*>(smem + kBwdTileBytes);   // [2][128]
-    float* s_delta = s_lse + 256;                                      // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
+    float* s_lse = reinterpret_cast<float*>(smem + kBwdTileBytes);   // [4][128] ring over query chunks
+    float* s_delta = s_lse + 512;                                      // [4][128]
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_delta + 512);     // [4][4 key words][128 queries] keep-bit words
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bits + 2048);
     uint64_t* bar_kv = bars;
     uint64_t* bar_q = bars + 1;      // [3]
     uint64_t* bar_s = bars + 4;
@@ -682,13 +704,27 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         tma_load_3d(sQ + st * 16384, &tma_q, bar_q + st, h * kHeadDim, i * 128, b);
         tma_load_3d(sdO + st * 16384, &tma_do, bar_q + st, h * kHeadDim, i * 128, b);
     };
-    auto load_vec = [&](int i) {  // lse / delta of query chunk i -> smem (all 256 threads)
+    // Per-query vectors of a chunk (lse, delta, and with stored dropout masks the four keep-bit words of this key
+    // tile) go global -> register at the TOP of an iteration and register -> shared memory at its END, two chunks
+    // ahead of their use: a global load feeding a shared store directly would stall the thread for an HBM/L2 round
+    // trip on every chunk.
+    const int nw = (p.lk + 31) >> 5;
+    auto fetch_vec = [&](int i, float& v, uint32_t& w) {
         const int qq = i * 128 + (tid & 127);
         const size_t base = ((size_t)b * p.heads + h) * p.lq;
-        if (tid < 128) s_lse[(i & 1) * 128 + tid] = qq < p.lq ? p.lse[base + qq] * kLog2e : INFINITY;
-        else if (tid < 256) s_delta[(i & 1) * 128 + (tid - 128)] = qq < p.lq ? p.delta[base + qq] * p.scale : 0.f;   // pre-scaled
+        v = 0.f, w = 0u;
+        if (tid < 128) v = qq < p.lq ? __ldg(p.lse + base + qq) * kLog2e : INFINITY;
+        else if (tid < 256) v = qq < p.lq ? __ldg(p.delta + base + qq) * p.scale : 0.f;       // pre-scaled
+        if (DROP == 2) {
+            const int ql = i * 128 + (tid >> 2), kw = (k0 >> 5) + (tid & 3);
+            if (ql < p.lq && kw < nw) w = __ldg(p.drop_bits + (base + ql) * nw + kw);
+        }
     };
-
+    auto stash_vec = [&](int i, float v, uint32_t w) {
+        if (tid < 128) s_lse[(i & 3) * 128 + tid] = v;
+        else if (tid < 256) s_delta[(i & 3) * 128 + (tid - 128)] = v;
+        if (DROP == 2) s_bits[(i & 3) * 512 + (tid & 3) * 128 + (tid >> 2)] = w;
+    };
     if (tid == 0) {
         mbar_expect_tx(bar_kv, 32768);
         tma_load_3d(sK, &tma_k, bar_kv, h * kHeadDim, k0, b);
@@ -701,7 +737,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         tc_fence_after();
         issue_s(0);
     }
-    load_vec(0);
+    {
+        float v;
+        uint32_t w;
+        fetch_vec(0, v, w), stash_vec(0, v, w);
+        if (n_qc > 1) fetch_vec(1, v, w), stash_vec(1, v, w);
+    }
     __syncthreads();
 
     const int row = (warp & 3) * 32 + lane, quad = warp >> 2;
@@ -715,7 +756,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     uint32_t dkey = 0, dth = 0, lane_mask = 0, pair_stride = 0, col_pair0 = 0;
     float inv_keep = 1.f;
     if (DROP) {
-        dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
+        if (DROP == 1) dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
         inv_keep = 1.f / (1.f - p.drop.p);
         lane_mask = (key & 1) ? 0xffff0000u : 0x0000ffffu;
         pair_stride = attn_row_pair0(0, p.heads, 0, p.lq, 1, p.lk);                 // pairs per query row
@@ -725,7 +766,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     const bool rows_live = k0 + (warp & 3) * 32 < p.lk;     // warps of key rows beyond lk: nothing to do (dK/dV rows unused)
     const float scale_keep = p.scale * inv_keep;
     for (int i = 0; i < n_qc; ++i) {
-        if (i + 1 < n_qc) load_vec(i + 1);          // other buffer; consumed after the next __syncthreads
+        float nxt_v = 0.f;
+        uint32_t nxt_w = 0u;
+        if (i + 2 < n_qc) fetch_vec(i + 2, nxt_v, nxt_w);
         const int n16 = chunk_n16(i);
         const int c = quad * 32;
         const bool live = rows_live && c < n16;     // warp-uniform
@@ -752,21 +795,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
         }
         if (live) {
-            const float* lse_i = s_lse + (i & 1) * 128 + c;
-            const float* del_i = s_delta + (i & 1) * 128 + c;
+            const float* lse_i = s_lse + (i & 3) * 128 + c;
+            const float* del_i = s_delta + (i & 3) * 128 + c;
+            const uint32_t* bits_i = s_bits + (i & 3) * 512 + (row >> 5) * 128 + c;
             uint32_t pr[16], ds[16];
             // first query of this group that sees the key (block-causal); queries beyond lq carry lse = +inf -> p = 0
             const int e_first = key_ok ? q_first - (i * 128 + c) : 32;
             const uint32_t pair0 = col_pair0 + (uint32_t)(i * 128 + c) * pair_stride;
             if (__all_sync(0xffffffffu, e_first <= 0))
-                dkv_group_math<DROP, true>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask);
+                dkv_group_math<DROP, true>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask, bits_i, row & 31);
             else
-                dkv_group_math<DROP, false>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask);
+                dkv_group_math<DROP, false>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask, bits_i, row & 31);
             if (i >= 1) mbar_wait(bar_acc, (i - 1) & 1);   // sPt / sdSt free again
             store_tile_chunk32_packed(sPt, row, c, pr);
             store_tile_chunk32_packed(sdSt, row, c, ds);
             fence_proxy_async_smem();
         }
+        if (i + 2 < n_qc) stash_vec(i + 2, nxt_v, nxt_w);     // slot (i + 2) & 3 was last read two chunks ago
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
@@ -850,6 +895,7 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     p.tmem_cols = need <= 128 ? 128 : (need <= 256 ? 256 : 512);
     p.scale = a->scale, p.mask_mode = a->mask_mode, p.q_per_frame = a->q_per_frame, p.k_per_frame = a->k_per_frame;
     p.drop.p = a->dropout_seed ? a->dropout_p : 0.f, p.drop.salt = a->dropout_salt, p.drop.seed = a->dropout_seed;
+    p.drop_bits = a->dropout_bits;
     SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_attn_fwd: dropout_p=%f", (double)p.drop.p);
     const size_t smem = (size_t)p.v_off + p.n_kbox * 8192 + (448 + 512) * 4 + 64 + 1024;
     SHG_REQUIRE(smem <= 227 * 1024, SHG_ESHAPE, "shg_attn_fwd: %zu B of shared memory needed", smem);
@@ -900,28 +946,33 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     p.scale = a->scale, p.mask_mode = a->mask_mode, p.q_per_frame = a->q_per_frame, p.k_per_frame = a->k_per_frame;
     p.drop.p = a->dropout_seed ? a->dropout_p : 0.f, p.drop.salt = a->dropout_salt, p.drop.seed = a->dropout_seed;
     SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_attn_bwd: dropout_p=%f", (double)p.drop.p);
-    const bool drop = p.drop.p > 0.f;
+    p.drop_bits = a->dropout_bits;
+    const int drop = p.drop.p > 0.f ? (p.drop_bits ? 2 : 1) : 0;
     const CUtensorMap* tq = head_tmap(a->q, a->ldq, a->heads, a->lq, a->batch, 128);
     const CUtensorMap* tdo = head_tmap(a->d_o, a->lddo, a->heads, a->lq, a->batch, 128);
     const CUtensorMap* tk = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, 128);
     const CUtensorMap* tv = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, 128);
     if (!tq || !tdo || !tk || !tv) return SHG_ECUDA;
-    const size_t smem = kBwdTileBytes + 4096 + 2048 + 128 + 1024;   // tiles + per-row vectors + key mask + barriers + slack
+    const size_t smem = kBwdTileBytes + 12288 + 128 + 1024;   // tiles + per-row vectors / key mask / keep words + barriers + slack
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 gq((a->lq + 127) / 128, a->heads, a->batch), gk((a->lk + 127) / 128, a->heads, a->batch);
-    if (drop) attn_bwd_dq_kernel<true><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
-    else attn_bwd_dq_kernel<false><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    if (drop == 2) attn_bwd_dq_kernel<2><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    else if (drop == 1) attn_bwd_dq_kernel<1><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    else attn_bwd_dq_kernel<0><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
     int rc = check_launch("shg_attn_bwd(dq)");
     if (rc) return rc;
-    if (drop) attn_bwd_dkv_kernel<true><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
-    else attn_bwd_dkv_kernel<false><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    if (drop == 2) attn_bwd_dkv_kernel<2><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    else if (drop == 1) attn_bwd_dkv_kernel<1><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    else attn_bwd_dkv_kernel<0><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
     return check_launch("shg_attn_bwd(dkv)");
 }

@@ -90,8 +90,13 @@ def attention_fwd(q, k, v, batch, lq, lk, heads=12, scale=0.125, key_mask=None, 
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
     a.o_f32, a.ldof = ptr(o32), heads * 64
     _set_drop(a, drop)
+    bits = None
+    if save_lse and drop is not None and drop[0] > 0:
+        # keep mask as bit words for the backward (1 bit per probability: 2 % of the bf16 score matrix it stands for)
+        bits = torch.empty(batch, heads, lq, (lk + 31) // 32, device=q.device, dtype=torch.int32)
+        a.dropout_bits = ptr(bits)
     call("shg_attn_fwd", a, stream(), work=("tensor", 4.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
-    return out, (lse, o32) if save_lse else None
+    return out, (lse, o32, bits) if save_lse else None
 
 
 def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, scale=0.125, key_mask=None,
@@ -99,9 +104,9 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     """Writes dq/dk/dv (bf16 views with the same head layout as q/k/v).  `lse` is what attention_fwd returned
     with save_lse: (log-sum-exp, fp32 O); a bare lse tensor selects the two-sweep delta."""
     require_device(q)
-    o32 = None
+    o32 = bits = None
     if isinstance(lse, tuple):
-        lse, o32 = lse
+        lse, o32, bits = lse
     delta = torch.empty_like(lse)
     a = AttnBwdArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = ptr(q), _ld(q), ptr(k), _ld(k), ptr(v), _ld(v)
@@ -114,6 +119,8 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     a.q_per_frame, a.k_per_frame = frames if frames is not None else (0, 0)
     a.o_f32, a.ldof = ptr(o32), (o32.stride(0) if o32 is not None else 0)
     _set_drop(a, drop)
+    if drop is not None and drop[0] > 0:
+        a.dropout_bits = ptr(bits)
     call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
 
 

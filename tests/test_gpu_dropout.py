@@ -117,6 +117,11 @@ def test_attention_dropout_fwd_bwd(ops, lq, lk, mode, p):
     out, lse = ops.attention_fwd(q, k, v, b, lq, lk, key_mask=key_mask, frames=frames, save_lse=True, drop=drop)
     keep = torch.from_numpy(keep_attn(seed_v, salt, b, 12, lq, lk, p)).to(_dev())
     assert abs(float(keep.float().mean()) - (1 - p)) < 1e-2
+    # the keep-bit words the forward hands to the backward are that same mask
+    words = lse[2].to(torch.int64) & 0xFFFFFFFF
+    kk = torch.arange(lk, device=_dev())
+    got_keep = ((words[..., kk >> 5] >> (kk & 31)) & 1).bool()
+    assert torch.equal(got_keep, keep)
 
     qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
     qh = qf.view(b, lq, 12, 64).transpose(1, 2)
@@ -138,7 +143,7 @@ def test_attention_dropout_fwd_bwd(ops, lq, lk, mode, p):
     ops.attention_bwd(q, k, v, out, d_o, lse, dq, dk, dv, b, lq, lk, key_mask=key_mask, frames=frames, drop=drop)
     dq2, dk2, dv2 = torch.zeros_like(dq), torch.zeros_like(dk), torch.zeros_like(dv)
     ops.attention_bwd(q, k, v, out, d_o, lse[0], dq2, dk2, dv2, b, lq, lk, key_mask=key_mask, frames=frames,
-                      drop=drop)                                                      # two-sweep delta route
+                      drop=drop)                                  # two-sweep delta route, mask re-hashed (no bit words)
     ref.backward(d_o.float())
     for name, got, got2, want in (("dq", dq, dq2, qf.grad), ("dk", dk, dk2, kf.grad), ("dv", dv, dv2, vf.grad)):
         tol = 3e-2 * want.abs().max().item() + 1e-6
