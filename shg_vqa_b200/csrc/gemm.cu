@@ -595,7 +595,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 // a wave model whose per-k-block time is the largest of: the tensor-core time (2*bn clk), the SM's own operand
 // ingress (64 B/clk) and the chip-wide L2 feed shared by the active CTAs; plus a fixed launch/prologue/epilogue
 // term (larger for pairs: cluster launch, 2-SM commits).  The four constants were fitted to forced-configuration
-// timings of the 45 shapes of the bs32 step (tools/gemm_probe.py tune, gpurun_out/gemm_tune.txt): the model's pick is
+// timings of the 45 shapes of the bs32 step (tools/gemm_probe.py tune, profiles/gemm_tune_r01.txt): the model's pick is
 // within 2 % of the best measured configuration in aggregate.  K = 768 projections are L2-feed-bound on B200
 // (256 x 256 pair tiles need 64 B/clk/SM at full tensor rate; the L2 delivers ~43 B/clk/SM chip-wide), which is why
 // wide pair tiles win once a grid is more than a wave deep.

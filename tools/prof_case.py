@@ -6,13 +6,15 @@ from shg_vqa_b200 import ops
 dev = torch.device("cuda:0")
 B = 32
 what = sys.argv[1]
+seed = torch.tensor([7], dtype=torch.int32, device=dev)
+DROP = (0.1, 3, seed)            # training mode, as in the bench step
 if what == "attn":
     lq = int(sys.argv[2]) if len(sys.argv) > 2 else 393
     lk = int(sys.argv[3]) if len(sys.argv) > 3 else 393
     q = torch.randn(B * lq, 2304, device=dev).to(torch.bfloat16)
     kv = torch.randn(B * lk, 2304, device=dev).to(torch.bfloat16)
     for _ in range(3):
-        ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk)
+        ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, save_lse=True, drop=DROP)
 elif what == "attn_bwd":
     lq = int(sys.argv[2]) if len(sys.argv) > 2 else 393
     lk = int(sys.argv[3]) if len(sys.argv) > 3 else 393
@@ -22,16 +24,17 @@ elif what == "attn_bwd":
     dq = torch.empty(B * lq, 768, device=dev, dtype=torch.bfloat16)
     dk = torch.empty(B * lk, 768, device=dev, dtype=torch.bfloat16)
     dv = torch.empty(B * lk, 768, device=dev, dtype=torch.bfloat16)
-    out, lse = ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, save_lse=True)
+    out, lse = ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, save_lse=True, drop=DROP)
     for _ in range(3):
-        ops.attention_bwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], out, d_o, lse, dq, dk, dv, B, lq, lk)
+        ops.attention_bwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], out, d_o, lse, dq, dk, dv, B, lq, lk, drop=DROP)
 elif what == "gemm":
     m, n, k = [int(v) for v in sys.argv[2:5]] if len(sys.argv) > 4 else (B * 393, 3072, 768)
     a = torch.randn(m, k, device=dev).to(torch.bfloat16)
     w = torch.randn(n, k, device=dev).to(torch.bfloat16)
     bias = torch.randn(n, device=dev)
     act = sys.argv[5] if len(sys.argv) > 5 else None
+    pre = torch.empty(m, n, device=dev, dtype=torch.bfloat16) if act == "gelu" else None     # FFN1 as the step runs it
     for _ in range(3):
-        ops.gemm(a, w, bias=bias, act=act)
+        ops.gemm(a, w, bias=bias, act=act, preact=pre)
 torch.cuda.synchronize()
 print("done")
