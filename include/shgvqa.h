@@ -247,6 +247,53 @@ int shg_bert_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg
                        const float* sumsq, float max_norm, float lr, const float* lr_dev, float b1, float b2, float eps,
                        float weight_decay, float grad_scale, int zero_grad, void* stream);
 
+/* ------------------------------------------------------------------ Conv3d visual front-end (tcgen05 implicit GEMM)
+ * Replaces VisualFeatEncoder.conv and the token assembly after it (lxrt/modeling_capsbert.py:989-996, 1037-1073):
+ *   nn.Sequential(ZeroPad2d(1), Conv3d(2048, 768, (5,3,3)), GeLU(), ZeroPad2d(1), Conv3d(768, 768, (5,3,3)), GeLU())
+ *   x = cat(cls_token, img.permute(0,2,3,4,1).view(B, t*H*W, c)); x = position_encoding(x); dropout(x)
+ * and their backward.  Activations are channels-last bf16 [batch, t, 7, 7, c] (the spatial size is fixed at 7x7, the
+ * slow_r50 output); the weight is bf16 packed [c_out, 45, c_in] with tap = (dt*3 + dh)*3 + dw — i.e.
+ * weight.permute(0,2,3,4,1) of the reference's [c_out, c_in, 5, 3, 3].  No im2col buffer: 5-D TMA boxes with
+ * out-of-bounds zero fill are the padded, shifted operand tiles.  t_out = t_in - 4; t_in a multiple of 4, >= 8;
+ * c_in, c_out multiples of 256. */
+typedef struct {
+    const void* x;          /* bf16 [batch, t_in, 7, 7, c_in] */
+    const void* w;          /* bf16 packed [c_out, 45, c_in] */
+    const float* bias;      /* fp32 [c_out] or NULL */
+    void* y;                /* bf16: GELU(conv) for output position pos = (t*7 + h)*7 + w of clip b is written to row
+                               b*y_rows_per_clip + y_row_off + pos (ldy elements per row) — (393, 1) drops the second
+                               conv's output straight into the [B*393, 768] token matrix behind the cls row */
+    int64_t ldy;
+    int y_rows_per_clip;    /* 0 = t_out*49 */
+    int y_row_off;
+    void* preact;           /* bf16 [batch*t_out*49, c_out]: conv + bias before the GELU, saved for the backward; or NULL */
+    const float* pos_emb;   /* fp32 [>= y_row_off + t_out*49, c_out]: row (y_row_off + pos) is added after the GELU
+                               (LearnedPositionalEncoding, lxrt/modeling_capsbert.py:1066); or NULL */
+    int batch, t_in, c_in, c_out;
+    float dropout_p;        /* nn.Dropout on the token (:1068); mask = f(*dropout_seed, salt, out_row*c_out + channel) */
+    uint32_t dropout_salt;
+    const uint32_t* dropout_seed;
+} shg_conv3d_args;
+int shg_conv3d_fwd(const shg_conv3d_args* args, void* stream);
+/* dx [batch, t_in, 7, 7, c_in] bf16 = conv_transpose(dy [batch, t_in-4, 7, 7, c_out], w) (x gelu'(preact) when preact,
+ * bf16 [batch*t_in*49, c_in] = the saved pre-activation of the layer that produced x, is given). */
+int shg_conv3d_dgrad(const void* dy, const void* w, const void* preact, void* dx, int batch, int t_in, int c_in,
+                     int c_out, void* stream);
+/* dw fp32 packed [c_out, 45, c_in] += sum over positions of dy (x) shifted x. */
+int shg_conv3d_wgrad(const void* dy, const void* x, float* dw, int batch, int t_in, int c_in, int c_out, void* stream);
+/* fp32 [batch, channels, positions] (the backbone's NCDHW output, positions = T*H*W) -> bf16 channels-last
+ * [batch, positions, channels], and the way back for the gradient handed to the backbone. */
+int shg_ncdhw_to_ndhwc(const float* x, void* y, int batch, int channels, int positions, void* stream);
+int shg_ndhwc_to_ncdhw(const void* x, float* y, int batch, int channels, int positions, void* stream);
+/* tokens[b*rows_per_clip, :] = dropout(cls + pe[0]) (bf16, ld elements per row) — the cls row of every clip. */
+int shg_frontend_cls(const float* cls, const float* pe, void* tokens, int64_t ld, int batch, int rows_per_clip, int n,
+                     float drop_p, uint32_t drop_salt, const uint32_t* seed, void* stream);
+/* Backward of the token assembly.  d_tok bf16 [batch*rows_per_clip, n] (ld): g = d_tok * dropmask/(1-p);
+ * d_pe fp32 [rows_per_clip, n] += sum_b g; d_cls fp32 [n] += sum_b g[b, 0]; d_pre bf16 [batch*(rows_per_clip-1), n] =
+ * g[b, 1:] * gelu'(preact) — the gradient wrt the second conv's pre-activation. */
+int shg_frontend_bwd(const void* d_tok, int64_t ld, const void* preact, void* d_pre, float* d_pe, float* d_cls, int batch,
+                     int rows_per_clip, int n, float drop_p, uint32_t drop_salt, const uint32_t* seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,13 @@ class AttnBwdArgs(ctypes.Structure):
                 ("dropout_bits", c_vp)]
 
 
+class Conv3dArgs(ctypes.Structure):
+    _fields_ = [("x", c_vp), ("w", c_vp), ("bias", c_vp), ("y", c_vp), ("ldy", c_i64),
+                ("y_rows_per_clip", c_int), ("y_row_off", c_int), ("preact", c_vp), ("pos_emb", c_vp),
+                ("batch", c_int), ("t_in", c_int), ("c_in", c_int), ("c_out", c_int),
+                ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp)]
+
+
 # name -> argtypes (all return int).  Must list every symbol include/shgvqa.h declares.
 SIGNATURES = {
     "shg_version": [],
@@ -80,6 +87,14 @@ SIGNATURES = {
     "shg_bert_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_f32, c_f32, c_vp,
                            c_f32, c_f32, c_f32, c_f32, c_f32, c_int, c_vp],
     "shg_f32_to_bf16": [c_vp, c_vp, c_i64, c_vp],
+    "shg_conv3d_fwd": [ctypes.POINTER(Conv3dArgs), c_vp],
+    "shg_conv3d_dgrad": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "shg_conv3d_wgrad": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "shg_ncdhw_to_ndhwc": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
+    "shg_ndhwc_to_ncdhw": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
+    "shg_frontend_cls": [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, ctypes.c_uint32, c_vp, c_vp],
+    "shg_frontend_bwd": [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, ctypes.c_uint32, c_vp,
+                         c_vp],
 }
 
 _lib = None

@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr"
 mkdir -p _obj
 pids=()
-for f in core lsap gemm rowops attn optim; do
+for f in core lsap gemm rowops attn optim conv; do
   [ -f $f.cu ] || continue
   if [ ! -f _obj/$f.o ] || [ $f.cu -nt _obj/$f.o ] || [ shg_common.cuh -nt _obj/$f.o ] || [ ../../include/shgvqa.h -nt _obj/$f.o ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o _obj/$f.o &

@@ -30,13 +30,13 @@ int check_launch(const char* what) {
 }
 
 struct TmapKey {
-    uint64_t w[12];
+    uint64_t w[20];
     bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
 };
 struct TmapHash {
     size_t operator()(const TmapKey& k) const {
         uint64_t h = 1469598103934665603ull;
-        for (int i = 0; i < 12; ++i) {
+        for (int i = 0; i < 20; ++i) {
             h ^= k.w[i];
             h *= 1099511628211ull;
         }
@@ -62,14 +62,18 @@ const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims
     static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> cache;
     int dev = 0;
     cudaGetDevice(&dev);
+    if (rank < 1 || rank > 5) {
+        set_error("tensor map rank %d", rank);
+        return nullptr;
+    }
     TmapKey key;
     memset(&key, 0, sizeof(key));
     key.w[0] = reinterpret_cast<uint64_t>(ptr);
     key.w[1] = (uint64_t)rank | ((uint64_t)dev << 8);
     for (int i = 0; i < rank; ++i) {
         key.w[2 + i] = dims[i];
-        key.w[5 + i] = i ? strides_bytes[i - 1] : 0;
-        key.w[8 + i] = box[i];
+        key.w[7 + i] = i ? strides_bytes[i - 1] : 0;
+        key.w[12 + i] = box[i];
     }
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -89,10 +93,10 @@ const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims
             return nullptr;
         }
     CUtensorMap* m = new CUtensorMap;
-    cuuint64_t gdim[3] = {1, 1, 1};
-    cuuint64_t gstr[2] = {0, 0};
-    cuuint32_t bx[3] = {1, 1, 1};
-    cuuint32_t es[3] = {1, 1, 1};
+    cuuint64_t gdim[5] = {1, 1, 1, 1, 1};
+    cuuint64_t gstr[4] = {0, 0, 0, 0};
+    cuuint32_t bx[5] = {1, 1, 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bx[i] = box[i];

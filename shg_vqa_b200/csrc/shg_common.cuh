@@ -380,7 +380,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------- host: TMA descriptor cache
-// 2-D / 3-D bf16 tensor maps with 128-byte swizzle, cached by (ptr, dims, strides, box).
+// 2-D .. 5-D bf16 tensor maps with 128-byte swizzle (out-of-bounds elements read as zero), cached by (ptr, dims, strides, box).
 const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                                  const uint32_t* box);
 

@@ -6,7 +6,7 @@ returns torch tensors it allocated; none falls back to PyTorch math.
 import torch
 
 from . import _lib
-from ._lib import AttnArgs, AttnBwdArgs, GemmArgs, call, ptr, require_device, stream
+from ._lib import AttnArgs, AttnBwdArgs, Conv3dArgs, GemmArgs, call, ptr, require_device, stream
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "tanh": 3}
 MUL = {None: 0, "gelu_grad": 1, "relu_mask": 2}
@@ -202,6 +202,111 @@ def to_bf16(x, out=None):
         out = torch.empty(x.shape, device=x.device, dtype=BF16)
     call("shg_f32_to_bf16", ptr(x), ptr(out), x.numel(), stream(), work=("hbm", 6.0 * x.numel()))
     return out
+
+
+# ----------------------------------------------------------------------------- Conv3d visual front-end
+
+def pack_conv_weight(w):
+    """Reference layout [c_out, c_in, 5, 3, 3] -> packed [c_out, 45*c_in] (tap-major, channel-minor)."""
+    return w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def unpack_conv_weight(wp, c_in):
+    """Packed [c_out, 45*c_in] -> a VIEW with the reference's shape [c_out, c_in, 5, 3, 3]."""
+    return wp.view(wp.shape[0], 5, 3, 3, c_in).permute(0, 4, 1, 2, 3)
+
+
+def ncdhw_to_ndhwc(x, out=None):
+    """fp32 [B, C, T, 7, 7] (backbone output) -> bf16 channels-last [B, T, 7, 7, C]."""
+    require_device(x)
+    b, c, t, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and h == 7 and w == 7
+    if out is None:
+        out = torch.empty(b, t, h, w, c, device=x.device, dtype=BF16)
+    call("shg_ncdhw_to_ndhwc", ptr(x), ptr(out), b, c, t * h * w, stream(), work=("hbm", 6.0 * x.numel()))
+    return out
+
+
+def ndhwc_to_ncdhw(x, out=None):
+    """bf16 [B, T, 7, 7, C] -> fp32 [B, C, T, 7, 7] (gradient handed back to the backbone)."""
+    require_device(x)
+    b, t, h, w, c = x.shape
+    assert x.dtype == BF16 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(b, c, t, h, w, device=x.device, dtype=torch.float32)
+    call("shg_ndhwc_to_ncdhw", ptr(x), ptr(out), b, c, t * h * w, stream(), work=("hbm", 6.0 * x.numel()))
+    return out
+
+
+def conv3d_fwd(x, wp, bias, *, out=None, rows_per_clip=0, row_off=0, preact=None, pos_emb=None, drop=None):
+    """GELU(Conv3d(ZeroPad2d(1)(x))) with kernel (5,3,3).  x bf16 [B, T, 7, 7, c_in]; wp bf16 packed [c_out, 45*c_in].
+    out: bf16 2-D token matrix the result rows are scattered into (see include/shgvqa.h) or None for a fresh
+    [B*(T-4)*49, c_out]; preact: True to save the pre-activation (returned), or a tensor to fill."""
+    require_device(x)
+    b, t, h, w, c_in = x.shape
+    c_out = wp.shape[0]
+    assert x.dtype == BF16 and wp.dtype == BF16 and x.is_contiguous() and wp.is_contiguous()
+    assert wp.shape[1] == 45 * c_in and h == 7 and w == 7
+    t_out = t - 4
+    if out is None:
+        out = torch.empty(b * t_out * 49, c_out, device=x.device, dtype=BF16)
+    if preact is True:
+        preact = torch.empty(b * t_out * 49, c_out, device=x.device, dtype=BF16)
+    a = Conv3dArgs()
+    a.x, a.w, a.bias, a.y, a.ldy = ptr(x), ptr(wp), ptr(bias), ptr(out), _ld(out)
+    a.y_rows_per_clip, a.y_row_off = rows_per_clip, row_off
+    a.preact, a.pos_emb = ptr(preact), ptr(pos_emb)
+    a.batch, a.t_in, a.c_in, a.c_out = b, t, c_in, c_out
+    _set_drop(a, drop)
+    call("shg_conv3d_fwd", a, stream(),
+         work=("tensor", 2.0 * b * t_out * 49 * c_out * 45 * c_in, "conv fwd %d->%d T%d" % (c_in, c_out, t)))
+    return out, preact
+
+
+def conv3d_dgrad(dy, wp, c_in, preact=None, out=None):
+    """dy bf16 [B, T_out, 7, 7, c_out] -> dx bf16 [B, T_out+4, 7, 7, c_in] (x gelu'(preact) if given)."""
+    require_device(dy)
+    b, t_out, h, w, c_out = dy.shape
+    assert dy.dtype == BF16 and dy.is_contiguous() and wp.shape == (c_out, 45 * c_in)
+    t_in = t_out + 4
+    if out is None:
+        out = torch.empty(b, t_in, 7, 7, c_in, device=dy.device, dtype=BF16)
+    call("shg_conv3d_dgrad", ptr(dy), ptr(wp), ptr(preact), ptr(out), b, t_in, c_in, c_out, stream(),
+         work=("tensor", 2.0 * b * t_in * 49 * c_in * 45 * c_out, "conv dgrad %d->%d T%d" % (c_in, c_out, t_in)))
+    return out
+
+
+def conv3d_wgrad(dy, x, dw):
+    """dw (fp32 packed [c_out, 45*c_in]) += grad of the conv weight; dy bf16 [B, T-4, 7, 7, c_out], x bf16 [B, T, 7, 7, c_in]."""
+    require_device(dy)
+    b, t, h, w, c_in = x.shape
+    c_out = dy.shape[-1]
+    assert dy.dtype == BF16 and x.dtype == BF16 and dy.is_contiguous() and x.is_contiguous()
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == c_out * 45 * c_in
+    assert dy.shape[:4] == (b, t - 4, 7, 7)
+    call("shg_conv3d_wgrad", ptr(dy), ptr(x), ptr(dw), b, t, c_in, c_out, stream(),
+         work=("tensor", 2.0 * b * (t - 4) * 49 * c_out * 45 * c_in, "conv wgrad %d->%d T%d" % (c_in, c_out, t)))
+    return dw
+
+
+def frontend_cls(cls, pe, tokens, batch, rows_per_clip, drop=None):
+    require_device(tokens)
+    n = tokens.shape[1]
+    d = drop if (drop is not None and drop[0] > 0) else None
+    call("shg_frontend_cls", ptr(cls), ptr(pe), ptr(tokens), _ld(tokens), batch, rows_per_clip, n,
+         d[0] if d else 0.0, d[1] if d else 0, ptr(d[2]) if d else None, stream())
+
+
+def frontend_bwd(d_tok, preact, d_pe, d_cls, batch, rows_per_clip, drop=None):
+    """Returns d_pre bf16 [batch*(rows_per_clip-1), n]; accumulates into d_pe [rows_per_clip, n] and d_cls [n]."""
+    require_device(d_tok)
+    n = d_tok.shape[1]
+    d_pre = torch.empty(batch * (rows_per_clip - 1), n, device=d_tok.device, dtype=BF16)
+    d = drop if (drop is not None and drop[0] > 0) else None
+    call("shg_frontend_bwd", ptr(d_tok), _ld(d_tok), ptr(preact), ptr(d_pre), ptr(d_pe), ptr(d_cls), batch,
+         rows_per_clip, n, d[0] if d else 0.0, d[1] if d else 0, ptr(d[2]) if d else None, stream(),
+         work=("hbm", 2.0 * batch * rows_per_clip * n * 3))
+    return d_pre
 
 
 # ----------------------------------------------------------------------------- matching
