@@ -98,26 +98,10 @@ class AGQAHotPath(nn.Module):
         self.engine.refresh_derived()
         return r
 
-    def visual_front_end(self, feat):
-        """VisualFeatEncoder (lxrt/modeling_capsbert.py:989-996, 1037-1073) with stock PyTorch ops."""
-        p = "lxrt_encoder.model.bert.encoder.visn_fc"
-        st = self.store
-
-        def gelu(x):
-            return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
-        x = feat.float()
-        x = gelu(F.conv3d(F.pad(x, (1, 1, 1, 1)), st.p(p + ".conv.1.weight"), st.p(p + ".conv.1.bias")))
-        x = gelu(F.conv3d(F.pad(x, (1, 1, 1, 1)), st.p(p + ".conv.4.weight"), st.p(p + ".conv.4.bias")))
-        b, c = x.shape[:2]
-        tok = x.permute(0, 2, 3, 4, 1).reshape(b, -1, c)
-        tok = torch.cat([st.p(p + ".cls_token").expand(b, -1, -1), tok], dim=1)
-        tok = tok + st.p(p + ".position_encoding.pe.weight")[: tok.shape[1]].unsqueeze(0)
-        return tok.reshape(-1, c).to(torch.bfloat16)
-
     @torch.no_grad()
     def forward(self, feat, pos, input_ids, input_masks, segment_ids, rel_segment_ids=None, rel_tgt_mask=None,
                 act_segment_ids=None, act_tgt_mask=None, hg_mask=None, rel_tgt_ids=None, act_tgt_ids=None):
-        inp = dict(visn_tokens=self.visual_front_end(feat), input_ids=input_ids, input_mask=input_masks,
+        inp = dict(feat=feat.float().contiguous(), input_ids=input_ids, input_mask=input_masks,
                    segment_ids=segment_ids, rel_segment_ids=rel_segment_ids, act_segment_ids=act_segment_ids)
         out, _ = self.engine.forward(inp, train=False)
         b = input_ids.shape[0]

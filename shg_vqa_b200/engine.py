@@ -153,6 +153,17 @@ class Engine:
                         gword=st.g(e + ".embeddings.word_embeddings.weight") if g else None,
                         gpos=st.g(e + ".embeddings.position_embeddings.weight") if g else None,
                         gtype=st.g(e + ".embeddings.token_type_embeddings.weight") if g else None)
+        # Conv3d visual front-end: packed bf16 weights, fp32 biases / cls / learned positions
+        v = e + ".encoder.visn_fc"
+        self.fe = dict(w1=st.w(v + ".conv.1.weight"), b1=st.p(v + ".conv.1.bias"),
+                       w2=st.w(v + ".conv.4.weight"), b2=st.p(v + ".conv.4.bias"),
+                       cls=st.p(v + ".cls_token").view(-1), pe=st.p(v + ".position_encoding.pe.weight"),
+                       gw1=st.packed(st.grad, v + ".conv.1.weight") if g else None,
+                       gb1=st.g(v + ".conv.1.bias") if g else None,
+                       gw2=st.packed(st.grad, v + ".conv.4.weight") if g else None,
+                       gb2=st.g(v + ".conv.4.bias") if g else None,
+                       gcls=st.g(v + ".cls_token").view(-1) if g else None,
+                       gpe=st.g(v + ".position_encoding.pe.weight") if g else None)
         self.l_layers = [self._bert_layer("%s.encoder.layer.%d" % (e, i)) for i in range(self.nl)]
         self.r_layers = [self._bert_layer("%s.encoder.r_layers.%d" % (e, i)) for i in range(self.nr)]
         self.x_layer = self._cross_layer(e + ".encoder.cross_attn_layer.cross")
@@ -212,6 +223,49 @@ class Engine:
             return None
         self._salt += 1
         return (p, self._salt, self.drop_seed)
+
+    # ------------------------------------------------------------------ Conv3d visual front-end
+    def frontend_fwd(self, feat, save):
+        """VisualFeatEncoder (lxrt/modeling_capsbert.py:989-996, 1037-1073): feat fp32 [B,2048,T,7,7] as the backbone
+        emits it (or bf16 channels-last [B,T,7,7,2048]) -> visual tokens bf16 [B*(1+(T-8)*49), 768].  Two implicit-GEMM
+        launches; the second one's epilogue writes GELU + learned position + dropout straight into the token matrix
+        behind each clip's cls row."""
+        F = self.fe
+        x0 = ops.ncdhw_to_ndhwc(feat) if feat.dtype == torch.float32 else feat
+        B, T = x0.shape[0], x0.shape[1]
+        a1, pre1 = ops.conv3d_fwd(x0, F["w1"], F["b1"], preact=True if save else None)
+        a1 = a1.view(B, T - 4, 7, 7, H)
+        nv = 1 + (T - 8) * 49
+        assert nv <= F["pe"].shape[0], "clip too long for the learned position table"
+        tokens = torch.empty(B * nv, H, device=self.dev, dtype=BF16)
+        dv = self._drop(self.p_hidden)
+        _, pre2 = ops.conv3d_fwd(a1, F["w2"], F["b2"], out=tokens, rows_per_clip=nv, row_off=1,
+                                 preact=True if save else None, pos_emb=F["pe"], drop=dv)
+        ops.frontend_cls(F["cls"], F["pe"], tokens, B, nv, drop=dv)
+        return tokens, (x0, pre1, a1, pre2, dv, nv)
+
+    def frontend_bwd(self, saved, d_tok, need_dfeat=False):
+        """Backward of frontend_fwd: position/cls gradients, both weight gradients (packed layout, straight into the
+        flat gradient buffer), bias gradients, and on request the gradient wrt the backbone features (fp32 NCDHW)."""
+        F = self.fe
+        x0, pre1, a1, pre2, dv, nv = saved
+        B, T = x0.shape[0], x0.shape[1]
+        d_pre2 = ops.frontend_bwd(d_tok, pre2, F["gpe"], F["gcls"], B, nv, drop=dv)
+        d_pre2v = d_pre2.view(B, T - 8, 7, 7, H)
+        self._conv_wgrad(d_pre2v, a1, F["gw2"], F["gb2"])
+        d_pre1 = ops.conv3d_dgrad(d_pre2v, F["w2"], H, preact=pre1)
+        self._conv_wgrad(d_pre1, x0, F["gw1"], F["gb1"])
+        if not need_dfeat:
+            return None
+        return ops.ndhwc_to_ncdhw(ops.conv3d_dgrad(d_pre1, F["w1"], x0.shape[-1]))
+
+    def _conv_wgrad(self, dy, x, gw, gb):
+        if self.use_streams:
+            self.sw.wait_event(torch.cuda.current_stream().record_event())
+            self._keep.append((dy, x))
+        with self._on(self.sw):
+            ops.conv3d_wgrad(dy, x, gw)
+            ops.colsum_accum(dy.view(-1, dy.shape[-1]), gb)
 
     # ------------------------------------------------------------------ primitive fwd/bwd helpers
     def _wgrad(self, lin, dy, x, bias=True):
@@ -475,7 +529,8 @@ class Engine:
 
     # ------------------------------------------------------------------ whole path
     def forward(self, inp, train=False):
-        """inp (device tensors): visn_tokens bf16 [B*393,768] (output of the stock Conv3d front-end + cls + pos),
+        """inp (device tensors): either visn_tokens bf16 [B*393,768] (output of a stock Conv3d front-end + cls + pos)
+        or feat (backbone features, fp32 [B,2048,16,7,7] / bf16 channels-last) for the built-in front-end;
         input_ids/input_mask/segment_ids int64 [B,40], rel_segment_ids [B,128], act_segment_ids [B,48]."""
         save = train
         B = inp["input_ids"].shape[0]
@@ -505,7 +560,10 @@ class Engine:
                 lang, s = self._bert_fwd(L, lang, B, nl, kmask, save)
                 ctx["L"].append(s)
         lang_l = lang
-        visn = inp["visn_tokens"]
+        if "visn_tokens" in inp:
+            visn = inp["visn_tokens"]
+        else:
+            visn, ctx["frontend"] = self.frontend_fwd(inp["feat"], save)
         nv = visn.shape[0] // B
         ctx["R"] = []
         for L in self.r_layers:
@@ -645,7 +703,9 @@ class Engine:
         d_visn = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True)
         for i in reversed(range(self.nr)):
             d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None,
-                                    need_dx=(i > 0 or need_dvisn))
+                                    need_dx=(i > 0 or need_dvisn or "frontend" in ctx))
+        if "frontend" in ctx:
+            ctx["d_feat"] = self.frontend_bwd(ctx["frontend"], d_visn, need_dfeat=need_dvisn)
         self._join(self.s1, self.sw)
         self._keep.clear()
         return d_visn

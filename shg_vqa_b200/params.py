@@ -150,8 +150,17 @@ def canonical_key(key):
     return key
 
 
+def _is_conv_weight(key, shape):
+    """Conv3d weights of the visual front-end: kept PACKED [c_out, 5, 3, 3, c_in] in the flat buffers (the layout
+    the implicit-GEMM kernels read, csrc/conv.cu); p()/g()/state_dict() expose the reference's
+    [c_out, c_in, 5, 3, 3] as a permuted view of that storage."""
+    return len(shape) == 5 and ".visn_fc.conv." in key
+
+
 def _is_matrix(key, shape):
     """Tensors that get a bf16 shadow (tensor-core operands)."""
+    if _is_conv_weight(key, shape):
+        return True
     return len(shape) == 2 and shape[1] >= 64 and "embeddings" not in key and "pe.weight" not in key \
         and "box_fc" not in key
 
@@ -220,7 +229,15 @@ class ParamStore:
     # ------------------------------------------------------------------ views
     def _view(self, buf, key):
         off, n, shape = self.offsets[canonical_key(key)]
+        if _is_conv_weight(key, shape):
+            return buf[off:off + n].view(shape[0], shape[2], shape[3], shape[4], shape[1]).permute(0, 4, 1, 2, 3)
         return buf[off:off + n].view(shape)
+
+    def packed(self, buf, key):
+        """Conv3d weight (or its gradient / shadow) as the packed matrix [c_out, 45 * c_in] it is stored as."""
+        off, n, shape = self.offsets[canonical_key(key)]
+        assert _is_conv_weight(key, shape), key
+        return buf[off:off + n].view(shape[0], n // shape[0])
 
     def p(self, key):
         return self._view(self.master, key)
@@ -232,6 +249,8 @@ class ParamStore:
         """bf16 shadow of a matrix."""
         off, n, shape = self.offsets[canonical_key(key)]
         assert off + n <= self.n_matrix, key + " has no bf16 shadow"
+        if _is_conv_weight(key, shape):
+            return self.packed(self.shadow, key)
         return self.shadow[off:off + n].view(shape)
 
     def fused(self, buf, first_key, rows, cols=None):

@@ -34,6 +34,16 @@ def live_in_hgqa_training(key):
     return True
 
 
+def live_with_frontend(key):
+    """live_in_hgqa_training plus the Conv3d front-end's own parameters (conv weights/biases, cls token, learned
+    positions — live in the reference; box_fc / pos_layer_norm never receive a gradient), for runs that start from
+    backbone features (`feat`) instead of precomputed visual tokens."""
+    k = canonical_key(key)
+    if ".visn_fc." in k:
+        return ".visn_fc.conv." in k or k.endswith((".visn_fc.cls_token", ".visn_fc.position_encoding.pe.weight"))
+    return live_in_hgqa_training(key)
+
+
 def warmup_linear(x, warmup=0.002):
     """lxrt/optimization.py:38-43."""
     if x < warmup:
@@ -78,8 +88,14 @@ def shard_seed(base_seed, rank):
 class HotPathTrainer:
     def __init__(self, device, task="hgqa", n_answers=171, n_rel_cls=457, n_act_cls=158, lr=1e-5, t_total=-1,
                  warmup=0.1, weight_decay=0.01, max_grad_norm=5.0, eos_coef=0.1, world_size=1, process_group=None,
-                 live=live_in_hgqa_training, dropout=False, dropout_seed=0, rank=0):
+                 live=None, dropout=False, dropout_seed=0, rank=0, frontend=False,
+                 backbone_grad=False):
         self.device = torch.device(device)
+        # frontend: the step starts from backbone features (inp['feat']) and trains the Conv3d front-end too;
+        # backbone_grad: also return the gradient wrt those features (ctx['d_feat']) for a trainable backbone
+        self.frontend, self.backbone_grad = bool(frontend), bool(backbone_grad)
+        if live is None:
+            live = live_with_frontend if frontend else live_in_hgqa_training
         self.key_shapes = build_key_shapes(task, n_answers, n_rel_cls, n_act_cls)
         self.store = ParamStore(self.key_shapes, self.device, live=live)
         self.engine = Engine(self.store, task)
@@ -117,6 +133,12 @@ class HotPathTrainer:
             elif k.startswith(("relation_query_embed.", "action_query_embed.")) and k.endswith("embeddings.weight"):
                 v.normal_(0.0, 1.0, generator=g)
                 v[0].zero_()
+            elif ".visn_fc.conv." in k:
+                # nn.Conv3d keeps torch's default init (init_bert_weights only touches Linear/Embedding/LayerNorm):
+                # U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias, fan_in = c_in * 45
+                c_in = 2048 if ".conv.1." in k else 768
+                bound = 1.0 / math.sqrt(c_in * 45)
+                v.uniform_(-bound, bound, generator=g)
             elif len(shape) >= 2 and not k.endswith(("cls_token", "act_token", "rel_token")):
                 v.normal_(0.0, 0.02, generator=g)
         st.refresh_shadow()
@@ -211,7 +233,8 @@ class HotPathTrainer:
         self._advance_seed()
         out, ctx = self.engine.forward(inp, train=True)
         scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, batch)
-        self.engine.backward(ctx, d_hg, d_rel, d_act)
+        self.engine.backward(ctx, d_hg, d_rel, d_act, need_dvisn=self.backbone_grad)
+        self.d_feat = ctx.get("d_feat")      # gradient wrt the backbone features (backbone_grad runs)
         self.all_reduce_grads()
         self.optimizer_step(lr_on_device)
         return out, scal
@@ -254,7 +277,7 @@ class HotPathTrainer:
                 self.static_out, self.static_scal = out, scal
             self.graph_bwd2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_bwd2, pool=self.graph.pool()):
-                self.engine.backward_early_params(ctx)
+                self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad)
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
                 self.optimizer_step(lr_on_device=True)

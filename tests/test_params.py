@@ -59,3 +59,31 @@ def test_store_roundtrip_aliases_and_fused_views():
         assert False
     except RuntimeError:
         pass
+
+
+def test_conv_weights_are_stored_packed_and_exposed_in_reference_layout(key_shapes):
+    """The Conv3d weights of the visual front-end live packed [c_out, 5, 3, 3, c_in] in the flat buffers (what the
+    implicit-GEMM kernels read); state_dict()/load_state_dict() keep the reference's [c_out, c_in, 5, 3, 3]."""
+    import torch
+    from shg_vqa_b200.params import ParamStore, build_key_shapes
+    from shg_vqa_b200.trainer import live_with_frontend, live_in_hgqa_training
+    ks = build_key_shapes("hgqa")
+    st = ParamStore(ks, "cpu", live=live_with_frontend)
+    k = "lxrt_encoder.model.bert.encoder.visn_fc.conv.4.weight"
+    w = torch.randn(768, 768, 5, 3, 3)
+    st.p(k).copy_(w)
+    assert tuple(st.state_dict()[k].shape) == (768, 768, 5, 3, 3)
+    assert torch.equal(st.state_dict()[k], w)
+    packed = st.packed(st.master, k)
+    assert packed.shape == (768, 45 * 768) and packed.is_contiguous()
+    assert torch.equal(packed, w.permute(0, 2, 3, 4, 1).reshape(768, -1))
+    # live with the front-end, frozen without; either way inside the bf16-shadowed matrix region
+    off, n, _ = st.offsets[k]
+    assert st.live_begin <= off and off + n <= st.live_end and off + n <= st.n_matrix
+    st2 = ParamStore(ks, "cpu", live=live_in_hgqa_training)
+    off2, n2, _ = st2.offsets[k]
+    assert off2 + n2 <= st2.live_begin and off2 + n2 <= st2.n_matrix
+    for dead in ("box_fc.weight", "pos_layer_norm.weight"):
+        assert not live_with_frontend("lxrt_encoder.model.bert.encoder.visn_fc." + dead)
+    for live in ("conv.1.bias", "cls_token", "position_encoding.pe.weight"):
+        assert live_with_frontend("lxrt_encoder.model.bert.encoder.visn_fc." + live)
