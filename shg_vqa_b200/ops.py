@@ -272,7 +272,7 @@ def conv3d_dgrad(dy, wp, c_in, preact=None, out=None):
     if out is None:
         out = torch.empty(b, t_in, 7, 7, c_in, device=dy.device, dtype=BF16)
     call("shg_conv3d_dgrad", ptr(dy), ptr(wp), ptr(preact), ptr(out), b, t_in, c_in, c_out, stream(),
-         work=("tensor", 2.0 * b * t_in * 49 * c_in * 45 * c_out, "conv dgrad %d->%d T%d" % (c_in, c_out, t_in)))
+         work=("tensor", 2.0 * b * t_out * 49 * c_in * 45 * c_out, "conv dgrad %d->%d T%d" % (c_in, c_out, t_in)))
     return out
 
 

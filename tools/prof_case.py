@@ -36,5 +36,19 @@ elif what == "gemm":
     pre = torch.empty(m, n, device=dev, dtype=torch.bfloat16) if act == "gelu" else None     # FFN1 as the step runs it
     for _ in range(3):
         ops.gemm(a, w, bias=bias, act=act, preact=pre)
+elif what in ("conv_fwd", "conv_wgrad", "conv_dgrad"):
+    c_in, c_out, t_in = (2048, 768, 16) if len(sys.argv) < 3 or sys.argv[2] == "1" else (768, 768, 12)
+    x = torch.randn(B, t_in, 7, 7, c_in, device=dev).relu_().to(torch.bfloat16)
+    wp = (torch.randn(c_out, 45 * c_in, device=dev) * 0.01).to(torch.bfloat16)
+    bias = torch.randn(c_out, device=dev)
+    dy = torch.randn(B, t_in - 4, 7, 7, c_out, device=dev).to(torch.bfloat16)
+    dw = torch.zeros(c_out, 45 * c_in, device=dev)
+    for _ in range(3):
+        if what == "conv_fwd":
+            ops.conv3d_fwd(x, wp, bias, preact=True)
+        elif what == "conv_wgrad":
+            ops.conv3d_wgrad(dy, x, dw)
+        else:
+            ops.conv3d_dgrad(dy, wp, c_in)
 torch.cuda.synchronize()
 print("done")
