@@ -156,11 +156,16 @@ def run_ours(args):
     losses = tr.losses_from_scalars(scal)
 
     # ---------------------------------------------------------------- end to end from pinned host buffers (`e2e`)
+    for _ in range(2):                              # untimed: staging buffers, copy stream
+        tr.train_step_host(h_inp, h_batch, next_inp=h_inp, next_batch=h_batch)
     barrier()
     t0 = time.perf_counter()
     s.record()
     for _ in range(args.steps):
-        tr.train_step_host(h_inp, h_batch)          # H2D of the inputs + step + D2H of the loss sums, every step
+        # H2D of this step's inputs + step + D2H of the loss sums, every step; the H2D of the FOLLOWING step's inputs
+        # (the same pinned buffers here, a data loader's next batch in use) is started on a copy stream while this
+        # step computes, so each step's inputs still cross PCIe exactly once inside the timed region
+        tr.train_step_host(h_inp, h_batch, next_inp=h_inp, next_batch=h_batch)
     e.record()
     barrier()
     e2e_ms = max_over_ranks(max(s.elapsed_time(e), (time.perf_counter() - t0) * 1e3) / args.steps)

@@ -29,6 +29,10 @@ const char* shg_last_error(void);
 int shg_version(void);
 /* Refuses anything that is not compute capability 10.x (there is no fallback path). */
 int shg_device_check(int device);
+/* Programmatic dependent launch between the library's kernels (default off — measured 1 % slower on the captured
+ * step; SHG_PDL=1 in the environment also switches it on): the next kernel's prologue overlaps the tail of the
+ * previous one on the same stream. */
+int shg_set_pdl(int on);
 
 /* ------------------------------------------------------------------ Hungarian matching
  * Replaces the CPU loop `[linear_sum_assignment(c[i]) for i, c in enumerate(C.split(sizes, -1))]`

@@ -73,13 +73,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         tma_prefetch_desc(&tma_v);
     }
     if (warp == 0) tmem_alloc(tmem_slot, p.tmem_cols);
-    if (HAS_KMASK)
-        for (int k = tid; k < p.lk32; k += kAttnThreads)
-            s_kmask[k] = k < p.lk ? p.key_mask[(size_t)b * p.lk + k] * 1.4426950408889634f : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();     // after the TMEM allocation (see shg_common.cuh)
+    pdl_wait();                  // nothing above reads global memory
 
     if (tid == 0) {
         mbar_expect_tx(bar_qk, 16384 + p.n_kbox * 8192);
@@ -102,6 +101,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         tc_commit(bar_s);
     }
     __syncwarp();
+    if (HAS_KMASK) {
+        for (int k = tid; k < p.lk32; k += kAttnThreads)
+            s_kmask[k] = k < p.lk ? p.key_mask[(size_t)b * p.lk + k] * 1.4426950408889634f : 0.f;
+        __syncthreads();
+    }
 
     // ---------------------------------------------------------------- softmax in the log2 domain
     const int row = (warp & 3) * 32 + lane, quad = warp >> 2;   // warp w may touch TMEM lanes [32(w%4), +32)
@@ -437,6 +441,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 256;
     const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
     // keys of chunk j that exist, rounded up to the MMA granule: the products of the last chunk are only that wide
@@ -682,6 +688,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t t_s = tmem, t_dp = tmem + 128, t_dk = tmem + 256, t_dv = tmem + 320;
     const uint32_t idesc_acc = make_idesc_bf16(128, kHeadDim, 0, 1);
     auto chunk_n16 = [&](int i) { return (min(128, p.lq - i * 128) + 15) & ~15; };   // queries of chunk i, MMA granule
@@ -916,11 +924,11 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const bool drop = p.drop.p > 0.f;
     if (a->mask_mode == 1) {
-        if (drop) attn_fwd_kernel<true, true><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
-        else attn_fwd_kernel<true, false><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
+        if (drop) shg::launch(attn_fwd_kernel<true, true>, grid, kAttnThreads, smem, s, *tq, *tk, *tv, p);
+        else shg::launch(attn_fwd_kernel<true, false>, grid, kAttnThreads, smem, s, *tq, *tk, *tv, p);
     } else {
-        if (drop) attn_fwd_kernel<false, true><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
-        else attn_fwd_kernel<false, false><<<grid, kAttnThreads, smem, s>>>(*tq, *tk, *tv, p);
+        if (drop) shg::launch(attn_fwd_kernel<false, true>, grid, kAttnThreads, smem, s, *tq, *tk, *tv, p);
+        else shg::launch(attn_fwd_kernel<false, false>, grid, kAttnThreads, smem, s, *tq, *tk, *tv, p);
     }
     return check_launch("shg_attn_fwd");
 }
@@ -966,13 +974,13 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     }
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 gq((a->lq + 127) / 128, a->heads, a->batch), gk((a->lk + 127) / 128, a->heads, a->batch);
-    if (drop == 2) attn_bwd_dq_kernel<2><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
-    else if (drop == 1) attn_bwd_dq_kernel<1><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
-    else attn_bwd_dq_kernel<0><<<gq, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    if (drop == 2) shg::launch(attn_bwd_dq_kernel<2>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+    else if (drop == 1) shg::launch(attn_bwd_dq_kernel<1>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+    else shg::launch(attn_bwd_dq_kernel<0>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
     int rc = check_launch("shg_attn_bwd(dq)");
     if (rc) return rc;
-    if (drop == 2) attn_bwd_dkv_kernel<2><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
-    else if (drop == 1) attn_bwd_dkv_kernel<1><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
-    else attn_bwd_dkv_kernel<0><<<gk, kBwdThreads, smem, s>>>(*tq, *tdo, *tk, *tv, p);
+    if (drop == 2) shg::launch(attn_bwd_dkv_kernel<2>, gk, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+    else if (drop == 1) shg::launch(attn_bwd_dkv_kernel<1>, gk, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+    else shg::launch(attn_bwd_dkv_kernel<0>, gk, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
     return check_launch("shg_attn_bwd(dkv)");
 }

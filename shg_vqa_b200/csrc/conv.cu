@@ -106,6 +106,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
@@ -300,6 +302,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
@@ -413,6 +417,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 // fp32 [B, C, S] (NCDHW, S = T*49) -> bf16 [B, S, C] (channels-last), and back (bf16 -> fp32).  64-channel x 32-position
 // tiles through shared memory: reads are contiguous along S, writes along C.
 __global__ void ncs_to_nsc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int S) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[64][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 64, s0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
@@ -430,6 +436,8 @@ __global__ void ncs_to_nsc_kernel(const float* __restrict__ x, __nv_bfloat16* __
     }
 }
 __global__ void nsc_to_ncs_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int S) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][65];
     const int b = blockIdx.z, c0 = blockIdx.y * 64, s0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -450,6 +458,8 @@ __global__ void nsc_to_ncs_kernel(const __nv_bfloat16* __restrict__ x, float* __
 // tokens (lxrt/modeling_capsbert.py:1049-1069)
 __global__ void frontend_cls_kernel(const float* __restrict__ cls, const float* __restrict__ pe,
                                     __nv_bfloat16* __restrict__ tokens, int64_t ld, int rows_per_clip, int n, DropCfg drop) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     const uint32_t key = drop.p > 0.f ? drop_key(__ldg(drop.seed), drop.salt) : 0u;
     const uint32_t th = drop_thresh(drop.p);
@@ -468,6 +478,8 @@ __global__ void frontend_cls_kernel(const float* __restrict__ cls, const float* 
 __global__ void frontend_bwd_kernel(const __nv_bfloat16* __restrict__ d_tok, int64_t ld, const __nv_bfloat16* __restrict__ pre,
                                     __nv_bfloat16* __restrict__ d_pre, float* __restrict__ d_pe, float* __restrict__ d_cls,
                                     int batch, int rows_per_clip, int n, DropCfg drop) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int tok = blockIdx.x, c0 = threadIdx.x * 8;
     if (c0 >= n) return;
     const uint32_t key = drop.p > 0.f ? drop_key(__ldg(drop.seed), drop.salt) : 0u;
@@ -568,7 +580,7 @@ extern "C" int shg_conv3d_fwd(const shg_conv3d_args* a, void* stream) {
     static bool attr = false;
     set_smem_once(conv_gemm_kernel<0>, &attr);
     const int grid = 2 * (p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2);
-    conv_gemm_kernel<0><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(*ta, *tb, p);
+    shg::launch(conv_gemm_kernel<0>, grid, kConvThreads, smem, (cudaStream_t)stream, *ta, *tb, p);
     return check_launch("shg_conv3d_fwd");
 }
 
@@ -594,7 +606,7 @@ extern "C" int shg_conv3d_dgrad(const void* dy, const void* w, const void* preac
     static bool attr = false;
     set_smem_once(conv_gemm_kernel<1>, &attr);
     const int grid = 2 * (p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2);
-    conv_gemm_kernel<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(*ta, *tb, p);
+    shg::launch(conv_gemm_kernel<1>, grid, kConvThreads, smem, (cudaStream_t)stream, *ta, *tb, p);
     return check_launch("shg_conv3d_dgrad");
 }
 
@@ -618,7 +630,7 @@ extern "C" int shg_conv3d_wgrad(const void* dy, const void* x, float* dw, int ba
     static bool attr = false;
     set_smem_once(conv_wgrad_kernel, &attr);
     const int grid = 2 * (p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2);
-    conv_wgrad_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(*ta, *tb, p);
+    shg::launch(conv_wgrad_kernel, grid, kConvThreads, smem, (cudaStream_t)stream, *ta, *tb, p);
     return check_launch("shg_conv3d_wgrad");
 }
 
@@ -627,7 +639,7 @@ extern "C" int shg_ncdhw_to_ndhwc(const float* x, void* y, int batch, int channe
     SHG_REQUIRE(x && y && batch > 0 && channels > 0 && positions > 0 && channels % 2 == 0, SHG_EINVAL,
                 "shg_ncdhw_to_ndhwc: bad arguments");
     dim3 grid((positions + 31) / 32, (channels + 63) / 64, batch), block(32, 8);
-    ncs_to_nsc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, channels, positions);
+    shg::launch(ncs_to_nsc_kernel, grid, block, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, channels, positions);
     return check_launch("shg_ncdhw_to_ndhwc");
 }
 
@@ -636,7 +648,7 @@ extern "C" int shg_ndhwc_to_ncdhw(const void* x, float* y, int batch, int channe
     SHG_REQUIRE(x && y && batch > 0 && channels > 0 && positions > 0 && channels % 2 == 0, SHG_EINVAL,
                 "shg_ndhwc_to_ncdhw: bad arguments");
     dim3 grid((positions + 31) / 32, (channels + 63) / 64, batch), block(32, 8);
-    nsc_to_ncs_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, channels, positions);
+    shg::launch(nsc_to_ncs_kernel, grid, block, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, y, channels, positions);
     return check_launch("shg_ndhwc_to_ncdhw");
 }
 
@@ -646,7 +658,7 @@ extern "C" int shg_frontend_cls(const float* cls, const float* pe, void* tokens,
     SHG_REQUIRE(cls && pe && tokens && batch > 0, SHG_EINVAL, "shg_frontend_cls: bad arguments");
     DropCfg d;
     d.p = seed ? drop_p : 0.f, d.salt = drop_salt, d.seed = seed;
-    frontend_cls_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(cls, pe, (__nv_bfloat16*)tokens, ld, rows_per_clip, n, d);
+    shg::launch(frontend_cls_kernel, batch, 256, 0, (cudaStream_t)stream, cls, pe, (__nv_bfloat16*)tokens, ld, rows_per_clip, n, d);
     return check_launch("shg_frontend_cls");
 }
 
@@ -659,7 +671,7 @@ extern "C" int shg_frontend_bwd(const void* d_tok, int64_t ld, const void* preac
     DropCfg d;
     d.p = seed ? drop_p : 0.f, d.salt = drop_salt, d.seed = seed;
     const int threads = ((n / 8 + 31) / 32) * 32;
-    frontend_bwd_kernel<<<rows_per_clip, threads, 0, (cudaStream_t)stream>>>(
+    shg::launch(frontend_bwd_kernel, rows_per_clip, threads, 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)d_tok, ld, (const __nv_bfloat16*)preact, (__nv_bfloat16*)d_pre, d_pe, d_cls, batch, rows_per_clip,
         n, d);
     return check_launch("shg_frontend_bwd");

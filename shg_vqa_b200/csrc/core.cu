@@ -1,6 +1,7 @@
 // Error reporting, device check and the host-side TMA descriptor cache.
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -27,6 +28,15 @@ int check_launch(const char* what) {
         return SHG_ECUDA;
     }
     return SHG_OK;
+}
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("SHG_PDL");
+        g_pdl = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_pdl != 0;
 }
 
 struct TmapKey {
@@ -122,7 +132,12 @@ extern "C" {
 
 const char* shg_last_error(void) { return shg::g_err; }
 
-int shg_version(void) { return 100; }
+int shg_version(void) { return 101; }
+
+int shg_set_pdl(int on) {
+    shg::g_pdl = on ? 1 : 0;
+    return SHG_OK;
+}
 
 int shg_device_check(int device) {
     cudaDeviceProp p;

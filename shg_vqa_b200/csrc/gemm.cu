@@ -309,6 +309,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();     // after the TMEM allocation: a dependent grid parked on this SM cannot starve it
+    pdl_wait();                  // everything above overlapped the previous kernel's tail
 
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     if (threadIdx.x == 0) SHG_STAMP(1);
@@ -477,6 +479,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;     // m_tiles counts 256-row pair tiles here
@@ -745,7 +749,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm2_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set2 = true;                                                                                  \
         }                                                                                                      \
-        gemm2_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, *td, *tpre, p);                                  \
+        shg::launch(gemm2_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, p);                                  \
     } while (0)
     if (pair) {
         if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);
@@ -762,7 +766,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set = true;                                                                                  \
         }                                                                                                     \
-        gemm_kernel<AM, BMJ><<<grid, kGemmThreads, smem, s>>>(*ta, *tb, *td, *tpre, p);                                  \
+        shg::launch(gemm_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, p);                                  \
     } while (0)
     if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM_LAUNCH(false, false);
     else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM_LAUNCH(false, true);

@@ -133,6 +133,8 @@ __device__ void emit_warp(int rc, bool transposed, int nr, int nc, int q_f, int 
 __global__ void __launch_bounds__(32) lsap_frames_kernel(const float* __restrict__ cost, int q_f, int ld,
                                                         const int32_t* __restrict__ col_off, int32_t* rows,
                                                         int32_t* cols, int32_t* n_match, int32_t* status) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sC[kMaxDim * kMaxDim];
     const int f = blockIdx.x, lane = threadIdx.x;
     const int c0 = col_off[f], n = col_off[f + 1] - c0;
@@ -172,6 +174,8 @@ __global__ void __launch_bounds__(256) match_from_logits_kernel(
     const T* __restrict__ logits, int q_f, int n_cls, int ld, const int32_t* __restrict__ labels,
     const int32_t* __restrict__ label_off, int32_t* rows, int32_t* cols, int32_t* n_match, int32_t* status,
     float* row_max, float* row_lse, int32_t* row_argmax, int32_t* target_classes) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sC[kMaxDim * kMaxDim];
     __shared__ int s_bad;
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -233,6 +237,8 @@ __global__ void __launch_bounds__(256) set_loss_fwd_kernel(const T* __restrict__
                                                           const float* __restrict__ row_lse,
                                                           const int32_t* __restrict__ row_argmax, float eos_coef,
                                                           float* out) {
+    pdl_launch_dependents();
+    pdl_wait();
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
         const int t = tgt[r];
@@ -262,6 +268,8 @@ __global__ void __launch_bounds__(256) set_loss_bwd_kernel(const T* __restrict__
                                                           const float* __restrict__ row_lse, float eos_coef,
                                                           const float* __restrict__ out, float grad_scale,
                                                           TO* __restrict__ dlogits, int ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
@@ -287,7 +295,7 @@ int shg_lsap_batched(const float* cost, int n_frames, int q_f, int ld, const int
     SHG_REQUIRE(q_f >= 1 && q_f <= shg::kMaxDim, SHG_ESHAPE, "shg_lsap_batched: q_f=%d outside [1,32]", q_f);
     SHG_REQUIRE(n_frames >= 0 && ld >= 0, SHG_EINVAL, "shg_lsap_batched: negative size");
     if (n_frames == 0) return SHG_OK;
-    shg::lsap_frames_kernel<<<n_frames, 32, 0, (cudaStream_t)stream>>>(cost, q_f, ld, col_off, rows, cols, n_match,
+    shg::launch(shg::lsap_frames_kernel, n_frames, 32, 0, (cudaStream_t)stream, cost, q_f, ld, col_off, rows, cols, n_match,
                                                                       status);
     return shg::check_launch("shg_lsap_batched");
 }
@@ -301,11 +309,11 @@ int shg_match_from_logits(const void* logits, int logits_bf16, int n_frames, int
     if (n_frames == 0) return SHG_OK;
     const int threads = 32 * (q_f < 8 ? q_f : 8);
     if (logits_bf16)
-        shg::match_from_logits_kernel<__nv_bfloat16><<<n_frames, threads, 0, (cudaStream_t)stream>>>(
+        shg::launch(shg::match_from_logits_kernel<__nv_bfloat16>, n_frames, threads, 0, (cudaStream_t)stream, 
             (const __nv_bfloat16*)logits, q_f, n_cls, ld_logits, labels, label_off, rows, cols, n_match, status,
             row_max, row_lse, row_argmax, target_classes);
     else
-        shg::match_from_logits_kernel<float><<<n_frames, threads, 0, (cudaStream_t)stream>>>(
+        shg::launch(shg::match_from_logits_kernel<float>, n_frames, threads, 0, (cudaStream_t)stream, 
             (const float*)logits, q_f, n_cls, ld_logits, labels, label_off, rows, cols, n_match, status, row_max,
             row_lse, row_argmax, target_classes);
     return shg::check_launch("shg_match_from_logits");
@@ -318,10 +326,10 @@ int shg_set_loss_fwd(const void* logits, int logits_bf16, int n_rows, int n_cls,
     if (n_rows == 0) return SHG_OK;
     const int blocks = (n_rows + 255) / 256 < 148 ? (n_rows + 255) / 256 : 148;
     if (logits_bf16)
-        shg::set_loss_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        shg::launch(shg::set_loss_fwd_kernel<__nv_bfloat16>, blocks, 256, 0, (cudaStream_t)stream, 
             (const __nv_bfloat16*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out);
     else
-        shg::set_loss_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        shg::launch(shg::set_loss_fwd_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, 
             (const float*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out);
     return shg::check_launch("shg_set_loss_fwd");
 }
@@ -333,7 +341,7 @@ int shg_set_loss_bwd(const void* logits, int logits_bf16, int n_rows, int n_cls,
     const int blocks = (n_rows + 7) / 8;
     cudaStream_t s = (cudaStream_t)stream;
 #define SHG_LAUNCH(T, TO)                                                                                          \
-    shg::set_loss_bwd_kernel<T, TO><<<blocks, 256, 0, s>>>((const T*)logits, n_rows, n_cls, ld_logits,             \
+    shg::launch(shg::set_loss_bwd_kernel<T, TO>, blocks, 256, 0, s, (const T*)logits, n_rows, n_cls, ld_logits,             \
                                                            target_classes, row_lse, eos_coef, out, grad_scale,     \
                                                            (TO*)dlogits, ld_dlogits)
     if (logits_bf16 && dlogits_bf16) SHG_LAUNCH(__nv_bfloat16, __nv_bfloat16);

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
                                                         const int64_t* __restrict__ seg_start,
                                                         const int64_t* __restrict__ seg_prefix, int n_seg,
                                                         int64_t total4, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     float acc = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = i * 4;
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(256) bert_adam_kernel(float* __restrict__ p, f
                                                        float max_norm, float lr, const float* __restrict__ lr_dev,
                                                        float b1, float b2, float eps, float wd, float grad_scale,
                                                        int zero_grad) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (lr_dev) lr = lr_dev[0];     // device-resident learning rate: the launch stays valid inside a CUDA graph
     float clip = 1.0f;
     if (max_norm > 0.f) {
@@ -100,7 +104,7 @@ int shg_grad_sumsq(const float* grad, const int64_t* seg_start, const int64_t* s
                 (long long)total);
     int64_t blocks = (total / 4 + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-    grad_sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(grad, seg_start, seg_prefix, n_seg, total / 4,
+    shg::launch(grad_sumsq_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, grad, seg_start, seg_prefix, n_seg, total / 4,
                                                                      out);
     return check_launch("shg_grad_sumsq");
 }
@@ -115,7 +119,7 @@ int shg_bert_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg
     SHG_REQUIRE(max_norm <= 0.f || sumsq, SHG_EINVAL, "shg_bert_adam_step: clipping needs the sum of squares");
     int64_t blocks = (total / 4 + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-    bert_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+    shg::launch(bert_adam_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, 
         param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow, shadow ? n_shadow : 0, seg_start, seg_prefix, n_seg,
         total / 4, sumsq, max_norm, lr, lr_dev, b1, b2, eps, weight_decay, grad_scale, zero_grad);
     return check_launch("shg_bert_adam_step");

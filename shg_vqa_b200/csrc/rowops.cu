@@ -69,6 +69,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
                      const __nv_bfloat16* __restrict__ addend, int addend_rows, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -118,6 +120,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dxsum, int rows,
                      __nv_bfloat16* __restrict__ dx_drop, DropCfg out_drop, DropCfg in_drop) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int N = 256 * CH;
     __shared__ float red[kRowWarps][256 + 8];
     uint32_t okey = 0, oth = 0, ikey = 0, ith = 0;
@@ -206,6 +210,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 // out[c] += sum_rows x[row, c]  (bias gradients).  Block = 256 threads over 8-column groups x row slices.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, int n,
                                                     float* __restrict__ out, int rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     // thread t owns column group (blockIdx.x*32 + t%32) of 8 columns, row phase t/32
     const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
     const int c = cg * 8;
@@ -245,6 +251,8 @@ embed_ln_fwd_kernel(const float* __restrict__ word, const int64_t* __restrict__ 
                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
                     __nv_bfloat16* __restrict__ pre_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                     int rows, int seq_len, DropCfg drop) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -304,6 +312,8 @@ embed_scatter_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int64_t* __
                          const int64_t* __restrict__ type_ids, float* __restrict__ dword, int word_pad,
                          float* __restrict__ dpos, int pos_pad, float* __restrict__ dtype, int type_pad, int rows,
                          int seq_len) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -329,6 +339,8 @@ embed_scatter_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int64_t* __
 __global__ void __launch_bounds__(256) add_rows_kernel(const __nv_bfloat16* __restrict__ x,
                                                       const __nv_bfloat16* __restrict__ add, int add_rows,
                                                       __nv_bfloat16* __restrict__ y, int64_t total8, int n8) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n8;
         const int c8 = (int)(i - r * n8);
@@ -348,6 +360,8 @@ __global__ void __launch_bounds__(256) copy3d_kernel(const __nv_bfloat16* __rest
                                                     __nv_bfloat16* __restrict__ dst,
                                                     const __nv_bfloat16* __restrict__ add, int n0, int n1, int chunk8,
                                                     int64_t s0, int64_t s1, int64_t d0, int64_t d1, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t total = (int64_t)n0 * n1 * chunk8;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int e8 = (int)(i % chunk8);
@@ -377,6 +391,8 @@ __global__ void __launch_bounds__(256) copy3d_kernel(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                      const __nv_bfloat16* __restrict__ aux,
                                                      __nv_bfloat16* __restrict__ dx, int64_t n8, int mode) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         float g[8], a[8];
         load8(dy + i * 8, g);
@@ -397,6 +413,8 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
                                                         const float* __restrict__ t, int rows, int cols,
                                                         float grad_scale, float* __restrict__ out,
                                                         __nv_bfloat16* __restrict__ dx, int64_t lddx) {
+    pdl_launch_dependents();
+    pdl_wait();
     float acc = 0.f;
     const int64_t total = (int64_t)rows * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -418,6 +436,8 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          int64_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t n8 = n / 8;
@@ -445,11 +465,11 @@ int shg_layernorm_fwd(const void* x, const void* residual, const float* gamma, c
     const int blocks = (rows + kRowWarps - 1) / kRowWarps;
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 768)
-        layernorm_fwd_kernel<3><<<blocks, kRowThreads, 0, s>>>(
+        shg::launch(layernorm_fwd_kernel<3>, blocks, kRowThreads, 0, s, 
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, eps, (__nv_bfloat16*)y,
             (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows);
     else
-        layernorm_fwd_kernel<6><<<blocks, kRowThreads, 0, s>>>(
+        shg::launch(layernorm_fwd_kernel<6>, blocks, kRowThreads, 0, s, 
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, eps, (__nv_bfloat16*)y,
             (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows);
     return check_launch("shg_layernorm_fwd");
@@ -467,12 +487,12 @@ int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void
     if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 768)
-        layernorm_bwd_kernel<3><<<blocks, kRowThreads, 0, s>>>(
+        shg::launch(layernorm_bwd_kernel<3>, blocks, kRowThreads, 0, s, 
             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
             (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
             (__nv_bfloat16*)dx_drop, od, id);
     else
-        layernorm_bwd_kernel<6><<<blocks, kRowThreads, 0, s>>>(
+        shg::launch(layernorm_bwd_kernel<6>, blocks, kRowThreads, 0, s, 
             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
             (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
             (__nv_bfloat16*)dx_drop, od, id);
@@ -489,7 +509,7 @@ int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, voi
     int rpb = (rows + row_blocks - 1) / row_blocks;
     if (rpb < 64) rpb = 64;
     row_blocks = (rows + rpb - 1) / rpb;
-    colsum_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, rows,
+    shg::launch(colsum_kernel, dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, rows,
                                                                                   n, out, rpb);
     return check_launch("shg_colsum_accum");
 }
@@ -503,7 +523,7 @@ int shg_embed_ln_fwd(const float* word, const int64_t* word_ids, const float* po
     SHG_REQUIRE((mean == nullptr) == (rstd == nullptr), SHG_EINVAL, "shg_embed_ln_fwd: mean and rstd go together");
     if (rows <= 0) return SHG_OK;
     const int blocks = (rows + kRowWarps - 1) / kRowWarps;
-    embed_ln_fwd_kernel<3><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
+    shg::launch(embed_ln_fwd_kernel<3>, blocks, kRowThreads, 0, (cudaStream_t)stream, 
         word, word_ids, pos, type, type_ids, gamma, beta, eps, (__nv_bfloat16*)y, (__nv_bfloat16*)pre, mean, rstd,
         rows, seq_len, DropCfg{seed ? drop_p : 0.f, drop_salt, seed});
     return check_launch("shg_embed_ln_fwd");
@@ -516,7 +536,7 @@ int shg_embed_scatter_bwd(const void* de, const int64_t* word_ids, const int64_t
     SHG_REQUIRE(n == 768, SHG_ESHAPE, "shg_embed_scatter_bwd: width %d (768 supported)", n);
     if (rows <= 0) return SHG_OK;
     const int blocks = (rows + kRowWarps - 1) / kRowWarps;
-    embed_scatter_bwd_kernel<3><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
+    shg::launch(embed_scatter_bwd_kernel<3>, blocks, kRowThreads, 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)de, word_ids, type_ids, dword, word_pad, dpos, pos_pad, dtype, type_pad, rows, seq_len);
     return check_launch("shg_embed_scatter_bwd");
 }
@@ -528,7 +548,7 @@ int shg_add_rows(const void* x, const void* add, int add_rows, void* y, int rows
     const int64_t total8 = (int64_t)rows * (n / 8);
     int blocks = (int)((total8 + 255) / 256);
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-    add_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add,
+    shg::launch(add_rows_kernel, blocks, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)add,
                                                               add_rows, (__nv_bfloat16*)y, total8, n / 8);
     return check_launch("shg_add_rows");
 }
@@ -542,7 +562,7 @@ int shg_copy3d(const void* src, void* dst, const void* add, int n0, int n1, int 
     const int64_t total = (int64_t)n0 * n1 * (chunk / 8);
     int64_t blocks = (total + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-    copy3d_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst,
+    shg::launch(copy3d_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst,
                                                                  (const __nv_bfloat16*)add, n0, n1, chunk / 8, s0, s1,
                                                                  d0, d1, accumulate);
     return check_launch("shg_copy3d");
@@ -555,7 +575,7 @@ int shg_act_bwd(const void* dy, const void* aux, void* dx, int64_t n, int act, v
     if (n <= 0) return SHG_OK;
     int64_t blocks = (n / 8 + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-    act_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux,
+    shg::launch(act_bwd_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux,
                                                                   (__nv_bfloat16*)dx, n / 8, act);
     return check_launch("shg_act_bwd");
 }
@@ -566,7 +586,7 @@ int shg_bce_logits(const float* x, int64_t ldx, const float* target, int rows, i
     if (rows <= 0 || cols <= 0) return SHG_OK;
     int blocks = (int)(((int64_t)rows * cols + 255) / 256);
     if (blocks > kNumSMs) blocks = kNumSMs;
-    bce_logits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, target, rows, cols, grad_scale, out,
+    shg::launch(bce_logits_kernel, blocks, 256, 0, (cudaStream_t)stream, x, ldx, target, rows, cols, grad_scale, out,
                                                                 (__nv_bfloat16*)dx, lddx);
     return check_launch("shg_bce_logits");
 }
@@ -579,7 +599,7 @@ int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
     int64_t blocks = (n / 8 + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     if (blocks < 1) blocks = 1;
-    f32_to_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+    shg::launch(f32_to_bf16_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n);
     return check_launch("shg_f32_to_bf16");
 }
 }

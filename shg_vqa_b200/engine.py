@@ -61,6 +61,8 @@ class Engine:
         # Independent sub-graphs run on side streams so that the small-M launches (40-token language side,
         # 48-query action decoder) fill SMs the 148-CTA persistent kernels of the visual side leave idle.
         self.use_streams = self.dev.type == "cuda"
+        self.join_wgrads_after_late = True
+        # (stream priorities — chains high, weight gradients low — were measured: no effect on the replayed step)
         self.s1 = torch.cuda.Stream(self.dev) if self.use_streams else None
         self.s2 = torch.cuda.Stream(self.dev) if self.use_streams else None
         # weight/bias-gradient products are off the critical path (nothing reads them before the optimiser): they
@@ -682,7 +684,10 @@ class Engine:
         for i, D in enumerate(self._dec_layers()):
             c = i * 2 * H
             self._wgrad(D["ca_kv"], dkv_mem[:, c:c + 2 * H], mem)
-        self._join(self.sw)
+        # data-parallel runs all-reduce the late parameters right after this half, so their weight gradients must
+        # be final here; a single-GPU step lets them drain under the second half instead
+        if self.join_wgrads_after_late:
+            self._join(self.sw)
 
     def backward_early_params(self, ctx, need_dvisn=False):
         """Second half: the hoisted K/V dgrad, relation layers (main stream), language layers and embeddings

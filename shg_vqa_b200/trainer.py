@@ -99,6 +99,7 @@ class HotPathTrainer:
         self.key_shapes = build_key_shapes(task, n_answers, n_rel_cls, n_act_cls)
         self.store = ParamStore(self.key_shapes, self.device, live=live)
         self.engine = Engine(self.store, task)
+        self.engine.join_wgrads_after_late = world_size > 1
         self.lr, self.t_total, self.warmup = lr, t_total, warmup
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-6           # BertAdam defaults (lxrt/optimization.py:63-64)
         self.wd, self.max_norm, self.eos = weight_decay, max_grad_norm, eos_coef
@@ -110,6 +111,7 @@ class HotPathTrainer:
         self.lr_dev = torch.zeros(1, device=self.device, dtype=torch.float32)   # device-resident lr (graph-safe)
         self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else None
         self.graph = None
+        self.copy_stream, self._staged = None, False
         # training-mode dropout (the reference trains with model.train(): hidden/attention 0.1, decoders 0.15).
         # Masks are counter-based functions of (step seed, call site, element); the seed lives on the device and
         # is advanced at the start of every step (inside the captured graph too), and differs per rank.
@@ -306,11 +308,45 @@ class HotPathTrainer:
         self.step_count += 1
         return self.static_out, self.static_scal
 
-    def train_step_host(self, host_inp, host_batch):
+    def prefetch_host(self, host_inp, host_batch):
+        """Start the H2D copies of the NEXT step's inputs (pinned host tensors) on the copy stream into staging
+        buffers; they overlap whatever the compute streams are running.  The next train_step_host consumes them
+        with a device-to-device copy instead of waiting for PCIe."""
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(self.device)
+            self.stage_inp = {k: torch.empty_like(v) for k, v in self.static_inp.items()}
+            self.stage_batch = {k: torch.empty_like(v) for k, v in self.static_batch.items()}
+            self.stage_ready = torch.cuda.Event()
+            self.stage_free = torch.cuda.Event()
+            self.stage_free.record()
+        self.copy_stream.wait_event(self.stage_free)          # the previous consumer has read the staging buffers
+        with torch.cuda.stream(self.copy_stream):
+            for k, v in host_inp.items():
+                self.stage_inp[k].copy_(v, non_blocking=True)
+            for k, v in host_batch.items():
+                self.stage_batch[k].copy_(v, non_blocking=True)
+            self.stage_ready.record()
+        self._staged = True
+
+    def train_step_host(self, host_inp, host_batch, next_inp=None, next_batch=None):
         """The call a user of the path makes with HOST (pinned) buffers: H2D copies of the step's inputs, the
-        step, and a D2H read of the loss sums.  Returns the loss dict."""
+        step, and a D2H read of the loss sums.  Returns the loss dict.  next_inp / next_batch (the following
+        step's host buffers, as a data loader has them) are prefetched to the device while this step computes."""
         if self.graph is not None:
-            _, scal = self.train_step_graph(host_inp, host_batch)
+            if self._staged:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(self.stage_ready)
+                for k in host_inp:
+                    self.static_inp[k].copy_(self.stage_inp[k], non_blocking=True)
+                for k in host_batch:
+                    self.static_batch[k].copy_(self.stage_batch[k], non_blocking=True)
+                self.stage_free.record()
+                self._staged = False
+                _, scal = self.train_step_graph()
+            else:
+                _, scal = self.train_step_graph(host_inp, host_batch)
+            if next_inp is not None:
+                self.prefetch_host(next_inp, next_batch)
             return self.losses_from_scalars(scal)
         inp = {k: v.to(self.device, non_blocking=True) for k, v in host_inp.items()}
         batch = {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
