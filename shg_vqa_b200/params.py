@@ -220,11 +220,38 @@ class ParamStore:
         self.bucket_late = slice(self.offsets[late_mats[0]][0], self.n_matrix) if late_mats else slice(0, 0)
         self.bucket_early_a = slice(self.live_begin, self.bucket_late.start if late_mats else self.live_begin)
         self.bucket_early_b = slice(self.n_matrix if late_mats else self.live_begin, self.live_end)
+        # finer split of the early parameters for the data-parallel schedule: the matrices of the UPPER language /
+        # relation layers (index >= split) are final after the first part of the second backward half and are
+        # reduced under the rest of it
+        self.bucket_early_upper, self.bucket_early_rest = self._split_early(mats, is_live, upper_from=2)
         # optimiser segment table (one contiguous live span)
         self.n_seg = 1
         self.seg_start = torch.tensor([self.live_begin], dtype=torch.int64, device=self.device)
         self.seg_prefix = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._shadow_fresh = False
+
+    def _split_early(self, mats, is_live, upper_from):
+        import re
+        pat = re.compile(r"\.encoder\.(?:layer|r_layers)\.(\d+)\.")
+        upper, rest = [], []
+        lo, hi = self.bucket_early_a.start, self.bucket_early_a.stop
+
+        def push(lst, a, b):
+            if b > a:
+                if lst and lst[-1].stop == a:
+                    lst[-1] = slice(lst[-1].start, b)
+                else:
+                    lst.append(slice(a, b))
+        keys = [k for k in mats if is_live(k) and lo <= self.offsets[k][0] < hi]
+        for i, k in enumerate(keys):
+            a = self.offsets[k][0]
+            b = self.offsets[keys[i + 1]][0] if i + 1 < len(keys) else hi
+            m = pat.search(k)
+            push(upper if (m and int(m.group(1)) >= upper_from) else rest, a, b)
+        if keys:
+            push(rest, lo, self.offsets[keys[0]][0])
+        push(rest, self.bucket_early_b.start, self.bucket_early_b.stop)
+        return upper, rest
 
     # ------------------------------------------------------------------ views
     def _view(self, buf, key):

@@ -279,7 +279,10 @@ class HotPathTrainer:
                 self.static_out, self.static_scal = out, scal
             self.graph_bwd2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_bwd2, pool=self.graph.pool()):
-                self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad)
+                self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=0)
+            self.graph_bwd3 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_bwd3, pool=self.graph.pool()):
+                self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=1)
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
                 self.optimizer_step(lr_on_device=True)
@@ -299,11 +302,13 @@ class HotPathTrainer:
         if self.graph_opt is not None:
             import torch.distributed as dist
             st = self.store
-            w1 = dist.all_reduce(st.grad[st.bucket_late], group=self.pg, async_op=True)   # overlaps graph_bwd2
-            self.graph_bwd2.replay()
-            w2 = dist.all_reduce(st.grad[st.bucket_early_a], group=self.pg, async_op=True)
-            w3 = dist.all_reduce(st.grad[st.bucket_early_b], group=self.pg, async_op=True)
-            w1.wait(), w2.wait(), w3.wait()
+            works = [dist.all_reduce(st.grad[st.bucket_late], group=self.pg, async_op=True)]   # under graph_bwd2/3
+            self.graph_bwd2.replay()                       # upper language / relation layers
+            works += [dist.all_reduce(st.grad[sl], group=self.pg, async_op=True) for sl in st.bucket_early_upper]
+            self.graph_bwd3.replay()                       # lower layers, embeddings (, front-end)
+            works += [dist.all_reduce(st.grad[sl], group=self.pg, async_op=True) for sl in st.bucket_early_rest]
+            for w in works:
+                w.wait()
             self.graph_opt.replay()
         self.step_count += 1
         return self.static_out, self.static_scal

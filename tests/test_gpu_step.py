@@ -80,3 +80,32 @@ def test_graph_and_host_steps_match_eager():
         agree = float(((w1[live] - w_ref[live]).abs() <= 1e-6).float().mean())
         assert agree >= 0.999, (mode, agree)
         assert float((w1[live] - w_ref[live]).abs().max()) <= 2.1 * 3.17e-3, mode      # at worst a sign flip
+
+
+def test_split_second_backward_half_equals_unsplit():
+    """backward_early_params in two parts (the data-parallel schedule reduces the upper layers' gradients between
+    them) accumulates the same gradients as the single pass."""
+    dev = torch.device("cuda:0")
+    h_inp, h_batch = _make(dev, 3)
+    inp = {k: v.to(dev) for k, v in h_inp.items()}
+    batch = {k: v.to(dev) for k, v in h_batch.items()}
+    grads = []
+    for split_run in (False, True):
+        tr = _trainer(dev)
+        out, ctx = tr.engine.forward(inp, train=True)
+        scal, d_hg, d_rel, d_act, _ = tr.loss_and_grads(out, batch)
+        tr.engine.backward_late_params(ctx, d_hg, d_rel, d_act)
+        if split_run:
+            tr.engine.backward_early_params(ctx, part=0)
+            tr.engine.backward_early_params(ctx, part=1)
+        else:
+            tr.engine.backward_early_params(ctx)
+        torch.cuda.synchronize()
+        grads.append(tr.store.grad[tr.store.live_extent].clone())
+    a, b = grads
+    assert float((a - b).norm() / a.norm()) <= 1e-5
+    for sl in tr.store.bucket_early_upper + tr.store.bucket_early_rest:
+        ga, gb = tr.store.grad.new_zeros(0), None
+        lo, hi = sl.start - tr.store.live_begin, sl.stop - tr.store.live_begin
+        assert float(a[lo:hi].abs().max()) > 0                      # every bucket actually receives gradients
+        assert float((a[lo:hi] - b[lo:hi]).norm() / a[lo:hi].norm()) <= 1e-4

@@ -87,3 +87,26 @@ def test_conv_weights_are_stored_packed_and_exposed_in_reference_layout(key_shap
         assert not live_with_frontend("lxrt_encoder.model.bert.encoder.visn_fc." + dead)
     for live in ("conv.1.bias", "cls_token", "position_encoding.pe.weight"):
         assert live_with_frontend("lxrt_encoder.model.bert.encoder.visn_fc." + live)
+
+
+def test_data_parallel_buckets_tile_the_live_span():
+    """late | early-upper | early-rest (the three all-reduce phases of the captured data-parallel step) cover the
+    live gradient span exactly once, with and without the front-end's parameters."""
+    from shg_vqa_b200.params import ParamStore, build_key_shapes
+    from shg_vqa_b200.trainer import live_in_hgqa_training, live_with_frontend
+    for live in (live_in_hgqa_training, live_with_frontend):
+        st = ParamStore(build_key_shapes("hgqa"), "cpu", live=live)
+        spans = sorted((s.start, s.stop) for s in st.bucket_early_upper + st.bucket_early_rest + [st.bucket_late])
+        pos = st.live_begin
+        for a, b in spans:
+            assert a == pos and b > a and a % 8 == 0
+            pos = b
+        assert pos == st.live_end
+        # the upper bucket holds exactly the matrices of language / relation layers 2..4
+        n_upper = sum(s.stop - s.start for s in st.bucket_early_upper)
+        per_layer = 4 * 768 * 768 + 2 * 768 * 3072
+        assert n_upper == 2 * 3 * per_layer
+        off = st.offsets["lxrt_encoder.model.bert.encoder.r_layers.3.output.dense.weight"][0]
+        assert any(s.start <= off < s.stop for s in st.bucket_early_upper)
+        off = st.offsets["lxrt_encoder.model.bert.encoder.layer.1.output.dense.weight"][0]
+        assert any(s.start <= off < s.stop for s in st.bucket_early_rest)
