@@ -691,44 +691,39 @@ class Engine:
 
     def backward_early_params(self, ctx, need_dvisn=False, part=None, split=2):
         """Second half: the hoisted K/V dgrad, relation layers (main stream), language layers and embeddings
-        (side stream).  part=None runs all of it; part=0 stops after the layers with index >= split (their weight
-        gradients are then final — the data-parallel schedule reduces them under part=1, the remaining layers,
-        the embeddings and the Conv3d front-end)."""
+        (side stream).  part=None runs all of it; part=0 runs the whole language side (40 tokens per clip: it ends
+        long before the relation side) and the relation layers with index >= split — their gradients are then final
+        and the data-parallel schedule reduces them under part=1: the remaining relation layers and the Conv3d
+        front-end."""
         B = ctx["B"]
         nl, nv, ng, nq_r, nq_a = ctx["dims"]
         kmask = ctx["kmask"]
         first, second = part in (None, 0), part in (None, 1)
-        l_hi = range(self.nl - 1, split - 1, -1) if part is not None else range(self.nl - 1, -1, -1)
-        l_lo = range(min(split, self.nl) - 1, -1, -1) if part is not None else range(0)
-        r_hi = range(self.nr - 1, split - 1, -1) if part is not None else range(self.nr - 1, -1, -1)
-        r_lo = range(min(split, self.nr) - 1, -1, -1) if part is not None else range(0)
-        self._fork(self.s1)
-        with self._on(self.s1):
-            d_lang = ctx["d_lang_l"] if first else ctx["d_lang_mid"]
-            for i in (l_hi if first else ()):
-                d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
-            for i in (l_lo if part == 1 else ()):
-                d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
-            ctx["d_lang_mid"] = d_lang
-            if second:
+        need0 = need_dvisn or "frontend" in ctx
+        if first:
+            self._fork(self.s1)
+            with self._on(self.s1):
+                d_lang = ctx["d_lang_l"]
+                for i in reversed(range(self.nl)):
+                    d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
                 ids, seg, pre, mean, rstd, _, d_emb = ctx["emb"]
                 E = self.emb
                 de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb, in_drop=d_emb)
                 ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
                          ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
-        need0 = need_dvisn or "frontend" in ctx
-        if first:
             d_visn = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True)
-            for i in r_hi:
-                d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None, need_dx=(i > 0 or need0))
+            r_range = range(self.nr - 1, (split if part == 0 else 0) - 1, -1)
         else:
             d_visn = ctx["d_visn_mid"]
-        for i in (r_lo if part == 1 else ()):
+            r_range = range(min(split, self.nr) - 1, -1, -1)
+        for i in r_range:
             d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None, need_dx=(i > 0 or need0))
         ctx["d_visn_mid"] = d_visn
         if second and "frontend" in ctx:
             ctx["d_feat"] = self.frontend_bwd(ctx["frontend"], d_visn, need_dfeat=need_dvisn)
-        self._join(self.s1, self.sw)
+        if first:
+            self._join(self.s1)
+        self._join(self.sw)
         if second:
             self._keep.clear()
         return d_visn

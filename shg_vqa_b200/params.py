@@ -231,8 +231,12 @@ class ParamStore:
         self._shadow_fresh = False
 
     def _split_early(self, mats, is_live, upper_from):
+        """(upper, rest) slice lists over the early parameters.  upper = what is final after part 0 of the second
+        backward half (engine.backward_early_params): every language-layer matrix, the relation-layer matrices with
+        index >= upper_from, and the BertEmbeddings tables (the language side is 40 tokens per clip and finishes long
+        before the relation side); rest = the lower relation layers, the Conv3d front-end and the small vectors."""
         import re
-        pat = re.compile(r"\.encoder\.(?:layer|r_layers)\.(\d+)\.")
+        pat = re.compile(r"\.encoder\.(layer|r_layers)\.(\d+)\.")
         upper, rest = [], []
         lo, hi = self.bucket_early_a.start, self.bucket_early_a.stop
 
@@ -243,14 +247,22 @@ class ParamStore:
                 else:
                     lst.append(slice(a, b))
         keys = [k for k in mats if is_live(k) and lo <= self.offsets[k][0] < hi]
+        if keys:
+            push(rest, lo, self.offsets[keys[0]][0])
         for i, k in enumerate(keys):
             a = self.offsets[k][0]
             b = self.offsets[keys[i + 1]][0] if i + 1 < len(keys) else hi
             m = pat.search(k)
-            push(upper if (m and int(m.group(1)) >= upper_from) else rest, a, b)
-        if keys:
-            push(rest, lo, self.offsets[keys[0]][0])
-        push(rest, self.bucket_early_b.start, self.bucket_early_b.stop)
+            is_upper = bool(m) and (m.group(1) == "layer" or int(m.group(2)) >= upper_from)
+            push(upper if is_upper else rest, a, b)
+        # vectors / tables: the BertEmbeddings block is the leading run of the region (key order)
+        a = b = self.bucket_early_b.start
+        for k in self.live_keys:
+            off, n, _ = self.offsets[k]
+            if off == b and k.startswith("lxrt_encoder.model.bert.embeddings."):
+                b = off + (n + 7) // 8 * 8
+        push(upper, a, b)
+        push(rest, b, self.bucket_early_b.stop)
         return upper, rest
 
     # ------------------------------------------------------------------ views

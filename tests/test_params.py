@@ -102,11 +102,15 @@ def test_data_parallel_buckets_tile_the_live_span():
             assert a == pos and b > a and a % 8 == 0
             pos = b
         assert pos == st.live_end
-        # the upper bucket holds exactly the matrices of language / relation layers 2..4
+        # the upper bucket: every language-layer matrix, relation layers 2..4, the BertEmbeddings tables
         n_upper = sum(s.stop - s.start for s in st.bucket_early_upper)
         per_layer = 4 * 768 * 768 + 2 * 768 * 3072
-        assert n_upper == 2 * 3 * per_layer
-        off = st.offsets["lxrt_encoder.model.bert.encoder.r_layers.3.output.dense.weight"][0]
-        assert any(s.start <= off < s.stop for s in st.bucket_early_upper)
-        off = st.offsets["lxrt_encoder.model.bert.encoder.layer.1.output.dense.weight"][0]
-        assert any(s.start <= off < s.stop for s in st.bucket_early_rest)
+        n_emb = (30522 + 512 + 2 + 2) * 768
+        assert n_upper == (5 + 3) * per_layer + n_emb
+        in_upper = lambda k: any(s.start <= st.offsets[k][0] < s.stop for s in st.bucket_early_upper)
+        e = "lxrt_encoder.model.bert."
+        assert in_upper(e + "encoder.r_layers.3.output.dense.weight")
+        assert in_upper(e + "encoder.layer.0.output.dense.weight")
+        assert in_upper(e + "embeddings.word_embeddings.weight") and in_upper(e + "embeddings.LayerNorm.bias")
+        assert not in_upper(e + "encoder.r_layers.1.output.dense.weight")
+        assert not in_upper(e + "encoder.layer.0.output.dense.bias")
