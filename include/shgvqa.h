@@ -148,6 +148,9 @@ typedef struct {
                                  k/32 = key k kept), so that the backward reads 1 bit instead of re-hashing per element */
 } shg_attn_args;
 int shg_attn_fwd(const shg_attn_args* args, void* stream);
+/* Selects the experimental warp-specialised, pipelined forward for mask_mode 0 (default off: measured slower; also
+ * SHG_ATTN_PIPE=1 in the environment).  Same results within the kernel's tolerance. */
+int shg_set_attn_pipeline(int on);
 
 /* Backward of the above (autograd of lxrt/modeling_capsbert.py:394-417 / nn.MultiheadAttention).  Recomputes
  * the probabilities from q, k and the saved lse; d_o is the gradient of o; writes dq/dk/dv (bf16, same head

@@ -300,9 +300,22 @@ def _attn_ref(q, k, v, b, lq, lk, scale, add_mask):
 @pytest.mark.parametrize("lq,lk,mode", [(40, 40, "key"), (393, 393, "none"), (40, 393, "none"), (393, 40, "key"),
                                         (128, 128, "causal8"), (128, 393, "none"), (48, 48, "causal3"),
                                         (48, 393, "none"), (40, 177, "key"), (177, 40, "key"), (1, 5, "none")])
-def test_attention_fwd_all_path_shapes(ops, lq, lk, mode):
-    """The ten (Lq, Lk, mask) problems of SURVEY §8d, read from packed QKV buffers in place.
+@pytest.mark.parametrize("pipelined", [0, 1])
+def test_attention_fwd_all_path_shapes(ops, lq, lk, mode, pipelined):
+    """The ten (Lq, Lk, mask) problems of SURVEY §8d, read from packed QKV buffers in place, through the default
+    kernel and (mask-free shapes) the experimental pipelined one.
     Tolerance: 2e-2 of the output scale (bf16 P and bf16 output)."""
+    from shg_vqa_b200 import _lib
+    if pipelined and mode != "none":
+        pytest.skip("the pipelined kernel only takes mask_mode 0")
+    _lib.check(_lib.lib().shg_set_attn_pipeline(pipelined))
+    try:
+        _attention_fwd_case(ops, lq, lk, mode)
+    finally:
+        _lib.check(_lib.lib().shg_set_attn_pipeline(0))
+
+
+def _attention_fwd_case(ops, lq, lk, mode):
     b = 3
     g = torch.Generator().manual_seed(lq * 1000 + lk)
     qkv_q = torch.randn(b * lq, 2304, generator=g).to(torch.bfloat16).to(_dev())
