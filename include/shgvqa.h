@@ -113,6 +113,12 @@ typedef struct {
     int splits;        /* 0 = choose (split-K only with SHG_GEMM_ACCUMULATE); > 1 requires SHG_GEMM_ACCUMULATE */
     int block_n;       /* 0 = choose; else 64|128|192|256, optionally | 1024 to force CTA-pair (256-row) tiles
                           (128/256 only) or | 2048 to forbid them */
+    /* grouped product (the two DETR decoders in lock-step, lxrt/transformer.py:95-124 run twice in
+     * tasks/agqa_model.py:220-249): rows [0, split_m) of A use b / bias, rows [split_m, m) use b2 / bias2 — two
+     * nn.Linear layers of the same shape in one launch.  b2 NULL = ordinary product.  split_m % 128 == 0. */
+    const void* b2;
+    const float* bias2;
+    int split_m;
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
 /* Debug aid: CTA 0 of subsequent shg_gemm launches writes 7 %globaltimer phase stamps to buf (8 x u64 device
@@ -200,6 +206,18 @@ int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void
                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
                       int rows, int n, void* dx_drop, float out_p, uint32_t out_salt, float in_p, uint32_t in_salt,
                       const uint32_t* seed, void* stream);
+
+/* Grouped forms: rows [0, split_row) use (gamma, beta, dgamma, dbeta, dxsum), rows [split_row, rows) the second set —
+ * the same LayerNorm position of the relation and action decoders (lxrt/transformer.py:199-201) in one launch over
+ * their stacked token rows.  split_row >= rows degenerates to the plain call. */
+int shg_layernorm_fwd_grouped(const void* x, const void* residual, const float* gamma, const float* beta, float eps,
+                              void* y, void* y2, const void* addend, int addend_rows, float* mean, float* rstd, int rows,
+                              int n, int split_row, const float* gamma2, const float* beta2, void* stream);
+int shg_layernorm_bwd_grouped(const void* dy, const void* dy2, const void* x, const void* residual, const float* gamma,
+                              const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
+                              int rows, int n, void* dx_drop, float out_p, uint32_t out_salt, float in_p,
+                              uint32_t in_salt, const uint32_t* seed, int split_row, const float* gamma2,
+                              float* dgamma2, float* dbeta2, float* dxsum2, void* stream);
 
 /* out[n] += column sums of the bf16 matrix x [rows, n] (ld elements per row, ld % 8 == 0): bias gradients. */
 int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, void* stream);

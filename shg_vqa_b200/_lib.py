@@ -28,7 +28,8 @@ class GemmArgs(ctypes.Structure):
                 ("preact", c_vp), ("act", c_int),
                 ("mul_aux", c_vp), ("mul_mode", c_int), ("mul_scale", c_f32),
                 ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp),
-                ("flags", c_int), ("splits", c_int), ("block_n", c_int)]
+                ("flags", c_int), ("splits", c_int), ("block_n", c_int),
+                ("b2", c_vp), ("bias2", c_vp), ("split_m", c_int)]
 
 
 class AttnArgs(ctypes.Structure):
@@ -77,6 +78,11 @@ SIGNATURES = {
     "shg_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp],
     "shg_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_f32,
                           ctypes.c_uint32, c_f32, ctypes.c_uint32, c_vp, c_vp],
+    "shg_layernorm_fwd_grouped": [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int,
+                                  c_int, c_vp, c_vp, c_vp],
+    "shg_layernorm_bwd_grouped": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp,
+                                  c_f32, ctypes.c_uint32, c_f32, ctypes.c_uint32, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp],
     "shg_colsum_accum": [c_vp, c_i64, c_int, c_int, c_vp, c_vp],
     "shg_embed_ln_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_int, c_int,
                          c_int, c_f32, ctypes.c_uint32, c_vp, c_vp],

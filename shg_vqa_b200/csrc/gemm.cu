@@ -38,6 +38,8 @@ struct GemmParams {
     int splits, block_n, n_stages;
     int m_tiles, n_tiles, kb_total, kb_per_split;
     unsigned long long* dbg;   // optional phase timestamps of CTA 0 (tools/gemm_phases.py), normally null
+    int split_m;               // grouped product: rows >= split_m use the second B operand / bias (INT_MAX: one group)
+    const float* bias2;
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -274,7 +276,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_b2, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stg = smem;                               // TMA-store staging (present only when p.tma_store)
@@ -337,11 +339,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         tma_load_2d(sa, &tma_a, full_bar + stage, m0, k0);
                         tma_load_2d(sa + 8192, &tma_a, full_bar + stage, m0 + 64, k0);
                     }
+                    const CUtensorMap* tb = m0 >= p.split_m ? &tma_b2 : &tma_b;
                     if (!B_MN) {
-                        tma_load_2d(sb, &tma_b, full_bar + stage, k0, n0);
+                        tma_load_2d(sb, tb, full_bar + stage, k0, n0);
                     } else {
                         for (int h = 0; h * 64 < p.block_n; ++h)
-                            tma_load_2d(sb + h * 8192, &tma_b, full_bar + stage, n0 + h * 64, k0);
+                            tma_load_2d(sb + h * 8192, tb, full_bar + stage, n0 + h * 64, k0);
                     }
                     if (++stage == p.n_stages) {
                         stage = 0;
@@ -404,7 +407,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const bool row_ok = row < p.m;
             // bias of this tile -> shared memory (zero past N), while the main loop is still running
             float* sb = s_bias + as * 256;
-            if (etid < 256) sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
+            const float* bias = m0 >= p.split_m ? p.bias2 : p.bias;
+            if (etid < 256) sb[etid] = (bias && n0 + etid < p.n) ? __ldg(bias + n0 + etid) : 0.f;
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
             epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk,
@@ -440,7 +444,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
-             const GemmParams p) {
+             const __grid_constant__ CUtensorMap tma_b2, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stg = smem;
@@ -508,11 +512,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         tma_load_2d_pair(sa, &tma_a, full_bar + stage, m0, k0);
                         tma_load_2d_pair(sa + 8192, &tma_a, full_bar + stage, m0 + 64, k0);
                     }
+                    const CUtensorMap* tb = m0 >= p.split_m ? &tma_b2 : &tma_b;
                     if (!B_MN) {
-                        tma_load_2d_pair(sb, &tma_b, full_bar + stage, k0, n0);
+                        tma_load_2d_pair(sb, tb, full_bar + stage, k0, n0);
                     } else {
                         for (int h = 0; h * 64 < half_n; ++h)
-                            tma_load_2d_pair(sb + h * 8192, &tma_b, full_bar + stage, n0 + h * 64, k0);
+                            tma_load_2d_pair(sb + h * 8192, tb, full_bar + stage, n0 + h * 64, k0);
                     }
                     if (++stage == p.n_stages) {
                         stage = 0;
@@ -571,7 +576,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             const int row = m0 + quarter * 32 + lane;
             const bool row_ok = row < p.m;
             float* sb = s_bias + as * 256;
-            if (etid < 256) sb[etid] = (p.bias && n0 + etid < p.n) ? __ldg(p.bias + n0 + etid) : 0.f;
+            const float* bias = m0 >= p.split_m ? p.bias2 : p.bias;
+            if (etid < 256) sb[etid] = (bias && n0 + etid < p.n) ? __ldg(bias + n0 + etid) : 0.f;
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
             epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk,
@@ -682,6 +688,10 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_gemm: dropout_p=%f", (double)p.drop.p);
     SHG_REQUIRE(p.drop.p == 0.f || (a->n % 2 == 0 && !accumulate), SHG_ESHAPE, "shg_gemm: dropout needs even N and a plain store");
     p.out_f32 = (a->flags & SHG_GEMM_OUT_F32) || accumulate, p.accumulate = accumulate;
+    const bool grouped = a->b2 != nullptr;
+    p.split_m = grouped ? a->split_m : 0x7fffffff, p.bias2 = a->bias2;
+    SHG_REQUIRE(!grouped || (a->split_m > 0 && a->split_m < a->m && a->split_m % BM == 0 && !a->a_mn_major && !accumulate),
+                SHG_ESHAPE, "shg_gemm: grouped product needs 0 < split_m < m, split_m %% 128 == 0, row-major A, no split-K");
     p.m_tiles = (a->m + BM - 1) / BM;
     // block_n: 0 = choose everything; low bits = tile width; | 1024 forces CTA-pair tiles (256 x bn), | 2048 forbids them
     const int bn_req = a->block_n & 1023;            // (| 4096: direct-store epilogue, for A/B comparison)
@@ -690,7 +700,10 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     if (!bn_req) {
         const bool forced = (a->block_n & (1024 | 2048)) != 0;
         pick_config(a->m, a->n, a->k, splits, a->b_mn_major != 0, accumulate, !forced || pair, !forced || !pair, &pair, &bn);
+        if (pair && grouped && a->split_m % 256 != 0)       // a 256-row pair tile must not straddle the groups
+            pick_config(a->m, a->n, a->k, splits, a->b_mn_major != 0, accumulate, false, true, &pair, &bn);
     }
+    SHG_REQUIRE(!(pair && grouped && a->split_m % 256 != 0), SHG_ESHAPE, "shg_gemm: CTA-pair tiles need split_m %% 256 == 0");
     SHG_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, SHG_ESHAPE, "shg_gemm: block_n=%d", bn);
     SHG_REQUIRE(!pair || bn == 128 || bn == 256 || (bn == 192 && !a->b_mn_major), SHG_ESHAPE,
                 "shg_gemm: CTA-pair tiles need block_n 128 or 256 (192 with a K-major B operand)");
@@ -726,6 +739,11 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     strides[0] = (uint64_t)a->ldb * 2;
     tb = get_tmap_bf16(a->b, 2, dims, strides, box);
     if (!tb) return SHG_ECUDA;
+    const CUtensorMap* tb2 = tb;
+    if (grouped) {
+        tb2 = get_tmap_bf16(a->b2, 2, dims, strides, box);     // same geometry as B
+        if (!tb2) return SHG_ECUDA;
+    }
     const CUtensorMap *td = ta, *tpre = ta;          // placeholders when the staged store is off
     if (p.tma_store) {
         dims[0] = a->n, dims[1] = a->m, box[0] = 64, box[1] = BM;
@@ -749,7 +767,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm2_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set2 = true;                                                                                  \
         }                                                                                                      \
-        shg::launch(gemm2_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, p);                                  \
+        shg::launch(gemm2_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, p);                                  \
     } while (0)
     if (pair) {
         if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);
@@ -766,7 +784,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set = true;                                                                                  \
         }                                                                                                     \
-        shg::launch(gemm_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, p);                                  \
+        shg::launch(gemm_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, p);                                  \
     } while (0)
     if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM_LAUNCH(false, false);
     else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM_LAUNCH(false, true);

@@ -68,13 +68,15 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
                      const __nv_bfloat16* __restrict__ addend, int addend_rows, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int rows) {
+                     float* __restrict__ rstd_out, int rows, int split_row, const float* __restrict__ gamma2,
+                     const float* __restrict__ beta2) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
+    if (row >= split_row) gamma = gamma2, beta = beta2;      // second parameter group (warp-uniform)
     float v[CH][8];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -119,10 +121,20 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dxsum, int rows,
-                     __nv_bfloat16* __restrict__ dx_drop, DropCfg out_drop, DropCfg in_drop) {
+                     __nv_bfloat16* __restrict__ dx_drop, DropCfg out_drop, DropCfg in_drop, int split_row,
+                     const float* __restrict__ gamma2, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
+                     float* __restrict__ dxsum2) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int N = 256 * CH;
+    // grouped launch: blockIdx.y = 1 handles rows [split_row, rows) with the second parameter / gradient set
+    int row_begin = 0;
+    if (blockIdx.y == 1) {
+        row_begin = split_row;
+        gamma = gamma2, dgamma = dgamma2, dbeta = dbeta2, dxsum = dxsum2;
+    } else if (gridDim.y == 2) {
+        rows = split_row;
+    }
     __shared__ float red[kRowWarps][256 + 8];
     uint32_t okey = 0, oth = 0, ikey = 0, ith = 0;
     float oinv = 1.f, iinv = 1.f;
@@ -138,7 +150,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
     for (int j = 0; j < CH; ++j) load8(gamma + (j * 32 + lane) * 8, gm[j]);
 
-    for (int row = blockIdx.x * kRowWarps + warp; row < rows; row += gridDim.x * kRowWarps) {
+    for (int row = row_begin + blockIdx.x * kRowWarps + warp; row < rows; row += gridDim.x * kRowWarps) {
         const float mean = mean_in[row], rstd = rstd_in[row];
         float g[CH][8], xh[CH][8];
         float s1 = 0.f, s2 = 0.f;
@@ -454,49 +466,74 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 
 extern "C" {
 
-int shg_layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta, float eps, void* y,
-                      void* y2, const void* addend, int addend_rows, float* mean, float* rstd, int rows, int n,
-                      void* stream) {
+int shg_layernorm_fwd_grouped(const void* x, const void* residual, const float* gamma, const float* beta, float eps,
+                              void* y, void* y2, const void* addend, int addend_rows, float* mean, float* rstd, int rows,
+                              int n, int split_row, const float* gamma2, const float* beta2, void* stream) {
     using namespace shg;
     SHG_REQUIRE(n == 768 || n == 1536, SHG_ESHAPE, "shg_layernorm_fwd: width %d (768 or 1536 supported)", n);
     SHG_REQUIRE((y2 == nullptr) == (addend == nullptr), SHG_EINVAL, "shg_layernorm_fwd: y2 and addend go together");
     SHG_REQUIRE((mean == nullptr) == (rstd == nullptr), SHG_EINVAL, "shg_layernorm_fwd: mean and rstd go together");
+    SHG_REQUIRE(split_row >= rows || (gamma2 && beta2 && split_row > 0), SHG_EINVAL,
+                "shg_layernorm_fwd_grouped: second parameter set missing");
     if (rows <= 0) return SHG_OK;
     const int blocks = (rows + kRowWarps - 1) / kRowWarps;
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 768)
-        shg::launch(layernorm_fwd_kernel<3>, blocks, kRowThreads, 0, s, 
+        shg::launch(layernorm_fwd_kernel<3>, blocks, kRowThreads, 0, s,
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, eps, (__nv_bfloat16*)y,
-            (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows);
+            (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows, split_row, gamma2, beta2);
     else
-        shg::launch(layernorm_fwd_kernel<6>, blocks, kRowThreads, 0, s, 
+        shg::launch(layernorm_fwd_kernel<6>, blocks, kRowThreads, 0, s,
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, eps, (__nv_bfloat16*)y,
-            (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows);
+            (__nv_bfloat16*)y2, (const __nv_bfloat16*)addend, addend_rows, mean, rstd, rows, split_row, gamma2, beta2);
     return check_launch("shg_layernorm_fwd");
+}
+
+int shg_layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta, float eps, void* y,
+                      void* y2, const void* addend, int addend_rows, float* mean, float* rstd, int rows, int n,
+                      void* stream) {
+    return shg_layernorm_fwd_grouped(x, residual, gamma, beta, eps, y, y2, addend, addend_rows, mean, rstd, rows, n,
+                                     0x7fffffff, nullptr, nullptr, stream);
+}
+
+int shg_layernorm_bwd_grouped(const void* dy, const void* dy2, const void* x, const void* residual, const float* gamma,
+                              const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
+                              int rows, int n, void* dx_drop, float out_p, uint32_t out_salt, float in_p,
+                              uint32_t in_salt, const uint32_t* seed, int split_row, const float* gamma2,
+                              float* dgamma2, float* dbeta2, float* dxsum2, void* stream) {
+    using namespace shg;
+    DropCfg od{(seed && dx_drop) ? out_p : 0.f, out_salt, seed}, id{seed ? in_p : 0.f, in_salt, seed};
+    SHG_REQUIRE(n == 768 || n == 1536, SHG_ESHAPE, "shg_layernorm_bwd: width %d (768 or 1536 supported)", n);
+    if (rows <= 0) return SHG_OK;
+    const bool grouped = split_row < rows;
+    SHG_REQUIRE(!grouped || (split_row > 0 && gamma2 && dgamma2 && dbeta2 && (dxsum2 != nullptr) == (dxsum != nullptr)),
+                SHG_EINVAL, "shg_layernorm_bwd_grouped: second parameter / gradient set missing");
+    const int rows_max = grouped ? (split_row > rows - split_row ? split_row : rows - split_row) : rows;
+    int blocks = (rows_max + kRowWarps - 1) / kRowWarps;
+    const int cap = grouped ? kNumSMs : 2 * kNumSMs;
+    if (blocks > cap) blocks = cap;
+    dim3 grid(blocks, grouped ? 2 : 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 768)
+        shg::launch(layernorm_bwd_kernel<3>, grid, kRowThreads, 0, s,
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
+            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
+            (__nv_bfloat16*)dx_drop, od, id, split_row, gamma2, dgamma2, dbeta2, dxsum2);
+    else
+        shg::launch(layernorm_bwd_kernel<6>, grid, kRowThreads, 0, s,
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
+            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
+            (__nv_bfloat16*)dx_drop, od, id, split_row, gamma2, dgamma2, dbeta2, dxsum2);
+    return check_launch("shg_layernorm_bwd");
 }
 
 int shg_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* residual, const float* gamma,
                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dxsum,
                       int rows, int n, void* dx_drop, float out_p, uint32_t out_salt, float in_p, uint32_t in_salt,
                       const uint32_t* seed, void* stream) {
-    using namespace shg;
-    DropCfg od{(seed && dx_drop) ? out_p : 0.f, out_salt, seed}, id{seed ? in_p : 0.f, in_salt, seed};
-    SHG_REQUIRE(n == 768 || n == 1536, SHG_ESHAPE, "shg_layernorm_bwd: width %d (768 or 1536 supported)", n);
-    if (rows <= 0) return SHG_OK;
-    int blocks = (rows + kRowWarps - 1) / kRowWarps;
-    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (n == 768)
-        shg::launch(layernorm_bwd_kernel<3>, blocks, kRowThreads, 0, s, 
-            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
-            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
-            (__nv_bfloat16*)dx_drop, od, id);
-    else
-        shg::launch(layernorm_bwd_kernel<6>, blocks, kRowThreads, 0, s, 
-            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x,
-            (const __nv_bfloat16*)residual, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum, rows,
-            (__nv_bfloat16*)dx_drop, od, id);
-    return check_launch("shg_layernorm_bwd");
+    return shg_layernorm_bwd_grouped(dy, dy2, x, residual, gamma, mean, rstd, dx, dgamma, dbeta, dxsum, rows, n, dx_drop,
+                                     out_p, out_salt, in_p, in_salt, seed, 0x7fffffff, nullptr, nullptr, nullptr,
+                                     nullptr, stream);
 }
 
 int shg_colsum_accum(const void* x, int64_t ld, int rows, int n, float* out, void* stream) {

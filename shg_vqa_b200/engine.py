@@ -62,6 +62,8 @@ class Engine:
         # 48-query action decoder) fill SMs the 148-CTA persistent kernels of the visual side leave idle.
         self.use_streams = self.dev.type == "cuda"
         self.join_wgrads_after_late = True
+        import os
+        self.fused_decoders = os.environ.get("SHG_FUSED_DECODERS", "1") != "0"
         # (stream priorities — chains high, weight gradients low — were measured: no effect on the replayed step)
         self.s1 = torch.cuda.Stream(self.dev) if self.use_streams else None
         self.s2 = torch.cuda.Stream(self.dev) if self.use_streams else None
@@ -448,6 +450,137 @@ class Engine:
         dtgt = ops.gemm(dv, D["sa_v"].w, b_t=True, residual=ds1)
         return dtgt, dtgt_p
 
+    # ------------------------------------------------------------------ both DETR decoders in lock-step
+    # The relation and the action decoder have the same structure and depth and different weights.  Run one after the
+    # other — or on two streams — their 5-30 us kernels on 4096 / 1536 rows mostly serialise (persistent one-CTA-per-SM
+    # GEMMs).  Here their token rows are stacked ([B*128 relation rows | B*48 action rows]) and every projection /
+    # LayerNorm of a layer position is ONE grouped launch (rows >= split read the action decoder's weights); only the
+    # attention calls (different query counts) and the weight-gradient products stay per decoder.
+    def _g2(self, x, A, Bm, split, **kw):
+        return ops.gemm(x, A.w, bias=A.b, b2=Bm.w, bias2=Bm.b, split_m=split, **kw)
+
+    def _g2t(self, dy, A, Bm, split, **kw):
+        return ops.gemm(dy, A.w, b_t=True, b2=Bm.w, split_m=split, **kw)
+
+    def _wgrad2(self, A, Bm, dy, x, split, bias=True):
+        self._wgrad(A, dy[:split], x[:split], bias=bias)
+        self._wgrad(Bm, dy[split:], x[split:], bias=bias)
+
+    def _ln2_fwd(self, x, NA, NB, split, eps, addend=None, save=False):
+        return ops.layernorm_fwd(x, NA.g, NA.b, eps, addend=addend, save_stats=save, group=(split, NB.g, NB.b))
+
+    def _ln2_bwd(self, dy, x, NA, NB, split, m, r, drop, dy2=None, dxsum=None):
+        res = ops.layernorm_bwd(dy, x, NA.g, m, r, NA.gg, NA.gb, dy2=dy2, dxsum=dxsum[0] if dxsum else None,
+                                out_drop=drop, group=(split, NB.g, NB.gg, NB.gb, dxsum[1] if dxsum else None))
+        return res if drop is not None else (res, res)
+
+    def _attn2_fwd(self, q, k, v, B, nq, lk, split, frames, save, drop, kv_rel=None, kv_act=None):
+        """Self-attention (k, v stacked like q) or cross-attention over the visual memory (kv_rel / kv_act =
+        (k, v) column slices of the hoisted K/V buffer) for both decoders; two launches into one stacked output."""
+        out = torch.empty(q.shape[0], H, device=self.dev, dtype=BF16)
+        res = []
+        for g, (r0, r1) in enumerate(((0, split), (split, q.shape[0]))):
+            n = nq[g]
+            if kv_rel is None:
+                kk, vv, lkk, fr = k[r0:r1], v[r0:r1], n, (frames[g], frames[g])
+            else:
+                kk, vv = (kv_rel, kv_act)[g]
+                lkk, fr = lk, None
+            _, sv = ops.attention_fwd(q[r0:r1], kk, vv, B, n, lkk, frames=fr, save_lse=save, drop=drop[g], out=out[r0:r1])
+            res.append(sv)
+        return out, res
+
+    def _dec2_fwd(self, DA, DB, tgt, tgt_p, qpos, kv_rel, kv_act, B, nq, per, split, save, first):
+        qk = self._g2(tgt_p, DA["sa_qk"], DB["sa_qk"], split)
+        v = self._g2(tgt, DA["sa_v"], DB["sa_v"], split)
+        da1 = (self._drop(self.p_dec), self._drop(self.p_dec))
+        da2 = (self._drop(self.p_dec), self._drop(self.p_dec))
+        sa, lse1 = self._attn2_fwd(qk[:, :H], qk[:, H:], v, B, nq, None, split, per, save, da1)
+        d1, d2 = self._drop(self.p_dec), self._drop(self.p_dec)
+        s1 = self._g2(sa, DA["sa_o"], DB["sa_o"], split, residual=tgt, drop=d1)
+        t1, t1p, m1, r1 = self._ln2_fwd(s1, DA["n1"], DB["n1"], split, EPS_DETR, addend=qpos, save=save)
+        cq = self._g2(t1p, DA["ca_q"], DB["ca_q"], split)
+        ca, lse2 = self._attn2_fwd(cq, None, None, B, nq, 393, split, None, save, da2, kv_rel=kv_rel, kv_act=kv_act)
+        s2 = self._g2(ca, DA["ca_o"], DB["ca_o"], split, residual=t1, drop=d2)
+        t2, _, m2, r2 = self._ln2_fwd(s2, DA["n2"], DB["n2"], split, EPS_DETR, save=save)
+        d_in, d_out = self._drop(self.p_dec), self._drop(self.p_dec)
+        h = self._g2(t2, DA["l1"], DB["l1"], split, act="relu", drop=d_in)
+        s3 = self._g2(h, DA["l2"], DB["l2"], split, residual=t2, drop=d_out)
+        t3, t3p, m3, r3 = self._ln2_fwd(s3, DA["n3"], DB["n3"], split, EPS_DETR, addend=qpos, save=save)
+        return t3, t3p, (tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, t2, h, s3, m3, r3,
+                         d_in, d_out, first, d1, d2, da1, da2)
+
+    def _dec2_bwd(self, DA, DB, saved, dt3, dt3p, dqpos, kv_rel, kv_act, dkv_rel, dkv_act, B, nq, per, split):
+        (tgt, tgt_p, qk, v, sa, lse1, s1, m1, r1, t1p, cq, ca, lse2, s2, m2, r2, t2, h, s3, m3, r3, d_in, d_out, first,
+         d1, d2, da1, da2) = saved
+        rng = ((0, split), (split, tgt.shape[0]))
+        if dt3p is not None:
+            self._acc(dqpos, dt3p)
+        # FFN
+        ds3, ds3d = self._ln2_bwd(dt3, s3, DA["n3"], DB["n3"], split, m3, r3, d_out, dy2=dt3p,
+                                  dxsum=(DA["l2"].gb, DB["l2"].gb))
+        self._wgrad2(DA["l2"], DB["l2"], ds3d, h, split, bias=False)
+        dpre = self._g2t(ds3d, DA["l2"], DB["l2"], split, mul_aux=h, mul_mode="relu_mask",
+                         mul_scale=1.0 / (1.0 - d_in[0]) if d_in is not None else 1.0)
+        self._wgrad2(DA["l1"], DB["l1"], dpre, t2, split)
+        dt2 = self._g2t(dpre, DA["l1"], DB["l1"], split, residual=ds3)
+        # cross-attention
+        ds2, ds2d = self._ln2_bwd(dt2, s2, DA["n2"], DB["n2"], split, m2, r2, d2, dxsum=(DA["ca_o"].gb, DB["ca_o"].gb))
+        self._wgrad2(DA["ca_o"], DB["ca_o"], ds2d, ca, split, bias=False)
+        dca = self._g2t(ds2d, DA["ca_o"], DB["ca_o"], split)
+        dcq = torch.empty_like(cq)
+        for g, (a0, a1) in enumerate(rng):
+            kk, vv = (kv_rel, kv_act)[g]
+            dkk, dvv = (dkv_rel, dkv_act)[g]
+            ops.attention_bwd(cq[a0:a1], kk, vv, ca[a0:a1], dca[a0:a1], lse2[g], dcq[a0:a1], dkk, dvv, B, nq[g], 393,
+                              drop=da2[g])
+        self._wgrad2(DA["ca_q"], DB["ca_q"], dcq, t1p, split)
+        dt1p = self._g2t(dcq, DA["ca_q"], DB["ca_q"], split)
+        self._acc(dqpos, dt1p)
+        # self-attention
+        ds1, ds1d = self._ln2_bwd(ds2, s1, DA["n1"], DB["n1"], split, m1, r1, d1, dy2=dt1p,
+                                  dxsum=(DA["sa_o"].gb, DB["sa_o"].gb))
+        self._wgrad2(DA["sa_o"], DB["sa_o"], ds1d, sa, split, bias=False)
+        dsa = self._g2t(ds1d, DA["sa_o"], DB["sa_o"], split)
+        dqk, dv = torch.empty_like(qk), torch.empty_like(v)
+        for g, (a0, a1) in enumerate(rng):
+            ops.attention_bwd(qk[a0:a1, :H], qk[a0:a1, H:], v[a0:a1], sa[a0:a1], dsa[a0:a1], lse1[g], dqk[a0:a1, :H],
+                              dqk[a0:a1, H:], dv[a0:a1], B, nq[g], nq[g], frames=(per[g], per[g]), drop=da1[g])
+        self._wgrad2(DA["sa_qk"], DB["sa_qk"], dqk, tgt_p, split)
+        dtgt_p = self._g2t(dqk, DA["sa_qk"], DB["sa_qk"], split)
+        if first:
+            # tgt is the constant zero tensor (tasks/agqa_model.py:235): only the bias of the value projection learns
+            self._bias_grad(dv[:split], DA["sa_v"].gb)
+            self._bias_grad(dv[split:], DB["sa_v"].gb)
+            self._acc(dqpos, dtgt_p)
+            return None, None
+        self._wgrad2(DA["sa_v"], DB["sa_v"], dv, tgt, split)
+        dtgt = self._g2t(dv, DA["sa_v"], DB["sa_v"], split, residual=ds1)
+        return dtgt, dtgt_p
+
+    def _decoders2_fwd(self, qpos, kv_mem, B, nq, per, split, save):
+        tgt = torch.zeros_like(qpos)
+        tgt_p = qpos
+        saved = []
+        for i in range(self.nd):
+            cr, ca = i * 2 * H, (self.nd + i) * 2 * H
+            tgt, tgt_p, s = self._dec2_fwd(self.rel_dec[i], self.act_dec[i], tgt, tgt_p, qpos,
+                                           (kv_mem[:, cr:cr + H], kv_mem[:, cr + H:cr + 2 * H]),
+                                           (kv_mem[:, ca:ca + H], kv_mem[:, ca + H:ca + 2 * H]), B, nq, per, split, save,
+                                           first=(i == 0))
+            saved.append(s)
+        return tgt, saved
+
+    def _decoders2_bwd(self, saved, d_out, kv_mem, dkv_mem, B, nq, per, split):
+        dqpos = torch.zeros_like(d_out)
+        dt3, dt3p = d_out, None
+        for i in reversed(range(self.nd)):
+            cr, ca = i * 2 * H, (self.nd + i) * 2 * H
+            sl = lambda t, c: (t[:, c:c + H], t[:, c + H:c + 2 * H])
+            dt3, dt3p = self._dec2_bwd(self.rel_dec[i], self.act_dec[i], saved[i], dt3, dt3p, dqpos, sl(kv_mem, cr),
+                                       sl(kv_mem, ca), sl(dkv_mem, cr), sl(dkv_mem, ca), B, nq, per, split)
+        return dqpos
+
     @staticmethod
     def _acc(dst, src):
         ops.copy3d(src, dst, 1, 1, src.numel(), 0, 0, 0, 0, accumulate=True)
@@ -593,17 +726,34 @@ class Engine:
         if not hgqa:
             return out, ctx
         nq_r, nq_a = self.T * self.n_rel, self.T * self.n_act
-        rel_q, ctx["rel_q"] = self._hg_embed_fwd(self.rel_q, inp["rel_segment_ids"].reshape(-1), B, nq_r, save,
-                                                 self.p_relq)
-        rel_out, ctx["rel_dec"] = self._decoder_fwd(self.rel_dec, rel_q, kv_mem, 0, B, nq_r, self.n_rel, save)
-        out["rel_logits"], ctx["rel_head"] = self._head_fwd(self.class_embed, rel_out, save)
-        with self._on(self.s2):
+        if self.fused_decoders:
+            # both decoders in lock-step over stacked token rows (see _dec2_fwd)
+            split = B * nq_r
+            rel_q, ctx["rel_q"] = self._hg_embed_fwd(self.rel_q, inp["rel_segment_ids"].reshape(-1), B, nq_r, save,
+                                                     self.p_relq)
             act_q, ctx["act_q"] = self._hg_embed_fwd(self.act_q, inp["act_segment_ids"].reshape(-1), B, nq_a, save,
                                                      self.p_actq)
-            act_out, ctx["act_dec"] = self._decoder_fwd(self.act_dec, act_q, kv_mem, self.nd, B, nq_a, self.n_act,
-                                                        save)
-            out["act_logits"], ctx["act_head"] = self._head_fwd(self.action_embed, act_out, save)
-        self._join(self.s1, self.s2)
+            qpos = torch.cat([rel_q, act_q], dim=0)
+            dec_out, ctx["dec2"] = self._decoders2_fwd(qpos, kv_mem, B, (nq_r, nq_a), (self.n_rel, self.n_act), split,
+                                                       save)
+            rel_out, act_out = dec_out[:split], dec_out[split:]
+            self._fork(self.s2)
+            out["rel_logits"], ctx["rel_head"] = self._head_fwd(self.class_embed, rel_out, save)
+            with self._on(self.s2):
+                out["act_logits"], ctx["act_head"] = self._head_fwd(self.action_embed, act_out, save)
+            self._join(self.s1, self.s2)
+        else:
+            rel_q, ctx["rel_q"] = self._hg_embed_fwd(self.rel_q, inp["rel_segment_ids"].reshape(-1), B, nq_r, save,
+                                                     self.p_relq)
+            rel_out, ctx["rel_dec"] = self._decoder_fwd(self.rel_dec, rel_q, kv_mem, 0, B, nq_r, self.n_rel, save)
+            out["rel_logits"], ctx["rel_head"] = self._head_fwd(self.class_embed, rel_out, save)
+            with self._on(self.s2):
+                act_q, ctx["act_q"] = self._hg_embed_fwd(self.act_q, inp["act_segment_ids"].reshape(-1), B, nq_a, save,
+                                                         self.p_actq)
+                act_out, ctx["act_dec"] = self._decoder_fwd(self.act_dec, act_q, kv_mem, self.nd, B, nq_a, self.n_act,
+                                                            save)
+                out["act_logits"], ctx["act_head"] = self._head_fwd(self.action_embed, act_out, save)
+            self._join(self.s1, self.s2)
         out["rel_out"], out["act_out"] = rel_out, act_out
         # hypergraph tokens: [cls | per frame: actions + act_token, relations + rel_token]
         per = self.n_act + self.n_rel
@@ -666,19 +816,37 @@ class Engine:
         kv_mem = ctx["kv_mem"]
         dkv_mem = torch.empty_like(kv_mem)
         ctx["dkv_mem"] = dkv_mem
-        self._fork(self.s2)
-        # side stream 2: action head + decoder; main: relation head + decoder (disjoint parameters and dK/dV slices)
-        with self._on(self.s2):
-            d_act_out = self._head_bwd(self.action_embed, ctx["act_head"], d_act_logits)
-            self._acc(d_act_out, d_act_hg)
-            dq_a = self._decoder_bwd(self.act_dec, ctx["act_dec"], d_act_out, kv_mem, dkv_mem, self.nd, B, nq_a,
-                                     self.n_act)
-            self._hg_embed_bwd(self.act_q, ctx["act_q"], dq_a, B, nq_a)
-        d_rel_out = self._head_bwd(self.class_embed, ctx["rel_head"], d_rel_logits)
-        self._acc(d_rel_out, d_rel_hg)
-        dq_r = self._decoder_bwd(self.rel_dec, ctx["rel_dec"], d_rel_out, kv_mem, dkv_mem, 0, B, nq_r, self.n_rel)
-        self._hg_embed_bwd(self.rel_q, ctx["rel_q"], dq_r, B, nq_r)
-        self._join(self.s2)
+        if "dec2" in ctx:
+            # both decoders in lock-step (see _dec2_bwd): head backward per decoder into one stacked gradient
+            split = B * nq_r
+            d_out = torch.empty(B * (nq_r + nq_a), H, device=self.dev, dtype=BF16)
+            self._fork(self.s2)
+            with self._on(self.s2):
+                d_act_out = self._head_bwd(self.action_embed, ctx["act_head"], d_act_logits)
+                ops.copy3d(d_act_out, d_out[split:], 1, 1, d_act_out.numel(), 0, 0, 0, 0)
+            d_rel_out = self._head_bwd(self.class_embed, ctx["rel_head"], d_rel_logits)
+            ops.copy3d(d_rel_out, d_out[:split], 1, 1, d_rel_out.numel(), 0, 0, 0, 0)
+            self._join(self.s2)
+            self._acc(d_out[:split], d_rel_hg)
+            self._acc(d_out[split:], d_act_hg)
+            dq = self._decoders2_bwd(ctx["dec2"], d_out, kv_mem, dkv_mem, B, (nq_r, nq_a), (self.n_rel, self.n_act),
+                                     split)
+            self._hg_embed_bwd(self.rel_q, ctx["rel_q"], dq[:split], B, nq_r)
+            self._hg_embed_bwd(self.act_q, ctx["act_q"], dq[split:], B, nq_a)
+        else:
+            self._fork(self.s2)
+            # side stream 2: action head + decoder; main: relation head + decoder (disjoint parameters and dK/dV slices)
+            with self._on(self.s2):
+                d_act_out = self._head_bwd(self.action_embed, ctx["act_head"], d_act_logits)
+                self._acc(d_act_out, d_act_hg)
+                dq_a = self._decoder_bwd(self.act_dec, ctx["act_dec"], d_act_out, kv_mem, dkv_mem, self.nd, B, nq_a,
+                                         self.n_act)
+                self._hg_embed_bwd(self.act_q, ctx["act_q"], dq_a, B, nq_a)
+            d_rel_out = self._head_bwd(self.class_embed, ctx["rel_head"], d_rel_logits)
+            self._acc(d_rel_out, d_rel_hg)
+            dq_r = self._decoder_bwd(self.rel_dec, ctx["rel_dec"], d_rel_out, kv_mem, dkv_mem, 0, B, nq_r, self.n_rel)
+            self._hg_embed_bwd(self.rel_q, ctx["rel_q"], dq_r, B, nq_r)
+            self._join(self.s2)
         # hoisted K/V projection: one wgrad per decoder layer (their parameters belong to this half)
         mem = ctx["visn_r"]
         for i, D in enumerate(self._dec_layers()):

@@ -23,7 +23,8 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, preact=None, mul_aux=None,
-         mul_mode=None, mul_scale=1.0, drop=None, out=None, out_f32=False, accumulate=False, splits=0, block_n=0):
+         mul_mode=None, mul_scale=1.0, drop=None, out=None, out_f32=False, accumulate=False, splits=0, block_n=0,
+         b2=None, bias2=None, split_m=0):
     # drop = (p, salt, seed_tensor) enables training-mode dropout on the output (before the residual add)
     """D = epilogue(A . B^T).  a: [M,K] (or stored [K,M] with a_t), b: [N,K] (or stored [K,N] with b_t); bf16."""
     require_device(a)
@@ -59,6 +60,11 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
     args.mul_aux, args.mul_mode, args.mul_scale = ptr(mul_aux), MUL[mul_mode], mul_scale
     if drop is not None and drop[0] > 0:
         args.dropout_p, args.dropout_salt, args.dropout_seed = drop[0], drop[1], ptr(drop[2])
+    if b2 is not None:
+        # grouped product: rows >= split_m of A go through the second weight / bias (same shapes)
+        assert b2.dtype == BF16 and b2.shape == b.shape and _ld(b2) == _ld(b) and 0 < split_m < m
+        assert (bias2 is None) == (bias is None)
+        args.b2, args.bias2, args.split_m = ptr(b2), ptr(bias2), split_m
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
     args.splits, args.block_n = splits, (block_n | _PAIR_FLAG if block_n == 0 and _PAIR_FLAG else block_n)
     call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k, "%dx%dx%d %s%s%s" % (m, n, k, "T" if a_t else "N", "T" if b_t else "N", " acc" if accumulate else "")))
@@ -124,7 +130,8 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
 
 
-def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False):
+def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False, group=None):
+    """group = (split_row, gamma2, beta2): rows >= split_row are normalised with the second parameter set."""
     require_device(x)
     rows, n = x.shape
     assert x.dtype == BF16 and x.is_contiguous() and gamma.dtype == torch.float32
@@ -132,15 +139,17 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0
     y2 = torch.empty_like(x) if addend is not None else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty_like(mean) if save_stats else None
-    call("shg_layernorm_fwd", ptr(x), ptr(residual), ptr(gamma), ptr(beta), eps, ptr(y), ptr(y2), ptr(addend),
-         addend_rows, ptr(mean), ptr(rstd), rows, n, stream(),
+    split, g2, b2 = group if group is not None else (0x7fffffff, None, None)
+    call("shg_layernorm_fwd_grouped", ptr(x), ptr(residual), ptr(gamma), ptr(beta), eps, ptr(y), ptr(y2), ptr(addend),
+         addend_rows, ptr(mean), ptr(rstd), rows, n, split, ptr(g2), ptr(b2), stream(),
          work=("hbm", 2.0 * rows * n * (2 + (residual is not None) + 2 * (addend is not None)), "%dx%d" % (rows, n)))
     return y, y2, mean, rstd
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dy2=None, residual=None, dxsum=None, out_drop=None,
-                  in_drop=None):
-    """out_drop / in_drop = (p, salt, seed_tensor).  With out_drop returns (dx, dx_drop)."""
+                  in_drop=None, group=None):
+    """out_drop / in_drop = (p, salt, seed_tensor).  With out_drop returns (dx, dx_drop).
+    group = (split_row, gamma2, dgamma2, dbeta2, dxsum2): second parameter / gradient set for rows >= split_row."""
     require_device(dy)
     rows, n = x.shape
     dx = torch.empty_like(x)
@@ -148,9 +157,11 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dy2=None, residual=No
     idr = in_drop if (in_drop is not None and in_drop[0] > 0) else None
     dxd = torch.empty_like(x) if od is not None else None
     seed = od[2] if od is not None else (idr[2] if idr is not None else None)
-    call("shg_layernorm_bwd", ptr(dy), ptr(dy2), ptr(x), ptr(residual), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx),
-         ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, ptr(dxd), od[0] if od else 0.0, od[1] if od else 0,
-         idr[0] if idr else 0.0, idr[1] if idr else 0, ptr(seed), stream(),
+    split, g2, dg2, db2, dxs2 = group if group is not None else (0x7fffffff, None, None, None, None)
+    call("shg_layernorm_bwd_grouped", ptr(dy), ptr(dy2), ptr(x), ptr(residual), ptr(gamma), ptr(mean), ptr(rstd),
+         ptr(dx), ptr(dgamma), ptr(dbeta), ptr(dxsum), rows, n, ptr(dxd), od[0] if od else 0.0, od[1] if od else 0,
+         idr[0] if idr else 0.0, idr[1] if idr else 0, ptr(seed), split, ptr(g2), ptr(dg2), ptr(db2), ptr(dxs2),
+         stream(),
          work=("hbm", 2.0 * rows * n * (3 + (dy2 is not None) + (residual is not None)), "%dx%d" % (rows, n)))
     return (dx, dxd) if od is not None else dx
 

@@ -412,3 +412,50 @@ def test_gemm_cta_pair_tiles(ops, m, n, k, bn):
         ops.gemm(dy, x, a_t=True, b_t=True, out=dw, accumulate=True, splits=3, block_n=bn | 1024)
         ref = 1.0 + dy.float().t() @ x.float()
         assert (dw - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+# ----------------------------------------------------------------------------- grouped launches (decoders in lock-step)
+
+@pytest.mark.parametrize("m,split,n,k,b_t", [(5632, 4096, 768, 768, False), (5632, 4096, 2048, 768, False),
+                                             (704, 512, 768, 2048, False), (384, 128, 1536, 768, False),
+                                             (5632, 4096, 768, 2048, True), (352, 256, 768, 768, True)])
+def test_grouped_gemm_equals_two_products(ops, m, split, n, k, b_t):
+    """Rows [0, split) through (W1, b1), rows [split, m) through (W2, b2) in ONE launch == the two separate launches
+    bit for bit (same tiles, same accumulation order)."""
+    g = torch.Generator().manual_seed(m + n)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16).to(_dev())
+    shape = (k, n) if b_t else (n, k)
+    w1 = (torch.randn(*shape, generator=g) * 0.05).to(torch.bfloat16).to(_dev())
+    w2 = (torch.randn(*shape, generator=g) * 0.05).to(torch.bfloat16).to(_dev())
+    b1 = torch.randn(n, generator=g).to(_dev()) if not b_t else None
+    b2 = torch.randn(n, generator=g).to(_dev()) if not b_t else None
+    res = torch.randn(m, n, generator=g).to(torch.bfloat16).to(_dev())
+    got = ops.gemm(a, w1, b_t=b_t, bias=b1, residual=res, b2=w2, bias2=b2, split_m=split)
+    ref = torch.cat([a[:split].float() @ (w1.float() if b_t else w1.float().t()) + (0 if b1 is None else b1),
+                     a[split:].float() @ (w2.float() if b_t else w2.float().t()) + (0 if b2 is None else b2)]) + res.float()
+    err = (got.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), err
+    # and the second group really used the second weight
+    wrong = ops.gemm(a, w1, b_t=b_t, bias=b1, residual=res)
+    assert (wrong[split:].float() - ref[split:]).abs().max().item() > 10 * err
+
+
+def test_grouped_layernorm_fwd_bwd(ops):
+    g = torch.Generator().manual_seed(5)
+    rows, split, n = 704, 512, 768
+    x = torch.randn(rows, n, generator=g).to(torch.bfloat16).to(_dev())
+    p = [torch.randn(n, generator=g).to(_dev()) for _ in range(4)]          # gamma1, beta1, gamma2, beta2
+    y, _, mean, rstd = ops.layernorm_fwd(x, p[0], p[1], 1e-5, save_stats=True, group=(split, p[2], p[3]))
+    ya, _, ma, ra = ops.layernorm_fwd(x[:split].contiguous(), p[0], p[1], 1e-5, save_stats=True)
+    yb, _, mb, rb = ops.layernorm_fwd(x[split:].contiguous(), p[2], p[3], 1e-5, save_stats=True)
+    assert torch.equal(y, torch.cat([ya, yb])) and torch.equal(mean, torch.cat([ma, mb]))
+    dy = torch.randn(rows, n, generator=g).to(torch.bfloat16).to(_dev())
+    z = lambda: torch.zeros(n, device=_dev())
+    dg1, db1, dx1, dg2, db2, dx2 = z(), z(), z(), z(), z(), z()
+    dx = ops.layernorm_bwd(dy, x, p[0], mean, rstd, dg1, db1, dxsum=dx1, group=(split, p[2], dg2, db2, dx2))
+    rg1, rb1, rx1, rg2, rb2, rx2 = z(), z(), z(), z(), z(), z()
+    dxa = ops.layernorm_bwd(dy[:split].contiguous(), x[:split].contiguous(), p[0], ma, ra, rg1, rb1, dxsum=rx1)
+    dxb = ops.layernorm_bwd(dy[split:].contiguous(), x[split:].contiguous(), p[2], mb, rb, rg2, rb2, dxsum=rx2)
+    assert torch.equal(dx, torch.cat([dxa, dxb]))
+    for a, b in ((dg1, rg1), (db1, rb1), (dx1, rx1), (dg2, rg2), (db2, rb2), (dx2, rx2)):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-3)
