@@ -479,6 +479,7 @@ class Engine:
         (k, v) column slices of the hoisted K/V buffer) for both decoders; two launches into one stacked output."""
         out = torch.empty(q.shape[0], H, device=self.dev, dtype=BF16)
         res = []
+        self._fork(self.s2)                     # the action decoder's (smaller) problem runs beside the relation one
         for g, (r0, r1) in enumerate(((0, split), (split, q.shape[0]))):
             n = nq[g]
             if kv_rel is None:
@@ -486,8 +487,11 @@ class Engine:
             else:
                 kk, vv = (kv_rel, kv_act)[g]
                 lkk, fr = lk, None
-            _, sv = ops.attention_fwd(q[r0:r1], kk, vv, B, n, lkk, frames=fr, save_lse=save, drop=drop[g], out=out[r0:r1])
+            with self._on(self.s2 if g == 1 else None):
+                _, sv = ops.attention_fwd(q[r0:r1], kk, vv, B, n, lkk, frames=fr, save_lse=save, drop=drop[g],
+                                          out=out[r0:r1])
             res.append(sv)
+        self._join(self.s2)
         return out, res
 
     def _dec2_fwd(self, DA, DB, tgt, tgt_p, qpos, kv_rel, kv_act, B, nq, per, split, save, first):
@@ -529,11 +533,14 @@ class Engine:
         self._wgrad2(DA["ca_o"], DB["ca_o"], ds2d, ca, split, bias=False)
         dca = self._g2t(ds2d, DA["ca_o"], DB["ca_o"], split)
         dcq = torch.empty_like(cq)
+        self._fork(self.s2)
         for g, (a0, a1) in enumerate(rng):
             kk, vv = (kv_rel, kv_act)[g]
             dkk, dvv = (dkv_rel, dkv_act)[g]
-            ops.attention_bwd(cq[a0:a1], kk, vv, ca[a0:a1], dca[a0:a1], lse2[g], dcq[a0:a1], dkk, dvv, B, nq[g], 393,
-                              drop=da2[g])
+            with self._on(self.s2 if g == 1 else None):
+                ops.attention_bwd(cq[a0:a1], kk, vv, ca[a0:a1], dca[a0:a1], lse2[g], dcq[a0:a1], dkk, dvv, B, nq[g],
+                                  393, drop=da2[g])
+        self._join(self.s2)
         self._wgrad2(DA["ca_q"], DB["ca_q"], dcq, t1p, split)
         dt1p = self._g2t(dcq, DA["ca_q"], DB["ca_q"], split)
         self._acc(dqpos, dt1p)
@@ -543,9 +550,13 @@ class Engine:
         self._wgrad2(DA["sa_o"], DB["sa_o"], ds1d, sa, split, bias=False)
         dsa = self._g2t(ds1d, DA["sa_o"], DB["sa_o"], split)
         dqk, dv = torch.empty_like(qk), torch.empty_like(v)
+        self._fork(self.s2)
         for g, (a0, a1) in enumerate(rng):
-            ops.attention_bwd(qk[a0:a1, :H], qk[a0:a1, H:], v[a0:a1], sa[a0:a1], dsa[a0:a1], lse1[g], dqk[a0:a1, :H],
-                              dqk[a0:a1, H:], dv[a0:a1], B, nq[g], nq[g], frames=(per[g], per[g]), drop=da1[g])
+            with self._on(self.s2 if g == 1 else None):
+                ops.attention_bwd(qk[a0:a1, :H], qk[a0:a1, H:], v[a0:a1], sa[a0:a1], dsa[a0:a1], lse1[g],
+                                  dqk[a0:a1, :H], dqk[a0:a1, H:], dv[a0:a1], B, nq[g], nq[g],
+                                  frames=(per[g], per[g]), drop=da1[g])
+        self._join(self.s2)
         self._wgrad2(DA["sa_qk"], DB["sa_qk"], dqk, tgt_p, split)
         dtgt_p = self._g2t(dqk, DA["sa_qk"], DB["sa_qk"], split)
         if first:
