@@ -184,6 +184,9 @@ typedef struct {
     const uint32_t* dropout_bits;   /* the forward's keep-bit words, or NULL: the mask is regenerated from the triple */
 } shg_attn_bwd_args;
 int shg_attn_bwd(const shg_attn_bwd_args* args, void* stream);
+/* Problems with a single query tile (lq <= 128, o_f32 given) take ONE merged pass that also produces dk and dv
+ * (default on; 0 restores the two-pass schedule, also SHG_ATTN_MERGE=0 in the environment). */
+int shg_set_attn_bwd_merge(int on);
 
 /* ------------------------------------------------------------------ LayerNorm family (HBM-bound)
  * y = LN(x (+ residual)) * gamma + beta, rows of width n (768 / 1536), statistics fp32.  Replaces

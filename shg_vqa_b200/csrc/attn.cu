@@ -644,6 +644,37 @@ __device__ __forceinline__ void dq_group_math(const uint32_t (&rs)[32], const ui
     }
 }
 
+// merged pass (single query tile): ds_e as in the dq pass plus pd_e = dropout(p)_e / (1-p), the operand of dV
+template <bool KMASK, int DROP, bool VIS>
+__device__ __forceinline__ void dqkv_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&ds)[16],
+                                                uint32_t (&pd)[16], float c1, float neg_lse, const float* km, int n_vis,
+                                                float scale_keep, float nds, float inv_keep, uint32_t dkey, uint32_t pair0,
+                                                uint32_t dth, uint32_t bits) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        uint32_t dmask = 0xffffffffu;
+        if (DROP == 1) dmask = drop_pair_mask(dkey, pair0 + (i >> 1), dth);
+        float v2[2], p2[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int e = i + t;
+            float x = fmaf(__uint_as_float(rs[e]), c1, neg_lse);
+            if (KMASK) x += km[e];
+            float pr = ex2_approx(x);
+            if (!VIS) pr = e < n_vis ? pr : 0.f;
+            float g = fmaf(__uint_as_float(rp[e]), scale_keep, nds);
+            bool keep = true;
+            if (DROP == 1) keep = (dmask & (t ? 0xffff0000u : 0x0000ffffu)) != 0;
+            if (DROP == 2) keep = ((bits >> e) & 1u) != 0;
+            if (DROP) g = keep ? g : nds;
+            v2[t] = pr * g;
+            p2[t] = DROP ? (keep ? pr * inv_keep : 0.f) : pr;
+        }
+        ds[i >> 1] = pack_bf16x2(v2[0], v2[1]);
+        pd[i >> 1] = pack_bf16x2(p2[0], p2[1]);
+    }
+}
+
 // dkv pass (thread = key row, 32 queries): p_e as above with per-query lse, pd_e = dropout(p)_e (-> dV), ds_e (-> dK)
 template <int DROP, bool VIS>
 __device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&pr)[16],
@@ -682,7 +713,12 @@ __device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[32], const u
     }
 }
 
-template <int DROP>
+// MERGE (problems with ONE query tile, lq <= 128, o_f32 given): the same pass also produces dK and dV of every key
+// chunk — dV_j = dropout(P)_j^T dO and dK_j = dS_j^T Q are complete after a single query tile, so the separate dkv
+// pass (which recomputes S, dP and the exponentials per key tile) is not launched.  The bf16 P / dS tiles written for
+// the K-major dQ product are read as MN-major A operands (M = keys) by the two extra products: same bytes, no
+// transposed copy.  dK_j / dV_j leave TMEM at the start of the next iteration.
+template <int DROP, bool MERGE>
 __global__ void __launch_bounds__(kBwdThreads)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
                    const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
@@ -698,7 +734,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     uint8_t* sdO = smem + 16384;              // 16 KB
     uint8_t* sK = smem + 32768;               // 3 x 16 KB
     uint8_t* sV = smem + 81920;               // 3 x 16 KB
-    uint8_t* sdS = smem + 131072;             // 2 x 32 KB
+    uint8_t* sdS = smem + 131072;             // 2 x 32 KB (MERGE: one dS tile, then one P tile)
+    uint8_t* sPd = smem + 131072 + 32768;
     float* s_part = reinterpret_cast<float*>(smem + kBwdTileBytes);   // [4 quarters][128 rows][2], then [512] key mask
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024 + 512);
     uint64_t* bar_q = bars;          // Q + dO landed
@@ -727,8 +764,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const uint32_t tmem = *tmem_slot;
     pdl_launch_dependents();
     pdl_wait();
-    const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 256;
+    const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 256, t_dv = tmem + 320, t_dk = tmem + 384;
     const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
+    const uint32_t idesc_kv = make_idesc_bf16(128, kHeadDim, 1, 1);     // A = P^T / dS^T (MN-major), B = dO / Q rows
+    if (MERGE) {
+        // rows of the P / dS tiles that no thread writes (query rows beyond lq) are read by the dK / dV products
+        // against zero-filled dO / Q rows: keep them finite
+        for (int i = tid; i < 65536 / 16; i += kBwdThreads) reinterpret_cast<uint4*>(sdS)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        __syncthreads();
+    }
     // keys of chunk j that exist, rounded up to the MMA granule: the products of the last chunk are only that wide
     auto chunk_n16 = [&](int j) { return (min(128, p.lk - j * 128) + 15) & ~15; };
 
@@ -817,6 +862,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     // chunk's keys do no math at all: their dS entries feed only dQ rows that are never stored / k-steps never issued.
     const bool rows_live = q0 + (warp & 3) * 32 < p.lq;
     const float scale_keep = p.scale * inv_keep;
+    // MERGE: dK / dV of key chunk j (TMEM lanes = keys) -> global; thread = (key row, 16 of the 64 head columns)
+    auto store_dkv = [&](int j) {
+        const int key = j * 128 + row;
+        uint32_t rk[16], rv[16];
+        tmem_ld16(t_dk + t_row + quad * 16, rk);
+        tmem_ld16(t_dv + t_row + quad * 16, rv);
+        tmem_ld_wait();
+        if (key < p.lk) {
+            __nv_bfloat16* dk = p.dk + ((size_t)b * p.lk + key) * p.lddk + h * kHeadDim + quad * 16;
+            __nv_bfloat16* dv = p.dv + ((size_t)b * p.lk + key) * p.lddv + h * kHeadDim + quad * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(rk[i]), __uint_as_float(rk[i + 1]));
+                u.y = pack_bf16x2(__uint_as_float(rk[i + 2]), __uint_as_float(rk[i + 3]));
+                u.z = pack_bf16x2(__uint_as_float(rk[i + 4]), __uint_as_float(rk[i + 5]));
+                u.w = pack_bf16x2(__uint_as_float(rk[i + 6]), __uint_as_float(rk[i + 7]));
+                *reinterpret_cast<uint4*>(dk + i) = u;
+                u.x = pack_bf16x2(__uint_as_float(rv[i]), __uint_as_float(rv[i + 1]));
+                u.y = pack_bf16x2(__uint_as_float(rv[i + 2]), __uint_as_float(rv[i + 3]));
+                u.z = pack_bf16x2(__uint_as_float(rv[i + 4]), __uint_as_float(rv[i + 5]));
+                u.w = pack_bf16x2(__uint_as_float(rv[i + 6]), __uint_as_float(rv[i + 7]));
+                *reinterpret_cast<uint4*>(dv + i) = u;
+            }
+        }
+    };
     for (int jj = 0; jj < n_it; ++jj) {
         const bool sweep2 = jj >= n_pre;
         const int j = sweep2 ? jj - n_pre : jj;     // key chunk
@@ -835,6 +906,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             tmem_ld32(t_dp + t_row + c, rp);
             tmem_ld_wait();
         }
+        if (MERGE && jj >= 1) {
+            // products of the previous chunk retired: its dK / dV leave TMEM, its P / dS tiles and K/V buffer are free
+            mbar_wait(bar_dq + ((jj - 1) & 1), ((jj - 1) >> 1) & 1);
+            tc_fence_after();
+            store_dkv(jj - 1);
+        }
         tc_fence_before();
         __syncthreads();                            // every thread holds its S/dP values: the TMEM tiles are free
         if (tid == 0) {
@@ -851,7 +928,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 load_kv(jj + 2);
             }
         }
-        uint8_t* tile = sdS + (j2 & 1) * 32768;
+        uint8_t* tile = MERGE ? sdS : sdS + (j2 & 1) * 32768;
         if (live) {
             const int key0 = j * 128 + c;
             const int n_vis = k_lim - key0;            // visible columns of this group (may be <= 0 or >= 32)
@@ -871,14 +948,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 uint32_t ds[16];
                 const uint32_t pair0 = row_pair0 + (uint32_t)(key0 >> 1);
                 const float* km = s_kmask + key0;
-                if (__all_sync(0xffffffffu, n_vis >= 32)) {
+                if (MERGE) {
+                    uint32_t pd[16];
+                    if (__all_sync(0xffffffffu, n_vis >= 32)) {
+                        if (kmask) dqkv_group_math<true, DROP, true>(rs, rp, ds, pd, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, inv_keep, dkey, pair0, dth, keep_word);
+                        else dqkv_group_math<false, DROP, true>(rs, rp, ds, pd, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, inv_keep, dkey, pair0, dth, keep_word);
+                    } else {
+                        if (kmask) dqkv_group_math<true, DROP, false>(rs, rp, ds, pd, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, inv_keep, dkey, pair0, dth, keep_word);
+                        else dqkv_group_math<false, DROP, false>(rs, rp, ds, pd, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, inv_keep, dkey, pair0, dth, keep_word);
+                    }
+                    store_tile_chunk32_packed(sPd, row, c, pd);
+                } else if (__all_sync(0xffffffffu, n_vis >= 32)) {
                     if (kmask) dq_group_math<true, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
                     else dq_group_math<false, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
                 } else {
                     if (kmask) dq_group_math<true, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
                     else dq_group_math<false, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
                 }
-                if (j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
+                if (!MERGE && j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);   // dS tile free again
                 store_tile_chunk32_packed(tile, row, c, ds);
                 fence_proxy_async_smem();
             }
@@ -898,16 +985,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         }
         if (tid == 0 && sweep2) {
             tc_fence_after();
-            if (j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);
+            if (!MERGE && j2 >= 2) mbar_wait(bar_dq + (j2 & 1), ((j2 - 2) >> 1) & 1);
             const uint32_t a = smem_u32(tile), bk = smem_u32(sK + (jj % 3) * 16384);
             for (int ks = 0; ks < (n16 >> 4); ++ks)
                 umma_bf16(t_dq, tile_a_desc(a, ks), rows_b_desc(bk, ks), idesc_dq, (j2 > 0 || ks > 0) ? 1u : 0u);
+            if (MERGE) {
+                // dV_j = dropout(P)^T dO, dK_j = dS^T Q: A = the same tiles read MN-major (64-key atoms 16 KB apart,
+                // 8 query rows per 1 KB group), k runs over the 128 query rows
+                const uint32_t ap = smem_u32(sPd), bdo = smem_u32(sdO), bq = smem_u32(sQ);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(t_dv, make_smem_desc(ap + ks * 2048, 16384, 1024), rows_b_desc(bdo, ks), idesc_kv, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(t_dk, make_smem_desc(a + ks * 2048, 16384, 1024), rows_b_desc(bq, ks), idesc_kv, ks > 0);
+            }
             tc_commit(bar_dq + (j2 & 1));
         }
         __syncwarp();
     }
     mbar_wait(bar_dq + ((n_kc - 1) & 1), ((n_kc - 1) >> 1) & 1);
     tc_fence_after();
+    if (MERGE) store_dkv(n_kc - 1);
     {
         uint32_t raw[16];
         tmem_ld16(t_dq + t_row + quad * 16, raw);
@@ -1165,6 +1264,11 @@ static const CUtensorMap* head_tmap(const void* ptr, int64_t ld, int heads, int 
 // kernel (393 x 393, B = 32: 141 vs 119 us plain, 184 vs 150 us with dropout).  SHG_ATTN_PIPE=1 or
 // shg_set_attn_pipeline(1) selects it for mask_mode 0; the attention tests run both.
 static int g_attn_pipe = -1;
+static int g_attn_merge = -1;     // single-query-tile backward in one merged pass (default on; SHG_ATTN_MERGE=0: two passes)
+extern "C" int shg_set_attn_bwd_merge(int on) {
+    g_attn_merge = on ? 1 : 0;
+    return SHG_OK;
+}
 extern "C" int shg_set_attn_pipeline(int on) {
     g_attn_pipe = on ? 1 : 0;
     return SHG_OK;
@@ -1280,19 +1384,33 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
     const size_t smem = kBwdTileBytes + 12288 + 128 + 1024;   // tiles + per-row vectors / key mask / keep words + barriers + slack
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(attn_bwd_dkv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(attn_bwd_dkv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(attn_bwd_dkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 gq((a->lq + 127) / 128, a->heads, a->batch), gk((a->lk + 127) / 128, a->heads, a->batch);
-    if (drop == 2) shg::launch(attn_bwd_dq_kernel<2>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
-    else if (drop == 1) shg::launch(attn_bwd_dq_kernel<1>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
-    else shg::launch(attn_bwd_dq_kernel<0>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+    if (g_attn_merge < 0) {
+        const char* e = getenv("SHG_ATTN_MERGE");
+        g_attn_merge = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (a->lq <= 128 && a->o_f32 && g_attn_merge) {
+        // one query tile: dQ, dK and dV from a single pass (see attn_bwd_dq_kernel<., true>)
+        if (drop == 2) shg::launch(attn_bwd_dq_kernel<2, true>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+        else if (drop == 1) shg::launch(attn_bwd_dq_kernel<1, true>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+        else shg::launch(attn_bwd_dq_kernel<0, true>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+        return check_launch("shg_attn_bwd(merged)");
+    }
+    if (drop == 2) shg::launch(attn_bwd_dq_kernel<2, false>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+    else if (drop == 1) shg::launch(attn_bwd_dq_kernel<1, false>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
+    else shg::launch(attn_bwd_dq_kernel<0, false>, gq, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);
     int rc = check_launch("shg_attn_bwd(dq)");
     if (rc) return rc;
     if (drop == 2) shg::launch(attn_bwd_dkv_kernel<2>, gk, kBwdThreads, smem, s, *tq, *tdo, *tk, *tv, p);

@@ -14,6 +14,7 @@ GEMM_OUT_F32 = 1
 GEMM_ACCUMULATE = 2
 BF16 = torch.bfloat16
 import os as _os
+ATTN_BWD_MERGE = _os.environ.get("SHG_ATTN_MERGE", "1") != "0"     # mirrors the library's default (see shg_set_attn_bwd_merge)
 _PAIR_FLAG = {"0": 2048, "1": 1024}.get(_os.environ.get("SHG_GEMM_PAIR", ""), 0)   # debugging: forbid / force CTA-pair tiles
 
 
@@ -128,6 +129,8 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     if drop is not None and drop[0] > 0:
         a.dropout_bits = ptr(bits)
     call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
+    if lq <= 128 and o32 is not None and ATTN_BWD_MERGE:
+        _lib.launch_count -= 1          # single-query-tile problems take one merged launch instead of two
 
 
 def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False, group=None):
