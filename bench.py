@@ -27,7 +27,7 @@ BATCH_PER_GPU = 32
 TRAIN_GFLOP_PER_CLIP = 199.3      # 3 x 62.29 (fwd+bwd blocks) + 12.45 (forward-only LXRT x-layers)
 WORKLOAD = ("AGQA taskHGQA hot-path train step, bs32/GPU, from [B,393,768] visual tokens + question ids: "
             "l5/r5/x2 LXRT stack, 2x5-layer hypergraph decoders, heads, CrossEncoder, per-frame Hungarian matching, "
-            "set+answer loss, backward, grad clip, BertAdam (slow_r50 + Conv3d front-end excluded: stock PyTorch)")
+            "set+answer loss, backward, grad clip, BertAdam (slow_r50 excluded: stock PyTorch; the same step started from backbone features through the Conv3d front-end is reported as with_frontend)")
 
 
 def read_peaks():

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshgvqa.so")
+LIB_PATH = os.environ.get("SHG_LIB_PATH") or os.path.join(_HERE, "libshgvqa.so")      # override: A/B builds
 
 c_int, c_i64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 

@@ -17,7 +17,7 @@ namespace shg {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kEpiSub = 2;          // epilogue warps per TMEM lane quarter
+constexpr int kEpiSub = 4;          // epilogue warps per TMEM lane quarter
 constexpr int kGemmThreads = 64 + kEpiSub * 128;   // TMA warp + MMA warp + 4 * kEpiSub epilogue warps
 constexpr int kMaxStages = 8;
 

@@ -84,7 +84,9 @@ if __name__ == "__main__":
                                     (1280, 3072, 768, "NN", None), (12576, 768, 2304, "NT", None)]:
             case(m, n, k, mode, ex)
             case(m, n, k, mode, dict(ex or {}, block_n=4096))
-    if sel == "tune":
+    if sel in ("tune", "tune2"):
+        shapes2 = [(5632, 768, 768, "NN"), (5632, 1536, 768, "NN"), (5632, 2048, 768, "NN"), (5632, 768, 2048, "NN"),
+                   (5632, 768, 768, "NT"), (5632, 768, 1536, "NT"), (5632, 2048, 768, "NT"), (5632, 768, 2048, "NT")]
         shapes = [(12576, 768, 768, "NN"), (12576, 768, 768, "NT"), (12576, 768, 3072, "NN"), (12576, 768, 3072, "NT"),
                   (12576, 768, 2304, "NT"), (12576, 3072, 768, "NT"), (12576, 768, 15360, "NT"),
                   (4096, 768, 768, "NN"), (4096, 768, 768, "NT"), (4096, 1536, 768, "NN"), (4096, 2048, 768, "NN"),
@@ -97,6 +99,8 @@ if __name__ == "__main__":
                   (768, 3072, 1280, "TT"), (3072, 768, 1280, "TT"), (2304, 768, 1280, "TT"), (768, 768, 1280, "TT"),
                   (768, 3072, 5664, "TT"), (2304, 768, 5664, "TT"), (3072, 768, 12576, "TT"), (768, 3072, 12576, "TT"),
                   (2304, 768, 12576, "TT"), (768, 768, 12576, "TT"), (1536, 768, 12576, "TT"), (1536, 768, 4096, "TT")]
+        if sel == "tune2":      # stacked decoder rows (both decoders in lock-step)
+            shapes = shapes2
         import io, contextlib, re
         cub = float('nan')
         for (m, n, k, mode) in shapes:
