@@ -112,6 +112,7 @@ class HotPathTrainer:
         self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else None
         self.graph = None
         self.copy_stream, self._staged = None, False
+        self._loss_slots = None
         # training-mode dropout (the reference trains with model.train(): hidden/attention 0.1, decoders 0.15).
         # Masks are counter-based functions of (step seed, call site, element); the seed lives on the device and
         # is advanced at the start of every step (inside the captured graph too), and differs per rank.
@@ -333,7 +334,19 @@ class HotPathTrainer:
             self.stage_ready.record()
         self._staged = True
 
-    def train_step_host(self, host_inp, host_batch, next_inp=None, next_batch=None):
+    def drain_losses(self):
+        """Loss dict of the most recent lagged step whose result has not been handed out yet (waits for its D2H
+        copy), or None."""
+        if self._loss_slots is None:
+            return None
+        j = self._loss_idx ^ 1
+        if not self._loss_pending[j]:
+            return None
+        self._loss_events[j].synchronize()
+        self._loss_pending[j] = False
+        return self.losses_from_scalars(self._loss_slots[j])
+
+    def train_step_host(self, host_inp, host_batch, next_inp=None, next_batch=None, lagged=False):
         """The call a user of the path makes with HOST (pinned) buffers: H2D copies of the step's inputs, the
         step, and a D2H read of the loss sums.  Returns the loss dict.  next_inp / next_batch (the following
         step's host buffers, as a data loader has them) are prefetched to the device while this step computes."""
@@ -352,7 +365,23 @@ class HotPathTrainer:
                 _, scal = self.train_step_graph(host_inp, host_batch)
             if next_inp is not None:
                 self.prefetch_host(next_inp, next_batch)
-            return self.losses_from_scalars(scal)
+            if not lagged:
+                return self.losses_from_scalars(scal)
+            # lagged read: this step's loss sums start their D2H copy into a pinned slot now and are handed out by the
+            # NEXT call (or drain_losses), so the host enqueues step i+1 while step i still runs — every step's
+            # result is still read back, just not synchronously
+            if self._loss_slots is None:
+                self._loss_slots = [torch.zeros(16, dtype=torch.float32).pin_memory() for _ in range(2)]
+                self._loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+                self._loss_pending = [False, False]
+                self._loss_idx = 0
+            i = self._loss_idx
+            prev = self.drain_losses()
+            self._loss_slots[i].copy_(scal, non_blocking=True)
+            self._loss_events[i].record()
+            self._loss_pending[i] = True
+            self._loss_idx = i ^ 1
+            return prev
         inp = {k: v.to(self.device, non_blocking=True) for k, v in host_inp.items()}
         batch = {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
         _, scal = self.train_step(inp, batch)

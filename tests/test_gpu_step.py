@@ -51,7 +51,7 @@ def test_graph_and_host_steps_match_eager():
         if w_ref is None:
             w_ref = ref.store.master.clone()
 
-    for mode in ("graph", "host", "host_prefetch"):
+    for mode in ("graph", "host", "host_prefetch", "host_lagged"):
         tr = _trainer(dev)
         tr.capture(to_dev(a[0]), to_dev(a[1]), warmup=1)
         tr.init_weights(seed=11)                      # capture ran real steps: restore weights and optimiser state
@@ -66,9 +66,19 @@ def test_graph_and_host_steps_match_eager():
                 got.append(tr.losses_from_scalars(scal))
             elif mode == "host":
                 got.append(tr.train_step_host(h_inp, h_batch))
-            else:
+            elif mode == "host_prefetch":
                 nxt = seq[i + 1] if i + 1 < len(seq) else (None, None)
                 got.append(tr.train_step_host(h_inp, h_batch, next_inp=nxt[0], next_batch=nxt[1]))
+            else:
+                # prefetch + lagged loss read: call i hands out the loss of call i-1
+                nxt = seq[i + 1] if i + 1 < len(seq) else (None, None)
+                prev = tr.train_step_host(h_inp, h_batch, next_inp=nxt[0], next_batch=nxt[1], lagged=True)
+                assert (prev is None) == (i == 0)
+                if prev is not None:
+                    got.append(prev)
+                if i + 1 == len(seq):
+                    got.append(tr.drain_losses())
+                    assert tr.drain_losses() is None
             if w1 is None:
                 torch.cuda.synchronize()
                 w1 = tr.store.master.clone()
