@@ -119,6 +119,11 @@ typedef struct {
     const void* b2;
     const float* bias2;
     int split_m;
+    /* grouped split-K accumulation (the same two layers' weight gradients in one launch): with SHG_GEMM_ACCUMULATE and
+     * splits = 0, K rows [0, k_split) accumulate into d and rows [k_split, k) into d2 (same shape / ld as d).
+     * d2 NULL = ordinary accumulation.  k_split % 64 == 0. */
+    void* d2;
+    int k_split;
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
 /* Debug aid: CTA 0 of subsequent shg_gemm launches writes 7 %globaltimer phase stamps to buf (8 x u64 device

@@ -40,6 +40,8 @@ struct GemmParams {
     unsigned long long* dbg;   // optional phase timestamps of CTA 0 (tools/gemm_phases.py), normally null
     int split_m;               // grouped product: rows >= split_m use the second B operand / bias (INT_MAX: one group)
     const float* bias2;
+    int kb_group;              // grouped split-K accumulation: splits starting at k-block >= kb_group add into d2
+    void* d2;
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -72,11 +74,12 @@ constexpr int kStageOutBytes = 2 * 16384;   // two [128 x 64] bf16 staging block
 template <int NSUB, class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* sb, uint32_t t_row, int row, bool row_ok,
                                               int m0, int n0, int sub, int etid, uint8_t* stg, const CUtensorMap* tm_d,
-                                              const CUtensorMap* tm_pre, uint32_t& nblk, WaitFn wait_accumulator) {
+                                              const CUtensorMap* tm_pre, uint32_t& nblk, void* dbase,
+                                              WaitFn wait_accumulator) {
     constexpr int COLS = 64 / NSUB;          // columns per thread and 64-column block (32 or 16)
     constexpr int NV = COLS / 8;             // 16-byte bf16 vectors per thread and block
-    const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
-    const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
+    const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0);
+    const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0);
     // the one bf16 side operand of the tile: the saved activation input/output (backward through an activation) or
     // the residual — never both on this path (checked on the host)
     const __nv_bfloat16* side_ptr = p.mul_aux ? p.mul_aux : p.residual;
@@ -230,7 +233,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
             staged_store(acc, tm_d, n0 + blk0, active);
         } else if (do_row) {
             if (p.accumulate) {
-                float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
+                float* o = reinterpret_cast<float*>(dbase) + (size_t)row * p.ldd + col0;
                 if (full_chunk && vec_ok_f32) {
 #pragma unroll
                     for (int i = 0; i < COLS; i += 4)
@@ -242,7 +245,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                         if (col0 + i < p.n) atomicAdd(o + i, acc[i]);
                 }
             } else if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + col0;
+                float* o = reinterpret_cast<float*>(dbase) + (size_t)row * p.ldd + col0;
                 if (full_chunk && vec_ok_f32) {
 #pragma unroll
                     for (int i = 0; i < COLS; i += 4)
@@ -253,7 +256,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                         if (col0 + i < p.n) o[i] = acc[i];
                 }
             } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)row * p.ldd + col0;
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dbase) + (size_t)row * p.ldd + col0;
                 if (full_chunk && vec_ok_bf16) {
 #pragma unroll
                     for (int i = 0; i < COLS; i += 8) {
@@ -411,7 +414,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (etid < 256) sb[etid] = (bias && n0 + etid < p.n) ? __ldg(bias + n0 + etid) : 0.f;
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk,
+            void* dbase = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group ? p.d2 : p.d;
+            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk, dbase,
                           [&] { mbar_wait(tmem_full + as, aphase); if (etid == 0 && tile == (int)blockIdx.x) SHG_STAMP(3); });
             if (etid == 0 && tile == (int)blockIdx.x) SHG_STAMP(4);
             tc_fence_before();
@@ -580,7 +584,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             if (etid < 256) sb[etid] = (bias && n0 + etid < p.n) ? __ldg(bias + n0 + etid) : 0.f;
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk,
+            void* dbase = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group ? p.d2 : p.d;
+            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk, dbase,
                           [&] { mbar_wait(tmem_full + as, aphase); });
             tc_fence_before();
             __syncwarp();
@@ -688,6 +693,10 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     SHG_REQUIRE(p.drop.p >= 0.f && p.drop.p < 1.f, SHG_EINVAL, "shg_gemm: dropout_p=%f", (double)p.drop.p);
     SHG_REQUIRE(p.drop.p == 0.f || (a->n % 2 == 0 && !accumulate), SHG_ESHAPE, "shg_gemm: dropout needs even N and a plain store");
     p.out_f32 = (a->flags & SHG_GEMM_OUT_F32) || accumulate, p.accumulate = accumulate;
+    const bool kgrouped = a->d2 != nullptr;     // two K-ranges accumulating into two outputs (stacked-row weight gradients)
+    SHG_REQUIRE(!kgrouped || (accumulate && a->k_split > 0 && a->k_split < a->k && a->k_split % BK == 0 && a->splits <= 0),
+                SHG_ESHAPE, "shg_gemm: d2 needs SHG_GEMM_ACCUMULATE, 0 < k_split < k, k_split %% 64 == 0 and automatic splits");
+    p.kb_group = kgrouped ? a->k_split / BK : 0x7fffffff, p.d2 = a->d2;
     const bool grouped = a->b2 != nullptr;
     p.split_m = grouped ? a->split_m : 0x7fffffff, p.bias2 = a->bias2;
     SHG_REQUIRE(!grouped || (a->split_m > 0 && a->split_m < a->m && a->split_m % BM == 0 && !a->a_mn_major && !accumulate),
@@ -713,6 +722,12 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     p.kb_total = (a->k + BK - 1) / BK;
     p.splits = splits > p.kb_total ? p.kb_total : splits;
     p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+    if (kgrouped) {
+        // a split never straddles the two K-ranges: the largest divisor of the boundary not above the chosen depth
+        int per = p.kb_per_split < p.kb_group ? p.kb_per_split : p.kb_group;
+        while (p.kb_group % per) --per;
+        p.kb_per_split = per;
+    }
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
     const int stage_bytes = BM * BK * 2 + (pair ? bn / 2 : bn) * BK * 2;
     const int bar_bytes = 1024 + 2048;   // barriers + TMEM slot + bias staging

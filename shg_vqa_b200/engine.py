@@ -463,8 +463,19 @@ class Engine:
         return ops.gemm(dy, A.w, b_t=True, b2=Bm.w, split_m=split, **kw)
 
     def _wgrad2(self, A, Bm, dy, x, split, bias=True):
-        self._wgrad(A, dy[:split], x[:split], bias=bias)
-        self._wgrad(Bm, dy[split:], x[split:], bias=bias)
+        """Weight (and bias) gradients of the same layer of both decoders: one split-K launch whose K rows below the
+        split accumulate into the relation decoder's gradient and the rest into the action decoder's."""
+        if split % 64 or not self.use_streams:
+            self._wgrad(A, dy[:split], x[:split], bias=bias)
+            self._wgrad(Bm, dy[split:], x[split:], bias=bias)
+            return
+        self.sw.wait_event(torch.cuda.current_stream().record_event())
+        self._keep.append((dy, x))
+        with torch.cuda.stream(self.sw):
+            ops.gemm(dy, x, a_t=True, b_t=True, out=A.gw, accumulate=True, d2=Bm.gw, k_split=split)
+            if bias:
+                ops.colsum_accum(dy[:split], A.gb)
+                ops.colsum_accum(dy[split:], Bm.gb)
 
     def _ln2_fwd(self, x, NA, NB, split, eps, addend=None, save=False):
         return ops.layernorm_fwd(x, NA.g, NA.b, eps, addend=addend, save_stats=save, group=(split, NB.g, NB.b))

@@ -25,7 +25,7 @@ def _ld(t):
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, preact=None, mul_aux=None,
          mul_mode=None, mul_scale=1.0, drop=None, out=None, out_f32=False, accumulate=False, splits=0, block_n=0,
-         b2=None, bias2=None, split_m=0):
+         b2=None, bias2=None, split_m=0, d2=None, k_split=0):
     # drop = (p, salt, seed_tensor) enables training-mode dropout on the output (before the residual add)
     """D = epilogue(A . B^T).  a: [M,K] (or stored [K,M] with a_t), b: [N,K] (or stored [K,N] with b_t); bf16."""
     require_device(a)
@@ -66,6 +66,11 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
         assert b2.dtype == BF16 and b2.shape == b.shape and _ld(b2) == _ld(b) and 0 < split_m < m
         assert (bias2 is None) == (bias is None)
         args.b2, args.bias2, args.split_m = ptr(b2), ptr(bias2), split_m
+    if d2 is not None:
+        # grouped split-K accumulation: K rows >= k_split add into d2 (second layer's weight gradient)
+        assert accumulate and d2.dtype == torch.float32 and d2.shape == out.shape and _ld(d2) == _ld(out)
+        assert 0 < k_split < k and splits == 0
+        args.d2, args.k_split = ptr(d2), k_split
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
     args.splits, args.block_n = splits, (block_n | _PAIR_FLAG if block_n == 0 and _PAIR_FLAG else block_n)
     call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k, "%dx%dx%d %s%s%s" % (m, n, k, "T" if a_t else "N", "T" if b_t else "N", " acc" if accumulate else "")))

@@ -459,3 +459,19 @@ def test_grouped_layernorm_fwd_bwd(ops):
     assert torch.equal(dx, torch.cat([dxa, dxb]))
     for a, b in ((dg1, rg1), (db1, rb1), (dx1, rx1), (dg2, rg2), (db2, rb2), (dx2, rx2)):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("rows,split,m,n", [(5632, 4096, 768, 768), (5632, 4096, 2048, 768), (704, 512, 768, 2048),
+                                            (448, 256, 1536, 768)])
+def test_grouped_splitk_wgrad_two_outputs(ops, rows, split, m, n):
+    """dW1 += dy[:split]^T x[:split], dW2 += dy[split:]^T x[split:] in ONE split-K launch == two launches."""
+    g = torch.Generator().manual_seed(rows + m)
+    dy = torch.randn(rows, m, generator=g).to(torch.bfloat16).to(_dev())
+    x = torch.randn(rows, n, generator=g).to(torch.bfloat16).to(_dev())
+    d1 = torch.full((m, n), 0.25, device=_dev())
+    d2 = torch.full((m, n), -0.5, device=_dev())
+    ops.gemm(dy, x, a_t=True, b_t=True, out=d1, accumulate=True, d2=d2, k_split=split)
+    r1 = 0.25 + dy[:split].float().t() @ x[:split].float()
+    r2 = -0.5 + dy[split:].float().t() @ x[split:].float()
+    for got, ref in ((d1, r1), (d2, r2)):
+        assert (got - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-3
