@@ -126,6 +126,9 @@ typedef struct {
     int k_split;
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
+/* Experimental cluster-of-four tiles with TMA multicast of the shared operand (default off: measured slower on
+ * the K = 768 projections because only 132 of 148 SMs hold clusters of four; also SHG_GEMM_QUAD=1). */
+int shg_set_gemm_quad(int on);
 /* Debug aid: CTA 0 of subsequent shg_gemm launches writes 7 %globaltimer phase stamps to buf (8 x u64 device
  * memory); NULL = off. */
 int shg_debug_gemm_stamps(void* buf);

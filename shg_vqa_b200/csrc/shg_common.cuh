@@ -237,6 +237,24 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same with a multicast mask: the box lands at the same offset in every CTA of `mask` and completes bytes on the
+// barrier of each destination's pair leader
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                    uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// commit of a pair's MMAs arriving on the barrier at this offset in every CTA of `mask` (cluster ranks)
+__device__ __forceinline__ void tc_commit_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
 // commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
     asm volatile(

@@ -389,9 +389,21 @@ def test_attention_bwd_all_path_shapes(ops, lq, lk, mode):
         assert (got.float() - want).abs().max().item() <= 3e-2 * want.abs().max().item() + 1e-6
 
 
+@pytest.mark.parametrize("quad", [0, 1])
 @pytest.mark.parametrize("bn", [128, 256])
 @pytest.mark.parametrize("m,n,k", [(12576, 768, 768), (1000, 3072, 768), (4096, 457, 1536), (512, 768, 3072)])
-def test_gemm_cta_pair_tiles(ops, m, n, k, bn):
+def test_gemm_cta_pair_tiles(ops, m, n, k, bn, quad):
+    from shg_vqa_b200 import _lib
+    if quad and bn != 256:
+        pytest.skip("cluster-of-four tiles are 256 wide")
+    _lib.check(_lib.lib().shg_set_gemm_quad(quad))
+    try:
+        _gemm_cta_pair_tiles(ops, m, n, k, bn)
+    finally:
+        _lib.check(_lib.lib().shg_set_gemm_quad(0))
+
+
+def _gemm_cta_pair_tiles(ops, m, n, k, bn):
     """cta_group::2 path forced (block_n | 1024): forward with every epilogue input, dgrad and split-K wgrad layouts."""
     g = torch.Generator().manual_seed(m + n + k + bn)
     x = torch.randn(m, k, generator=g).to(torch.bfloat16).to(_dev())
