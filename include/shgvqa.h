@@ -29,11 +29,6 @@ const char* shg_last_error(void);
 int shg_version(void);
 /* Refuses anything that is not compute capability 10.x (there is no fallback path). */
 int shg_device_check(int device);
-/* Programmatic dependent launch between the library's kernels (default off — measured 1 % slower on the captured
- * step; SHG_PDL=1 in the environment also switches it on): the next kernel's prologue overlaps the tail of the
- * previous one on the same stream. */
-int shg_set_pdl(int on);
-
 /* ------------------------------------------------------------------ Hungarian matching
  * Replaces the CPU loop `[linear_sum_assignment(c[i]) for i, c in enumerate(C.split(sizes, -1))]`
  * (lxrt/matcher.py:76-80; scipy's rectangular_lsap, tie-break included).  One CTA per frame.
@@ -42,7 +37,8 @@ int shg_set_pdl(int on);
  *           [col_off[f], col_off[f+1]) — the layout of `C.view(bs*clip_len, q, -1)` (matcher.py:76).
  * rows/cols int32 [n_frames, q_f]: matched (query, target) pairs, query ascending, -1 padded.
  * n_match   int32 [n_frames]; status int32 [n_frames]: 0 ok, -1 infeasible, -2 NaN/-inf entry
- *           (scipy raises ValueError for both).
+ *           (scipy raises ValueError for both), -3 more than 32 targets in the frame, -4 (fused matcher only) a label
+ *           outside [0, n_cls) — an IndexError in the reference (lxrt/matcher.py:73).
  * q_f <= 32 and every frame's target count <= 32.
  */
 int shg_lsap_batched(const float* cost, int n_frames, int q_f, int ld, const int32_t* col_off,
@@ -63,10 +59,15 @@ int shg_match_from_logits(const void* logits, int logits_bf16, int n_frames, int
  * F.cross_entropy(weight=empty_weight) = sum w_t nll / sum w_t with w[0] = eos_coef, else 1) plus the
  * counts behind class_error (tasks/agqaHGQA.py:228).  fwd ADDS into out[0]=sum w*nll, out[1]=sum w,
  * out[2]=#matched, out[3]=#matched whose argmax is the label (caller zeroes `out`); bwd writes
- * dlogits = grad_scale * w_t (softmax - onehot) / out[1] as bf16 or fp32. */
+ * dlogits = grad_scale * w_t (softmax - onehot) / out[1] as bf16 or fp32.
+ * Error reporting without a synchronisation: `status` (int32 [n_frames], as written by shg_match_from_logits; may be
+ * NULL) and target classes outside [0, n_cls) are COUNTED into *err_out (fp32 device scalar, may be NULL): the
+ * reference raises for those inputs (scipy ValueError on NaN/-inf costs, IndexError on a label >= n_cls); the host
+ * turns a non-zero count into an exception when it reads the loss sums.  Such rows add nothing to the loss or the
+ * gradient. */
 int shg_set_loss_fwd(const void* logits, int logits_bf16, int n_rows, int n_cls, int ld_logits,
                      const int32_t* target_classes, const float* row_lse, const int32_t* row_argmax, float eos_coef,
-                     float* out, void* stream);
+                     float* out, const int32_t* status, int n_frames, float* err_out, void* stream);
 int shg_set_loss_bwd(const void* logits, int logits_bf16, int n_rows, int n_cls, int ld_logits,
                      const int32_t* target_classes, const float* row_lse, float eos_coef, const float* out,
                      float grad_scale, void* dlogits, int dlogits_bf16, int ld_dlogits, void* stream);
@@ -126,9 +127,6 @@ typedef struct {
     int k_split;
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
-/* Experimental cluster-of-four tiles with TMA multicast of the shared operand (default off: measured slower on
- * the K = 768 projections because only 132 of 148 SMs hold clusters of four; also SHG_GEMM_QUAD=1). */
-int shg_set_gemm_quad(int on);
 /* Debug aid: CTA 0 of subsequent shg_gemm launches writes 7 %globaltimer phase stamps to buf (8 x u64 device
  * memory); NULL = off. */
 int shg_debug_gemm_stamps(void* buf);
@@ -162,9 +160,6 @@ typedef struct {
                                  k/32 = key k kept), so that the backward reads 1 bit instead of re-hashing per element */
 } shg_attn_args;
 int shg_attn_fwd(const shg_attn_args* args, void* stream);
-/* Selects the experimental warp-specialised, pipelined forward for mask_mode 0 (default off: measured slower; also
- * SHG_ATTN_PIPE=1 in the environment).  Same results within the kernel's tolerance. */
-int shg_set_attn_pipeline(int on);
 
 /* Backward of the above (autograd of lxrt/modeling_capsbert.py:394-417 / nn.MultiheadAttention).  Recomputes
  * the probabilities from q, k and the saved lse; d_o is the gradient of o; writes dq/dk/dv (bf16, same head

@@ -64,14 +64,11 @@ class Conv3dArgs(ctypes.Structure):
 SIGNATURES = {
     "shg_version": [],
     "shg_device_check": [c_int],
-    "shg_set_pdl": [c_int],
-    "shg_set_attn_pipeline": [c_int],
-    "shg_set_gemm_quad": [c_int],
     "shg_set_attn_bwd_merge": [c_int],
     "shg_lsap_batched": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "shg_match_from_logits": [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_vp],
-    "shg_set_loss_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp],
+    "shg_set_loss_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_int, c_vp, c_vp],
     "shg_set_loss_bwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_int, c_int, c_vp],
     "shg_gemm": [ctypes.POINTER(GemmArgs), c_vp],
     "shg_debug_gemm_stamps": [c_vp],
@@ -153,7 +150,7 @@ def check(rc):
 
 
 # kernels launched per entry point (for the bench's gpu_launches count)
-LAUNCHES = {"shg_attn_bwd": 2, "shg_version": 0, "shg_device_check": 0, "shg_set_pdl": 0, "shg_set_attn_pipeline": 0, "shg_set_attn_bwd_merge": 0, "shg_set_gemm_quad": 0}
+LAUNCHES = {"shg_attn_bwd": 2, "shg_version": 0, "shg_device_check": 0, "shg_set_attn_bwd_merge": 0}
 launch_count = 0
 profiler = None     # set to a Profiler to time every call with CUDA events on the launching stream
 

@@ -79,8 +79,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    pdl_launch_dependents();     // after the TMEM allocation (see shg_common.cuh)
-    pdl_wait();                  // nothing above reads global memory
 
     if (tid == 0) {
         mbar_expect_tx(bar_qk, 16384 + p.n_kbox * 8192);
@@ -259,288 +257,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem, p.tmem_cols);
-    }
-}
-
-// =====================================================================================================
-// Pipelined forward (mask_mode 0): one persistent CTA per (batch, head, group of query tiles), warp-specialised.
-//
-//   warp 0      : TMA producer — K and V of the head once (resident for all tiles of the CTA), Q per tile (2 buffers)
-//   warp 1      : MMA issuer  — per tile: S chunks (128 keys each) for the max pass, the same chunks again for the
-//                 exponential pass (recomputing QK^T costs the tensor core ~1 % of its time; holding the whole S row
-//                 costs 416 TMEM columns and forces every phase of a tile to run one after the other), and O += P.V
-//                 one chunk behind.  S chunks alternate between two 128-column TMEM buffers, O between two 64-column
-//                 ones, so the products of the next chunk / next tile run under the softmax of the current one.
-//   warps 4..19 : softmax — thread = (row, 32-column group of the chunk): pass A takes the row maximum, pass B
-//                 exponentiates, applies dropout, writes bf16 P chunks into two swizzled staging tiles; epilogue
-//                 normalises O from TMEM and stores it.
-// Hand-offs are mbarriers: s_full/s_empty (MMA <-> softmax, per S buffer), p_full/p_empty (softmax <-> MMA, per P
-// tile), o_full/o_empty, q_full/q_empty, kv_full.
-//
-// STATUS: correct (the attention parity tests run it), but SLOWER than the unpipelined kernel above and therefore not
-// the default: 393 x 393 at B = 32 takes 141 us (184 us with dropout) against 119 us (150 us).  What the experiment
-// showed: with head dimension 64 the forward is bound by the exponential pass itself — 53 K exponentials per
-// 128 x 416 tile are 2.1 us of MUFU time and ~20 K warp instructions with the counter-based dropout mask, against
-// 0.8 us of tensor time — and that pass runs at ~33 % issue utilisation in BOTH kernels (tcgen05.ld -> FFMA -> MUFU ->
-// pack -> st.shared chains, four warps per scheduler); hiding the load / MMA phases behind it gains less than the
-// per-chunk hand-offs (eight mbarrier round trips per tile, the max pass now paced by them) cost.  The next step
-// is inside the exponential pass (polynomial exp2 on the FMA pipe for part of the elements, 8-bit keep masks from one
-// hash per 4 elements, two row tiles per softmax warp for ILP), not around it.
-// =====================================================================================================
-constexpr int kPipeThreads = 640;
-constexpr int kPipeSoftmaxThreads = 512;
-
-struct PipeBars {
-    uint64_t kv_full, q_full[2], q_empty[2], s_full[3], s_empty[3], p_full[2], p_empty[2], o_full[2], o_empty[2];
-};
-
-template <bool DROP>
-__global__ void __launch_bounds__(kPipeThreads, 1)
-attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                     const __grid_constant__ CUtensorMap tma_v, const AttnParams p, const int n_qt, const int n_groups) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                              // 2 x 16 KB
-    uint8_t* sP = smem + 32768;                      // 2 x 32 KB: [128 rows x 128 keys] bf16, two swizzled blocks each
-    uint8_t* sK = smem + 98304;                      // n_kbox x 8 KB
-    uint8_t* sV = sK + p.n_kbox * 8192;
-    float* s_red = reinterpret_cast<float*>(sV + p.n_kbox * 8192);   // [2 tile parities][2 (max, sum)][4][128]
-    PipeBars* bars = reinterpret_cast<PipeBars*>(s_red + 2048);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int t_begin = grp, t_end = grp == n_groups - 1 ? n_qt : grp + 1;   // the last group takes the tail tile too
-    const int n_kc = (p.lk + 127) >> 7;
-
-    if (tid == 0) {
-        mbar_init(&bars->kv_full, 1);
-        for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1), mbar_init(&bars->s_empty[i], 16);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->q_full[i], 1), mbar_init(&bars->q_empty[i], 1);
-            mbar_init(&bars->p_full[i], 16), mbar_init(&bars->p_empty[i], 1);
-            mbar_init(&bars->o_full[i], 1), mbar_init(&bars->o_empty[i], 16);
-        }
-        fence_barrier_init();
-        tma_prefetch_desc(&tma_q);
-        tma_prefetch_desc(&tma_k);
-        tma_prefetch_desc(&tma_v);
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
-    // TMEM columns: S ring at 0 / 128 / 256, O buffers at 384 / 448
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(&bars->kv_full, 2 * p.n_kbox * 8192);
-            for (int i = 0; i < p.n_kbox; ++i) tma_load_3d(sK + i * 8192, &tma_k, &bars->kv_full, h * kHeadDim, i * 64, b);
-            for (int i = 0; i < p.n_kbox; ++i) tma_load_3d(sV + i * 8192, &tma_v, &bars->kv_full, h * kHeadDim, i * 64, b);
-            int it = 0;
-            for (int t = t_begin; t < t_end; ++t, ++it) {
-                const int qb = it & 1;
-                mbar_wait(&bars->q_empty[qb], ((it >> 1) & 1) ^ 1);
-                mbar_expect_tx(&bars->q_full[qb], 16384);
-                tma_load_3d(sQ + qb * 16384, &tma_q, &bars->q_full[qb], h * kHeadDim, t * 128, b);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
-            const uint32_t idesc_pv = make_idesc_bf16(128, kHeadDim, 0, 1);
-            int s_it = 0, p_it = 0, it = 0;
-            mbar_wait(&bars->kv_full, 0);
-            for (int t = t_begin; t < t_end; ++t, ++it) {
-                const int qb = it & 1, ob = it & 1;
-                const uint32_t aq = smem_u32(sQ + qb * 16384);
-                mbar_wait(&bars->q_full[qb], (it >> 1) & 1);
-                auto issue_pv = [&](int c) {
-                    const int pb = p_it & 1;
-                    if (c == 0) {
-                        mbar_wait(&bars->o_empty[ob], ((it >> 1) & 1) ^ 1);
-                    }
-                    mbar_wait(&bars->p_full[pb], (p_it >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t ap = smem_u32(sP + pb * 32768);
-                    const int n16 = min(128, p.lk16 - c * 128);
-                    for (int k = 0; k < n16; k += 16)
-                        umma_bf16(tmem + 384 + ob * 64, make_smem_desc(ap + (k >> 6) * 16384 + ((k & 63) >> 4) * 32, 16, 1024),
-                                  make_smem_desc(av + (c * 128 + k) * 128, 8192, 1024), idesc_pv, (c > 0 || k > 0) ? 1u : 0u);
-                    tc_commit(&bars->p_empty[pb]);
-                    ++p_it;
-                };
-                for (int pass = 0; pass < 2; ++pass) {
-                    for (int c = 0; c < n_kc; ++c) {
-                        const int sb = s_it % 3;
-                        mbar_wait(&bars->s_empty[sb], ((s_it / 3) & 1) ^ 1);
-                        tc_fence_after();
-                        const int n16 = min(128, p.lk16 - c * 128);
-                        const uint32_t idesc = make_idesc_bf16(128, n16, 0, 0);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_bf16(tmem + sb * 128, make_smem_desc(aq + ks * 32, 16, 1024),
-                                      make_smem_desc(ak + c * 16384 + ks * 32, 16, 1024), idesc, ks > 0);
-                        tc_commit(&bars->s_full[sb]);
-                        ++s_it;
-                        if (pass == 1 && c >= 1) issue_pv(c - 1);
-                    }
-                }
-                tc_commit(&bars->q_empty[qb]);          // every product that reads this Q buffer has been issued
-                issue_pv(n_kc - 1);
-                tc_commit(&bars->o_full[ob]);
-            }
-        }
-    } else if (warp >= 4) {
-        const int quarter = warp & 3, sub = (warp - 4) >> 2;
-        const int row = quarter * 32 + lane;
-        const uint32_t t_lane = tmem + (uint32_t(quarter * 32) << 16);
-        const float c1 = p.scale * 1.4426950408889634f;
-        uint32_t dkey = 0, dth = 0;
-        if (DROP) dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
-        int s_it = 0, p_it = 0, it = 0;
-        for (int t = t_begin; t < t_end; ++t, ++it) {
-            const int q0 = t * 128, q = q0 + row;
-            const bool rows_live = q0 + quarter * 32 < p.lq;     // warp-uniform: dead warps only keep the hand-offs going
-            float* red_max = s_red + (it & 1) * 1024;
-            float* red_sum = red_max + 512;
-            // ---------------------------------------------------------------- pass A: row maximum
-            float mx = -INFINITY;
-            for (int c = 0; c < n_kc; ++c, ++s_it) {
-                const int sb = s_it % 3;
-                if (lane == 0) mbar_wait(&bars->s_full[sb], (s_it / 3) & 1);
-                __syncwarp();
-                tc_fence_after();
-                const int col = c * 128 + sub * 32;
-                if (rows_live && col < p.lk) {
-                    uint32_t raw[32];
-                    tmem_ld32(t_lane + sb * 128 + sub * 32, raw);
-                    tmem_ld_wait();
-                    if (col + 32 <= p.lk) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, col + i < p.lk ? __uint_as_float(raw[i]) : -INFINITY);
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
-            }
-            red_max[sub * 128 + row] = mx * c1;
-            asm volatile("bar.sync 1, %0;" ::"n"(kPipeSoftmaxThreads) : "memory");
-            mx = fmaxf(fmaxf(red_max[row], red_max[128 + row]), fmaxf(red_max[256 + row], red_max[384 + row]));
-            if (mx == -INFINITY) mx = 0.f;
-            // ---------------------------------------------------------------- pass B: exponentials -> P chunks
-            float sum = 0.f;
-            const uint32_t row_pair0 = DROP ? attn_row_pair0(b, p.heads, h, p.lq, q, p.lk) : 0u;
-            for (int c = 0; c < n_kc; ++c, ++s_it, ++p_it) {
-                const int sb = s_it % 3, pb = p_it & 1;
-                if (lane == 0) mbar_wait(&bars->s_full[sb], (s_it / 3) & 1);
-                __syncwarp();
-                tc_fence_after();
-                const int col = c * 128 + sub * 32;
-                const bool active = rows_live && col < p.lk16;      // columns the P.V product of this chunk reads
-                uint32_t raw[32];
-                if (active) {
-                    tmem_ld32(t_lane + sb * 128 + sub * 32, raw);
-                    tmem_ld_wait();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
-                if (lane == 0) mbar_wait(&bars->p_empty[pb], ((p_it >> 1) & 1) ^ 1);
-                __syncwarp();
-                if (active) {
-                    float pv[32];
-                    if (col + 32 <= p.lk) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(raw[i]), c1, -mx));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            pv[i] = col + i < p.lk ? ex2_approx(fmaf(__uint_as_float(raw[i]), c1, -mx)) : 0.f;
-                    }
-                    uint8_t* blk = sP + pb * 32768 + (sub >> 1) * 16384 + row * 128;
-                    const int j0 = (sub & 1) ? 4 : 0;
-                    uint32_t keep_bits = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        u.x = pack_bf16x2(pv[8 * j], pv[8 * j + 1]), u.y = pack_bf16x2(pv[8 * j + 2], pv[8 * j + 3]);
-                        u.z = pack_bf16x2(pv[8 * j + 4], pv[8 * j + 5]), u.w = pack_bf16x2(pv[8 * j + 6], pv[8 * j + 7]);
-                        // normalise by the sum of the ROUNDED probabilities (see attn_fwd_kernel)
-                        sum += (__uint_as_float(u.x << 16) + __uint_as_float(u.x & 0xffff0000u)) +
-                               (__uint_as_float(u.y << 16) + __uint_as_float(u.y & 0xffff0000u)) +
-                               (__uint_as_float(u.z << 16) + __uint_as_float(u.z & 0xffff0000u)) +
-                               (__uint_as_float(u.w << 16) + __uint_as_float(u.w & 0xffff0000u));
-                        if (DROP) {
-                            const uint32_t pbase = row_pair0 + ((col + 8 * j) >> 1);
-                            const uint32_t k0 = drop_pair(dkey, pbase, dth), k1 = drop_pair(dkey, pbase + 1, dth);
-                            const uint32_t k2 = drop_pair(dkey, pbase + 2, dth), k3 = drop_pair(dkey, pbase + 3, dth);
-                            u.x &= (k0 & 1u) * 0xffffu + (k0 >> 1) * 0xffff0000u, u.y &= (k1 & 1u) * 0xffffu + (k1 >> 1) * 0xffff0000u;
-                            u.z &= (k2 & 1u) * 0xffffu + (k2 >> 1) * 0xffff0000u, u.w &= (k3 & 1u) * 0xffffu + (k3 >> 1) * 0xffff0000u;
-                            keep_bits |= (k0 | (k1 << 2) | (k2 << 4) | (k3 << 6)) << (8 * j);
-                        }
-                        *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ (row & 7)) << 4)) = u;
-                    }
-                    if (DROP && p.drop_bits && q < p.lq && col < p.lk32)
-                        p.drop_bits[(((size_t)b * p.heads + h) * p.lq + q) * (p.lk32 >> 5) + (col >> 5)] = keep_bits;
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->p_full[pb]);
-            }
-            red_sum[sub * 128 + row] = sum;
-            asm volatile("bar.sync 1, %0;" ::"n"(kPipeSoftmaxThreads) : "memory");
-            sum = (red_sum[row] + red_sum[128 + row]) + (red_sum[256 + row] + red_sum[384 + row]);
-            // ---------------------------------------------------------------- epilogue: O / sum
-            const int ob = it & 1;
-            if (lane == 0) mbar_wait(&bars->o_full[ob], (it >> 1) & 1);
-            __syncwarp();
-            tc_fence_after();
-            uint32_t raw[16];
-            if (rows_live) {
-                tmem_ld16(t_lane + 384 + ob * 64 + sub * 16, raw);
-                tmem_ld_wait();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->o_empty[ob]);
-            if (rows_live && q < p.lq) {
-                const float inv = DROP ? 1.0f / (sum * (1.0f - p.drop.p)) : 1.0f / sum;
-                __nv_bfloat16* dst = p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim + sub * 16;
-#pragma unroll
-                for (int i = 0; i < 16; i += 8) {
-                    uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
-                    u.y = pack_bf16x2(__uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
-                    u.z = pack_bf16x2(__uint_as_float(raw[i + 4]) * inv, __uint_as_float(raw[i + 5]) * inv);
-                    u.w = pack_bf16x2(__uint_as_float(raw[i + 6]) * inv, __uint_as_float(raw[i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + i) = u;
-                }
-                if (p.o_f32) {
-                    float* df = p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + sub * 16;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4*>(df + i) =
-                            make_float4(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv,
-                                        __uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
-                }
-                if (p.lse && sub == 0)
-                    p.lse[((size_t)b * p.heads + h) * p.lq + q] = (mx + log2f(sum)) * 0.6931471805599453f;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 512);
     }
 }
 
@@ -762,8 +478,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
     const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 256, t_dv = tmem + 320, t_dk = tmem + 384;
     const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
     const uint32_t idesc_kv = make_idesc_bf16(128, kHeadDim, 1, 1);     // A = P^T / dS^T (MN-major), B = dO / Q rows
@@ -1071,8 +785,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
     const uint32_t t_s = tmem, t_dp = tmem + 128, t_dk = tmem + 256, t_dv = tmem + 320;
     const uint32_t idesc_acc = make_idesc_bf16(128, kHeadDim, 0, 1);
     auto chunk_n16 = [&](int i) { return (min(128, p.lq - i * 128) + 15) & ~15; };   // queries of chunk i, MMA granule
@@ -1260,20 +972,11 @@ static const CUtensorMap* head_tmap(const void* ptr, int64_t ld, int heads, int 
 
 }  // namespace shg
 
-// Experimental pipelined forward (attn_fwd_pipe_kernel): off by default — measured slower than the unpipelined
-// kernel (393 x 393, B = 32: 141 vs 119 us plain, 184 vs 150 us with dropout).  SHG_ATTN_PIPE=1 or
-// shg_set_attn_pipeline(1) selects it for mask_mode 0; the attention tests run both.
-static int g_attn_pipe = -1;
 static int g_attn_merge = -1;     // single-query-tile backward in one merged pass (default on; SHG_ATTN_MERGE=0: two passes)
 extern "C" int shg_set_attn_bwd_merge(int on) {
     g_attn_merge = on ? 1 : 0;
     return SHG_OK;
 }
-extern "C" int shg_set_attn_pipeline(int on) {
-    g_attn_pipe = on ? 1 : 0;
-    return SHG_OK;
-}
-
 extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     using namespace shg;
     SHG_REQUIRE(a && a->q && a->k && a->v && a->o, SHG_EINVAL, "shg_attn_fwd: null operand");
@@ -1319,29 +1022,6 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     }
     cudaStream_t s = (cudaStream_t)stream;
     const bool drop = p.drop.p > 0.f;
-    if (g_attn_pipe < 0) {
-        const char* e = getenv("SHG_ATTN_PIPE");
-        g_attn_pipe = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (a->mask_mode == 0 && g_attn_pipe) {
-        // pipelined, warp-specialised kernel: one CTA per (batch, head, query-tile group); a short tail tile
-        // (393 = 3 x 128 + 9) rides with the tile before it, on the K/V already resident
-        const int n_qt = (a->lq + 127) / 128;
-        const int tail = a->lq - (n_qt - 1) * 128;
-        const int n_groups = (n_qt >= 2 && tail <= 32) ? n_qt - 1 : n_qt;
-        const size_t smem_pipe = 98304 + (size_t)2 * p.n_kbox * 8192 + 2048 * 4 + sizeof(PipeBars) + 16 + 1024;
-        SHG_REQUIRE(smem_pipe <= 227 * 1024, SHG_ESHAPE, "shg_attn_fwd: %zu B of shared memory needed", smem_pipe);
-        static bool pipe_attr = false;
-        if (!pipe_attr) {
-            cudaFuncSetAttribute(attn_fwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            cudaFuncSetAttribute(attn_fwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            pipe_attr = true;
-        }
-        dim3 gridp(n_groups, a->heads, a->batch);
-        if (drop) shg::launch(attn_fwd_pipe_kernel<true>, gridp, kPipeThreads, smem_pipe, s, *tq, *tk, *tv, p, n_qt, n_groups);
-        else shg::launch(attn_fwd_pipe_kernel<false>, gridp, kPipeThreads, smem_pipe, s, *tq, *tk, *tv, p, n_qt, n_groups);
-        return check_launch("shg_attn_fwd(pipe)");
-    }
     dim3 grid((a->lq + 127) / 128, a->heads, a->batch);
     if (a->mask_mode == 1) {
         if (drop) shg::launch(attn_fwd_kernel<true, true>, grid, kAttnThreads, smem, s, *tq, *tk, *tv, p);

@@ -106,8 +106,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
 
     const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
@@ -302,8 +300,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
 
     const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
@@ -417,8 +413,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 // fp32 [B, C, S] (NCDHW, S = T*49) -> bf16 [B, S, C] (channels-last), and back (bf16 -> fp32).  64-channel x 32-position
 // tiles through shared memory: reads are contiguous along S, writes along C.
 __global__ void ncs_to_nsc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int S) {
-    pdl_launch_dependents();
-    pdl_wait();
     __shared__ float tile[64][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 64, s0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
@@ -436,8 +430,6 @@ __global__ void ncs_to_nsc_kernel(const float* __restrict__ x, __nv_bfloat16* __
     }
 }
 __global__ void nsc_to_ncs_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int S) {
-    pdl_launch_dependents();
-    pdl_wait();
     __shared__ float tile[32][65];
     const int b = blockIdx.z, c0 = blockIdx.y * 64, s0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -458,8 +450,6 @@ __global__ void nsc_to_ncs_kernel(const __nv_bfloat16* __restrict__ x, float* __
 // tokens (lxrt/modeling_capsbert.py:1049-1069)
 __global__ void frontend_cls_kernel(const float* __restrict__ cls, const float* __restrict__ pe,
                                     __nv_bfloat16* __restrict__ tokens, int64_t ld, int rows_per_clip, int n, DropCfg drop) {
-    pdl_launch_dependents();
-    pdl_wait();
     const int b = blockIdx.x;
     const uint32_t key = drop.p > 0.f ? drop_key(__ldg(drop.seed), drop.salt) : 0u;
     const uint32_t th = drop_thresh(drop.p);
@@ -478,8 +468,6 @@ __global__ void frontend_cls_kernel(const float* __restrict__ cls, const float* 
 __global__ void frontend_bwd_kernel(const __nv_bfloat16* __restrict__ d_tok, int64_t ld, const __nv_bfloat16* __restrict__ pre,
                                     __nv_bfloat16* __restrict__ d_pre, float* __restrict__ d_pe, float* __restrict__ d_cls,
                                     int batch, int rows_per_clip, int n, DropCfg drop) {
-    pdl_launch_dependents();
-    pdl_wait();
     const int tok = blockIdx.x, c0 = threadIdx.x * 8;
     if (c0 >= n) return;
     const uint32_t key = drop.p > 0.f ? drop_key(__ldg(drop.seed), drop.salt) : 0u;

@@ -30,15 +30,6 @@ int check_launch(const char* what) {
     return SHG_OK;
 }
 
-static int g_pdl = -1;
-bool pdl_enabled() {
-    if (g_pdl < 0) {
-        const char* e = getenv("SHG_PDL");
-        g_pdl = (e && e[0] == '1') ? 1 : 0;
-    }
-    return g_pdl != 0;
-}
-
 struct TmapKey {
     uint64_t w[20];
     bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
@@ -132,12 +123,7 @@ extern "C" {
 
 const char* shg_last_error(void) { return shg::g_err; }
 
-int shg_version(void) { return 101; }
-
-int shg_set_pdl(int on) {
-    shg::g_pdl = on ? 1 : 0;
-    return SHG_OK;
-}
+int shg_version(void) { return 200; }
 
 int shg_device_check(int device) {
     cudaDeviceProp p;

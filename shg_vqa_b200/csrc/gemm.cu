@@ -316,8 +316,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();     // after the TMEM allocation: a dependent grid parked on this SM cannot starve it
-    pdl_wait();                  // everything above overlapped the previous kernel's tail
 
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     if (threadIdx.x == 0) SHG_STAMP(1);
@@ -489,8 +487,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
 
     const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;     // m_tiles counts 256-row pair tiles here
@@ -608,176 +604,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Cluster-of-four variant: TWO CTA pairs (adjacent 256-row tiles of the same n-tile) share the B tile.  Each CTA
-// fetches a quarter of it and TMA-multicasts that quarter to the CTA of the other pair staging the same half, so a
-// CTA pulls 16 KB of A + 8 KB of B per k-block through L2 instead of 16 + 16 — the K = 768..3072 projections are
-// L2-feed-bound (see pick_config).  A stage is released only when both pairs' products have read it (their commits
-// arrive on every CTA's empty barrier).  256 x 256 tiles, no split-K, no grouping.
-// ---------------------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm4_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
-             const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_bq,
-             const GemmParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stg = smem;
-    if (p.tma_store) smem += kStageOutBytes;
-    const uint32_t a_bytes = BM * BK * 2;
-    const int half_n = p.block_n / 2;
-    const uint32_t b_bytes = half_n * BK * 2;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
-    uint64_t* empty_bar = full_bar + kMaxStages;
-    uint64_t* tmem_full = empty_bar + kMaxStages;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t crank = cluster_ctarank();      // 0..3: two CTA pairs that share the B tile through TMA multicast
-    const uint32_t pr = crank >> 1, rank = crank & 1;
-    const bool leader = rank == 0;
-    const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));   // the CTAs holding this half of B
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.n_stages; ++s) {
-            mbar_init(full_bar + s, 1);      // leader's: one arrive.expect_tx covering both CTAs' bytes
-            mbar_init(empty_bar + s, 2);     // each CTA's: multicast commits from BOTH pairs' MMAs (the stage is shared)
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(tmem_full + s, 1);     // each CTA's: multicast commit
-            mbar_init(tmem_empty + s, 8 * kEpiSub);   // leader's: the epilogue warps of both CTAs
-        }
-        fence_barrier_init();
-        tma_prefetch_desc(&tma_a);
-        tma_prefetch_desc(&tma_b);
-    }
-    cluster_sync_all();                      // barriers of both CTAs exist before anything signals across
-    if (warp == 1) tmem_alloc2(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
-
-    const int n_pairs = gridDim.x >> 2, pair = blockIdx.x >> 2;   // clusters; a cluster tile = two 256-row tiles of one n-tile
-    const int m_super = (p.m_tiles + 1) >> 1;
-    const int total_tiles = m_super * p.n_tiles;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-                const int mt = min(2 * (tile / p.n_tiles) + (int)pr, p.m_tiles - 1);   // an odd tile count: recompute the last
-                const int m0 = mt * 256 + rank * BM;
-                const int n0 = (tile % p.n_tiles) * p.block_n + rank * half_n;
-                const int kb0 = 0, kb1 = p.kb_total;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty_bar + stage, phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    if (leader) mbar_expect_tx(full_bar + stage, 2 * stage_bytes);
-                    const int k0 = kb * BK;
-                    if (!A_MN) {
-                        tma_load_2d_pair(sa, &tma_a, full_bar + stage, k0, m0);
-                    } else {
-                        tma_load_2d_pair(sa, &tma_a, full_bar + stage, m0, k0);
-                        tma_load_2d_pair(sa + 8192, &tma_a, full_bar + stage, m0 + 64, k0);
-                    }
-                    // this CTA fetches one quarter of the B tile and multicasts it to the CTA of the other pair that
-                    // stages the same half: per k-block a CTA pulls 16 KB of A + 8 KB of B through L2 instead of 16 + 16
-                    if (!B_MN) {
-                        const int qn = half_n >> 1;
-                        tma_load_2d_pair_mc(sb + pr * qn * 128, &tma_bq, full_bar + stage, k0, n0 + pr * qn, mc_mask);
-                    } else {
-                        tma_load_2d_pair_mc(sb + pr * 8192, &tma_b, full_bar + stage, n0 + pr * 64, k0, mc_mask);
-                    }
-                    if (++stage == p.n_stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (leader && lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(256, p.block_n, A_MN, B_MN);
-            int stage = 0, as = 0;
-            uint32_t phase = 0, aphase = 0;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-                const int kb0 = 0, kb1 = p.kb_total;
-                mbar_wait(tmem_empty + as, aphase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 256;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(full_bar + stage, phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
-#pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) {
-                        const uint64_t adesc = A_MN ? make_smem_desc(sa + ks * 2048, 8192, 1024)
-                                                    : make_smem_desc(sa + ks * 32, 16, 1024);
-                        const uint64_t bdesc = B_MN ? make_smem_desc(sb + ks * 2048, 8192, 1024)
-                                                    : make_smem_desc(sb + ks * 32, 16, 1024);
-                        umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
-                    }
-                    tc_commit_mask(empty_bar + stage, 0xF);
-                    if (++stage == p.n_stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                tc_commit_mask(tmem_full + as, (uint16_t)(3u << (2 * pr)));
-                if (++as == 2) {
-                    as = 0;
-                    aphase ^= 1;
-                }
-            }
-        }
-    } else {
-        const int quarter = warp & 3, sub = (warp - 2) >> 2;
-        const int etid = (warp - 2) * 32 + lane;
-        int as = 0;
-        uint32_t aphase = 0, nblk = 0;
-        const uint32_t leader_empty0 = mapa_u32(smem_u32(tmem_empty), 2 * pr);
-        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-            const int mt = 2 * (tile / p.n_tiles) + (int)pr;
-            // the recomputed duplicate of an odd tile count stores nothing: rows (and the TMA store box) lie past M
-            const int m0 = (mt < p.m_tiles ? mt * 256 : ((p.m + 255) & ~255)) + rank * BM, n0 = (tile % p.n_tiles) * p.block_n;
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < p.m;
-            float* sb = s_bias + as * 256;
-            const float* bias = m0 >= p.split_m ? p.bias2 : p.bias;
-            if (etid < 256) sb[etid] = (bias && n0 + etid < p.n) ? __ldg(bias + n0 + etid) : 0.f;
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
-            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk, p.d,
-                          [&] { mbar_wait(tmem_full + as, aphase); });
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_empty0 + as * 8);
-            if (++as == 2) {
-                as = 0;
-                aphase ^= 1;
-            }
-        }
-        if (etid == 0) bulk_wait_read<0>();
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();                      // the peer may still be reading this CTA's smem / signalling its barriers
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc2(tmem_base, 512);
-    }
-}
-
 // Tile selection.  Every candidate (single CTA 128 x {64,128,192,256}; CTA pair 256 x {128,192,256}) is costed with
 // a wave model whose per-k-block time is the largest of: the tensor-core time (2*bn clk), the SM's own operand
 // ingress (64 B/clk) and the chip-wide L2 feed shared by the active CTAs; plus a fixed launch/prologue/epilogue
@@ -830,16 +656,6 @@ static unsigned long long* g_gemm_dbg = nullptr;
 // (device memory, 8 x u64); NULL switches it off.  Not part of the product path.
 extern "C" int shg_debug_gemm_stamps(void* buf) {
     g_gemm_dbg = (unsigned long long*)buf;
-    return SHG_OK;
-}
-
-// Cluster-of-four multicast tiles (gemm4_kernel): OFF by default.  Measured at bs32: 33 clusters of four are resident
-// (132 of 148 SMs); per SM the multicast saves a few per cent, which the 16 idle SMs more than give back on the
-// K = 768 projections (12576x3072x768: 60.2 vs 55.6 us) — only the K = 15360 dgrad of the hoisted K/V projection
-// wins (251 vs 278 us).  SHG_GEMM_QUAD=1 / shg_set_gemm_quad(1) enables it; the GEMM tests run both.
-static int g_gemm_quad = -1;
-extern "C" int shg_set_gemm_quad(int on) {
-    g_gemm_quad = on ? 1 : 0;
     return SHG_OK;
 }
 
@@ -966,52 +782,6 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
         }                                                                                                      \
         shg::launch(gemm2_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, p);                                  \
     } while (0)
-    if (g_gemm_quad < 0) {
-        const char* e = getenv("SHG_GEMM_QUAD");
-        g_gemm_quad = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (pair && g_gemm_quad && bn == 256 && p.splits == 1 && !grouped && !kgrouped && p.m_tiles >= 2 && !(a->block_n & 8192)) {
-        // cluster of four: two pair tiles share the B tile through TMA multicast (gemm4_kernel)
-        const CUtensorMap* tbq = tb;
-        if (!a->b_mn_major) {
-            uint64_t qd[2] = {(uint64_t)a->k, (uint64_t)a->n}, qs[1] = {(uint64_t)a->ldb * 2};
-            uint32_t qb[2] = {BK, 64};
-            tbq = get_tmap_bf16(a->b, 2, qd, qs, qb);
-            if (!tbq) return SHG_ECUDA;
-        }
-        const int total4 = ((p.m_tiles + 1) / 2) * p.n_tiles;
-        static int max_clusters = -1;       // resident clusters of four (GPC boundaries leave some SMs out)
-        if (max_clusters < 0) {
-            cudaFuncSetAttribute(gemm4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(4 * (kNumSMs / 4)), cfg.blockDim = dim3(kGemmThreads), cfg.dynamicSmemBytes = 227 * 1024 - 1024;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 4, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-            cfg.attrs = at, cfg.numAttrs = 1;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm4_kernel<false, false>, &cfg) != cudaSuccess || n < 1) n = kNumSMs / 4;
-            cudaGetLastError();
-            max_clusters = n < kNumSMs / 4 ? n : kNumSMs / 4;
-            if (getenv("SHG_GEMM_DEBUG")) fprintf(stderr, "gemm4: %d resident clusters of 4\n", max_clusters);
-        }
-        const int grid4 = 4 * (total4 < max_clusters ? total4 : max_clusters);
-#define SHG_GEMM4_LAUNCH(AM, BMJ)                                                                              \
-    do {                                                                                                       \
-        static bool attr_set4 = false;                                                                         \
-        if (!attr_set4) {                                                                                      \
-            cudaFuncSetAttribute(gemm4_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-            attr_set4 = true;                                                                                  \
-        }                                                                                                      \
-        shg::launch(gemm4_kernel<AM, BMJ>, grid4, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *tbq, p); \
-    } while (0)
-        if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM4_LAUNCH(false, false);
-        else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM4_LAUNCH(false, true);
-        else if (a->a_mn_major && a->b_mn_major) SHG_GEMM4_LAUNCH(true, true);
-        else SHG_GEMM4_LAUNCH(true, false);
-#undef SHG_GEMM4_LAUNCH
-        return check_launch("shg_gemm(quad)");
-    }
     if (pair) {
         if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);
         else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM2_LAUNCH(false, true);

@@ -133,8 +133,6 @@ __device__ void emit_warp(int rc, bool transposed, int nr, int nc, int q_f, int 
 __global__ void __launch_bounds__(32) lsap_frames_kernel(const float* __restrict__ cost, int q_f, int ld,
                                                         const int32_t* __restrict__ col_off, int32_t* rows,
                                                         int32_t* cols, int32_t* n_match, int32_t* status) {
-    pdl_launch_dependents();
-    pdl_wait();
     __shared__ float sC[kMaxDim * kMaxDim];
     const int f = blockIdx.x, lane = threadIdx.x;
     const int c0 = col_off[f], n = col_off[f + 1] - c0;
@@ -174,8 +172,6 @@ __global__ void __launch_bounds__(256) match_from_logits_kernel(
     const T* __restrict__ logits, int q_f, int n_cls, int ld, const int32_t* __restrict__ labels,
     const int32_t* __restrict__ label_off, int32_t* rows, int32_t* cols, int32_t* n_match, int32_t* status,
     float* row_max, float* row_lse, int32_t* row_argmax, int32_t* target_classes) {
-    pdl_launch_dependents();
-    pdl_wait();
     __shared__ float sC[kMaxDim * kMaxDim];
     __shared__ int s_bad;
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -213,8 +209,12 @@ __global__ void __launch_bounds__(256) match_from_logits_kernel(
         }
         if (lane < n && n <= kMaxDim) {
             const int lab = labels[l0 + lane];
-            const float c = -(expf(ldf(x + lab) - mx) / sum);
-            if (isnan(c) || c == -INFINITY) s_bad = 1;
+            // a label outside [0, n_cls) is an IndexError in the reference (prob[:, tgt_ids], lxrt/matcher.py:73):
+            // never dereferenced here, the frame is flagged (status -4) and left unmatched
+            const bool lab_ok = lab >= 0 && lab < n_cls;
+            const float c = lab_ok ? -(expf(ldf(x + lab) - mx) / sum) : 0.f;
+            if (!lab_ok) atomicMax(&s_bad, 2);
+            else if (isnan(c) || c == -INFINITY) atomicMax(&s_bad, 1);
             if (transposed) sC[lane * kMaxDim + q] = c;
             else sC[q * kMaxDim + lane] = c;
         }
@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(256) match_from_logits_kernel(
     if (warp != 0) return;
     const int nr = transposed ? n : q_f, nc = transposed ? q_f : n;
     int col4row = -1, row4col = -1, rc = 0;
-    if (s_bad) rc = -2;
+    if (s_bad == 2) rc = -4;
+    else if (s_bad) rc = -2;
     else if (n > kMaxDim) rc = -3;
     else if (nr > 0) rc = solve_warp(sC, nr, nc, lane, col4row, row4col);
     emit_warp(rc, transposed, nr, nc, q_f, lane, col4row, row4col, rows + (size_t)f * q_f, cols + (size_t)f * q_f,
@@ -236,12 +237,22 @@ __global__ void __launch_bounds__(256) set_loss_fwd_kernel(const T* __restrict__
                                                           const int32_t* __restrict__ tgt,
                                                           const float* __restrict__ row_lse,
                                                           const int32_t* __restrict__ row_argmax, float eos_coef,
-                                                          float* out) {
-    pdl_launch_dependents();
-    pdl_wait();
+                                                          float* out, int n_cls, const int32_t* __restrict__ status,
+                                                          int n_frames, float* err_out) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int n_err = 0;
+    // frames the matcher refused (NaN / -inf costs, too many targets, label out of range: the reference raises
+    // there) and target classes outside [0, n_cls) are counted into *err_out, which the host turns into an exception
+    // when it reads the loss sums — no extra synchronisation
+    if (status)
+        for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += gridDim.x * blockDim.x)
+            n_err += status[f] != 0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
         const int t = tgt[r];
+        if (t < 0 || t >= n_cls) {
+            ++n_err;
+            continue;
+        }
         const float w = t == 0 ? eos_coef : 1.0f;
         a0 += w * (row_lse[r] - ldf(logits + (size_t)r * ld + t));
         a1 += w;
@@ -260,6 +271,7 @@ __global__ void __launch_bounds__(256) set_loss_fwd_kernel(const T* __restrict__
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
         atomicAdd(out + threadIdx.x, s);
     }
+    if (err_out && n_err) atomicAdd(err_out, (float)n_err);
 }
 
 template <typename T, typename TO>
@@ -268,13 +280,13 @@ __global__ void __launch_bounds__(256) set_loss_bwd_kernel(const T* __restrict__
                                                           const float* __restrict__ row_lse, float eos_coef,
                                                           const float* __restrict__ out, float grad_scale,
                                                           TO* __restrict__ dlogits, int ldo) {
-    pdl_launch_dependents();
-    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
     const int t = tgt[r];
-    const float s = grad_scale * (t == 0 ? eos_coef : 1.0f) / out[1];
+    // rows with an out-of-range class were excluded from the loss (and flagged) by the forward: zero gradient
+    const bool t_ok = t >= 0 && t < n_cls;
+    const float s = t_ok ? grad_scale * (t == 0 ? eos_coef : 1.0f) / out[1] : 0.f;
     const float lse = row_lse[r];
     const T* x = logits + (size_t)r * ld;
     TO* g = dlogits + (size_t)r * ldo;
@@ -321,16 +333,17 @@ int shg_match_from_logits(const void* logits, int logits_bf16, int n_frames, int
 
 int shg_set_loss_fwd(const void* logits, int logits_bf16, int n_rows, int n_cls, int ld_logits,
                      const int32_t* target_classes, const float* row_lse, const int32_t* row_argmax, float eos_coef,
-                     float* out, void* stream) {
-    (void)n_cls;
+                     float* out, const int32_t* status, int n_frames, float* err_out, void* stream) {
     if (n_rows == 0) return SHG_OK;
     const int blocks = (n_rows + 255) / 256 < 148 ? (n_rows + 255) / 256 : 148;
     if (logits_bf16)
         shg::launch(shg::set_loss_fwd_kernel<__nv_bfloat16>, blocks, 256, 0, (cudaStream_t)stream, 
-            (const __nv_bfloat16*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out);
+            (const __nv_bfloat16*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out,
+            n_cls, status, n_frames, err_out);
     else
         shg::launch(shg::set_loss_fwd_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, 
-            (const float*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out);
+            (const float*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out, n_cls, status,
+            n_frames, err_out);
     return shg::check_launch("shg_set_loss_fwd");
 }
 

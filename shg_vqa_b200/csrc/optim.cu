@@ -14,8 +14,6 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
                                                         const int64_t* __restrict__ seg_start,
                                                         const int64_t* __restrict__ seg_prefix, int n_seg,
                                                         int64_t total4, float* __restrict__ out) {
-    pdl_launch_dependents();
-    pdl_wait();
     float acc = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = i * 4;
@@ -50,8 +48,6 @@ __global__ void __launch_bounds__(256) bert_adam_kernel(float* __restrict__ p, f
                                                        float max_norm, float lr, const float* __restrict__ lr_dev,
                                                        float b1, float b2, float eps, float wd, float grad_scale,
                                                        int zero_grad) {
-    pdl_launch_dependents();
-    pdl_wait();
     if (lr_dev) lr = lr_dev[0];     // device-resident learning rate: the launch stays valid inside a CUDA graph
     float clip = 1.0f;
     if (max_norm > 0.f) {

@@ -70,8 +70,6 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      const __nv_bfloat16* __restrict__ addend, int addend_rows, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int rows, int split_row, const float* __restrict__ gamma2,
                      const float* __restrict__ beta2) {
-    pdl_launch_dependents();
-    pdl_wait();
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -124,8 +122,6 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      __nv_bfloat16* __restrict__ dx_drop, DropCfg out_drop, DropCfg in_drop, int split_row,
                      const float* __restrict__ gamma2, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
                      float* __restrict__ dxsum2) {
-    pdl_launch_dependents();
-    pdl_wait();
     constexpr int N = 256 * CH;
     // grouped launch: blockIdx.y = 1 handles rows [split_row, rows) with the second parameter / gradient set
     int row_begin = 0;
@@ -222,8 +218,6 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 // out[c] += sum_rows x[row, c]  (bias gradients).  Block = 256 threads over 8-column groups x row slices.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, int n,
                                                     float* __restrict__ out, int rows_per_block) {
-    pdl_launch_dependents();
-    pdl_wait();
     // thread t owns column group (blockIdx.x*32 + t%32) of 8 columns, row phase t/32
     const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
     const int c = cg * 8;
@@ -263,8 +257,6 @@ embed_ln_fwd_kernel(const float* __restrict__ word, const int64_t* __restrict__ 
                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
                     __nv_bfloat16* __restrict__ pre_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                     int rows, int seq_len, DropCfg drop) {
-    pdl_launch_dependents();
-    pdl_wait();
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -324,8 +316,6 @@ embed_scatter_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int64_t* __
                          const int64_t* __restrict__ type_ids, float* __restrict__ dword, int word_pad,
                          float* __restrict__ dpos, int pos_pad, float* __restrict__ dtype, int type_pad, int rows,
                          int seq_len) {
-    pdl_launch_dependents();
-    pdl_wait();
     constexpr int N = 256 * CH;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -351,8 +341,6 @@ embed_scatter_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int64_t* __
 __global__ void __launch_bounds__(256) add_rows_kernel(const __nv_bfloat16* __restrict__ x,
                                                       const __nv_bfloat16* __restrict__ add, int add_rows,
                                                       __nv_bfloat16* __restrict__ y, int64_t total8, int n8) {
-    pdl_launch_dependents();
-    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n8;
         const int c8 = (int)(i - r * n8);
@@ -372,8 +360,6 @@ __global__ void __launch_bounds__(256) copy3d_kernel(const __nv_bfloat16* __rest
                                                     __nv_bfloat16* __restrict__ dst,
                                                     const __nv_bfloat16* __restrict__ add, int n0, int n1, int chunk8,
                                                     int64_t s0, int64_t s1, int64_t d0, int64_t d1, int accumulate) {
-    pdl_launch_dependents();
-    pdl_wait();
     const int64_t total = (int64_t)n0 * n1 * chunk8;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int e8 = (int)(i % chunk8);
@@ -403,8 +389,6 @@ __global__ void __launch_bounds__(256) copy3d_kernel(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                      const __nv_bfloat16* __restrict__ aux,
                                                      __nv_bfloat16* __restrict__ dx, int64_t n8, int mode) {
-    pdl_launch_dependents();
-    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         float g[8], a[8];
         load8(dy + i * 8, g);
@@ -425,8 +409,6 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
                                                         const float* __restrict__ t, int rows, int cols,
                                                         float grad_scale, float* __restrict__ out,
                                                         __nv_bfloat16* __restrict__ dx, int64_t lddx) {
-    pdl_launch_dependents();
-    pdl_wait();
     float acc = 0.f;
     const int64_t total = (int64_t)rows * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -448,8 +430,6 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          int64_t n) {
-    pdl_launch_dependents();
-    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t n8 = n / 8;

@@ -27,28 +27,13 @@ int check_launch(const char* what);
 
 constexpr int kNumSMs = 148;
 
-// ---------------------------------------------------------------- programmatic dependent launch (PDL)
-// Every kernel of the library is launched through shg::launch with programmatic stream serialisation allowed, calls
-// pdl_launch_dependents() first thing and pdl_wait() before it touches global memory: the next kernel of a
-// dependent chain is rasterised and runs its prologue (barrier init, TMEM allocation, descriptor prefetch) while
-// this one is still draining, then blocks in pdl_wait() until this grid has completed and flushed.  The step is a
-// chain of ~850 mostly 5-30 us kernels.  Measured on the captured bs32 step: 16.7 ms with PDL vs 16.5 ms without (the
-// replayed graph has < 10 us of idle gaps in total, and parked dependents hold shared memory / TMEM that kernels of
-// the other streams could use), so it is OFF by default; SHG_PDL=1 in the environment or shg_set_pdl(1) enables it.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();
-
+// Every kernel of the library is launched through shg::launch (cudaLaunchKernelEx on the caller's stream).
 template <class... KArgs, class... Args>
 inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                           Args&&... args) {
     static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count mismatch");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

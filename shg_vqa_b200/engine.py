@@ -58,10 +58,10 @@ class Engine:
         self.p_hidden, self.p_attn, self.p_dec, self.p_emb, self.p_relq, self.p_actq = 0.1, 0.1, 0.15, 0.1, 0.1, 0.15
         self.drop_seed = torch.zeros(1, device=self.dev, dtype=torch.int32) if self.dev.type == "cuda" else None
         self._salt, self._training = 0, False
+        self.nv_mem = 393
         # Independent sub-graphs run on side streams so that the small-M launches (40-token language side,
         # 48-query action decoder) fill SMs the 148-CTA persistent kernels of the visual side leave idle.
         self.use_streams = self.dev.type == "cuda"
-        self.join_wgrads_after_late = True
         import os
         self.fused_decoders = os.environ.get("SHG_FUSED_DECODERS", "1") != "0"
         # (stream priorities — chains high, weight gradients low — were measured: no effect on the replayed step)
@@ -404,7 +404,7 @@ class Engine:
         s1 = ops.gemm(sa, D["sa_o"].w, bias=D["sa_o"].b, residual=tgt, drop=d1)
         t1, t1p, m1, r1 = ops.layernorm_fwd(s1, D["n1"].g, D["n1"].b, EPS_DETR, addend=qpos, save_stats=save)
         cq = ops.gemm(t1p, D["ca_q"].w, bias=D["ca_q"].b)
-        ca, lse2 = ops.attention_fwd(cq, k_mem, v_mem, B, nq, 393, save_lse=save, drop=da2)
+        ca, lse2 = ops.attention_fwd(cq, k_mem, v_mem, B, nq, self.nv_mem, save_lse=save, drop=da2)
         s2 = ops.gemm(ca, D["ca_o"].w, bias=D["ca_o"].b, residual=t1, drop=d2)
         t2, _, m2, r2 = ops.layernorm_fwd(s2, D["n2"].g, D["n2"].b, EPS_DETR, save_stats=save)
         t3, t3p, ffn = self._ffn_fwd(D["l1"], D["l2"], D["n3"], t2, save, act="relu", eps=EPS_DETR, addend=qpos,
@@ -422,11 +422,9 @@ class Engine:
         self._wgrad(D["ca_o"], ds2d, ca, bias=False)
         dca = ops.gemm(ds2d, D["ca_o"].w, b_t=True)
         dcq = torch.empty_like(cq)
-        ops.attention_bwd(cq, k_mem, v_mem, ca, dca, lse2, dcq, dk_mem, dv_mem, B, nq, 393, drop=da2)
+        ops.attention_bwd(cq, k_mem, v_mem, ca, dca, lse2, dcq, dk_mem, dv_mem, B, nq, self.nv_mem, drop=da2)
         self._wgrad(D["ca_q"], dcq, t1p)
         dt1p = ops.gemm(dcq, D["ca_q"].w, b_t=True)
-        if getattr(self, "_trace", None) is not None:
-            self._trace.append(("dt1p", dt1p.float().cpu(), dcq.float().cpu()))
         self._acc(dqpos, dt1p)
         ds1, ds1d = self._ln_bwd_split(ds2, s1, D["n1"], m1, r1, d1, dy2=dt1p, dxsum=D["sa_o"].gb)
         self._wgrad(D["sa_o"], ds1d, sa, bias=False)
@@ -434,13 +432,8 @@ class Engine:
         dqk, dv = torch.empty_like(qk), torch.empty_like(v)
         ops.attention_bwd(qk[:, :H], qk[:, H:], v, sa, dsa, lse1, dqk[:, :H], dqk[:, H:], dv, B, nq, nq,
                           frames=(per, per), drop=da1)
-        if getattr(self, "_trace", None) is not None:
-            self._trace_self = getattr(self, "_trace_self", [])
-            self._trace_self.append(tuple(t.float().cpu() for t in (qk, v, dsa, dqk, dv, sa)))
         self._wgrad(D["sa_qk"], dqk, tgt_p)
         dtgt_p = ops.gemm(dqk, D["sa_qk"].w, b_t=True)
-        if getattr(self, "_trace", None) is not None:
-            self._trace.append(("dtgt_p", dtgt_p.float().cpu(), dqk.float().cpu()))
         if first:
             # tgt is the constant zero tensor (tasks/agqa_model.py:235): only the bias of the value projection learns
             self._bias_grad(dv, D["sa_v"].gb)
@@ -515,7 +508,7 @@ class Engine:
         s1 = self._g2(sa, DA["sa_o"], DB["sa_o"], split, residual=tgt, drop=d1)
         t1, t1p, m1, r1 = self._ln2_fwd(s1, DA["n1"], DB["n1"], split, EPS_DETR, addend=qpos, save=save)
         cq = self._g2(t1p, DA["ca_q"], DB["ca_q"], split)
-        ca, lse2 = self._attn2_fwd(cq, None, None, B, nq, 393, split, None, save, da2, kv_rel=kv_rel, kv_act=kv_act)
+        ca, lse2 = self._attn2_fwd(cq, None, None, B, nq, self.nv_mem, split, None, save, da2, kv_rel=kv_rel, kv_act=kv_act)
         s2 = self._g2(ca, DA["ca_o"], DB["ca_o"], split, residual=t1, drop=d2)
         t2, _, m2, r2 = self._ln2_fwd(s2, DA["n2"], DB["n2"], split, EPS_DETR, save=save)
         d_in, d_out = self._drop(self.p_dec), self._drop(self.p_dec)
@@ -550,7 +543,7 @@ class Engine:
             dkk, dvv = (dkv_rel, dkv_act)[g]
             with self._on(self.s2 if g == 1 else None):
                 ops.attention_bwd(cq[a0:a1], kk, vv, ca[a0:a1], dca[a0:a1], lse2[g], dcq[a0:a1], dkk, dvv, B, nq[g],
-                                  393, drop=da2[g])
+                                  self.nv_mem, drop=da2[g])
         self._join(self.s2)
         self._wgrad2(DA["ca_q"], DB["ca_q"], dcq, t1p, split)
         dt1p = self._g2t(dcq, DA["ca_q"], DB["ca_q"], split)
@@ -690,6 +683,9 @@ class Engine:
         or feat (backbone features, fp32 [B,2048,16,7,7] / bf16 channels-last) for the built-in front-end;
         input_ids/input_mask/segment_ids int64 [B,40], rel_segment_ids [B,128], act_segment_ids [B,48]."""
         save = train
+        # LXRT cross layers / pooler / first answer head: forward-only in --taskHGQA training (the loss never reads
+        # `logit`, SURVEY §3.1) unless the caller wants their gradient (--taskVQA training, tasks/agqaVQA.py)
+        save_x = train and (self.task != "hgqa" or bool(inp.get("x_grad", False)))
         B = inp["input_ids"].shape[0]
         ctx = dict(B=B)
         ids, seg = inp["input_ids"].reshape(-1), inp["segment_ids"].reshape(-1)
@@ -722,6 +718,8 @@ class Engine:
         else:
             visn, ctx["frontend"] = self.frontend_fwd(inp["feat"], save)
         nv = visn.shape[0] // B
+        assert visn.shape[0] == B * nv and nv <= 416, "visual memory: %d rows for %d clips" % (visn.shape[0], B)
+        self.nv_mem = nv                 # memory length of the decoders' cross-attention (393 for 16-frame clips)
         ctx["R"] = []
         for L in self.r_layers:
             visn, s = self._bert_fwd(L, visn, B, nv, None, save)
@@ -740,11 +738,15 @@ class Engine:
             # LXRT cross layers + pooler + answer head: forward-only in --taskHGQA training → side stream
             with self._on(self.s1) if hgqa else self._on(None):
                 xl, xv = lang_l, visn_r
+                ctx["X"] = []
                 for _ in range(self.nx):             # the same module twice (lxrt/modeling_capsbert.py:1247-1249)
-                    xl, xv, _ = self._cross_fwd(self.x_layer, xl, xv, B, nl, nv, kmask, None, False)
-                pooled, _ = self._pool_fwd(self.pooler, xv, nv, xl, nl, B)
-                out["logit"], _ = self._head_fwd(self.logit_fc, pooled, False)
+                    xl, xv, sx = self._cross_fwd(self.x_layer, xl, xv, B, nl, nv, kmask, None, save_x)
+                    ctx["X"].append(sx)
+                pooled, ctx["x_pool"] = self._pool_fwd(self.pooler, xv, nv, xl, nl, B)
+                out["logit"], ctx["x_head"] = self._head_fwd(self.logit_fc, pooled, save_x)
                 out["lang"], out["visn"], out["pooled"] = xl, xv, pooled
+        ctx["save_x"] = save_x
+        ctx["dims"] = (nl, nv, 0, 0, 0)
         if not hgqa:
             return out, ctx
         nq_r, nq_a = self.T * self.n_rel, self.T * self.n_act
@@ -802,11 +804,34 @@ class Engine:
         ctx["dims"] = (nl, nv, ng, nq_r, nq_a)
         return out, ctx
 
-    def backward(self, ctx, d_hg_logit, d_rel_logits, d_act_logits, need_dvisn=False):
+    def backward(self, ctx, d_hg_logit, d_rel_logits, d_act_logits, need_dvisn=False, d_logit=None):
         """Gradients of the --taskHGQA loss (hg answer loss + relation CE + action CE, tasks/agqaHGQA.py:344-378)
-        accumulated into the flat gradient buffer.  d_* are bf16 [rows, n_cls] views with ld % 8 == 0."""
-        self.backward_late_params(ctx, d_hg_logit, d_rel_logits, d_act_logits)
+        accumulated into the flat gradient buffer.  d_* are bf16 [rows, n_cls] views with ld % 8 == 0.
+        d_logit: gradient of the LXRT answer logits (`logit`) — the --taskVQA loss (tasks/agqaVQA.py); needs a
+        forward that saved the cross layers (task 'vqa', or inp['x_grad'])."""
+        if d_logit is not None:
+            self.backward_x(ctx, d_logit)
+        if self.task == "hgqa":
+            self.backward_late_params(ctx, d_hg_logit, d_rel_logits, d_act_logits)
         return self.backward_early_params(ctx, need_dvisn)
+
+    def backward_x(self, ctx, d_logit):
+        """Backward of the LXRT answer branch: logit_fc -> BertPooler2 -> the shared CrossLayer applied twice
+        (lxrt/modeling_capsbert.py:658-677, 1247-1249, 1525-1533).  Leaves the gradients w.r.t. the language-layer
+        and relation-layer outputs in ctx['d_x_lang'] / ctx['d_x_visn'] for backward_early_params."""
+        if not ctx.get("save_x"):
+            raise RuntimeError("the LXRT cross layers were run forward-only: pass x_grad=True (or use task='vqa') to "
+                               "backpropagate through `logit`")
+        B = ctx["B"]
+        nl, nv = ctx["dims"][0], ctx["dims"][1]
+        kmask = ctx["kmask"]
+        d_pool = self._head_bwd(self.logit_fc, ctx["x_head"], d_logit)
+        d_xv = torch.zeros(B * nv, H, device=self.dev, dtype=BF16)
+        d_xl = torch.zeros(B * nl, H, device=self.dev, dtype=BF16)
+        self._pool_bwd(self.pooler, ctx["x_pool"], d_pool, d_xv, nv, d_xl, nl, B)
+        for sx in reversed(ctx["X"]):
+            d_xl, d_xv = self._cross_bwd(self.x_layer, sx, d_xl, d_xv, B, nl, nv, kmask, None)
+        ctx["d_x_lang"], ctx["d_x_visn"] = d_xl, d_xv
 
     def backward_late_params(self, ctx, d_hg_logit, d_rel_logits, d_act_logits):
         """First half of the backward: answer head, CrossEncoder, classifier heads, both decoders, query embeddings
@@ -815,6 +840,7 @@ class Engine:
         all-reduce here, overlapped with backward_early_params."""
         B = ctx["B"]
         nl, nv, ng, nq_r, nq_a = ctx["dims"]
+        self.nv_mem = nv
         kmask = ctx["kmask"]
         per = self.n_act + self.n_rel
         # answer head → pooler → CrossEncoder
@@ -874,26 +900,29 @@ class Engine:
         for i, D in enumerate(self._dec_layers()):
             c = i * 2 * H
             self._wgrad(D["ca_kv"], dkv_mem[:, c:c + 2 * H], mem)
-        # data-parallel runs all-reduce the late parameters right after this half, so their weight gradients must
-        # be final here; a single-GPU step lets them drain under the second half instead
-        if self.join_wgrads_after_late:
-            self._join(self.sw)
+        # (the weight-gradient stream is NOT drained here: a data-parallel trainer issues the all-reduce of these
+        # parameters from that stream, see HotPathTrainer._reduce_async; a single-GPU step lets it run on)
 
-    def backward_early_params(self, ctx, need_dvisn=False, part=None, split=2):
+    def backward_early_params(self, ctx, need_dvisn=False, part=None, split=2, join=True):
         """Second half: the hoisted K/V dgrad, relation layers (main stream), language layers and embeddings
         (side stream).  part=None runs all of it; part=0 runs the whole language side (40 tokens per clip: it ends
         long before the relation side) and the relation layers with index >= split — their gradients are then final
         and the data-parallel schedule reduces them under part=1: the remaining relation layers and the Conv3d
         front-end."""
         B = ctx["B"]
-        nl, nv, ng, nq_r, nq_a = ctx["dims"]
+        nl, nv = ctx["dims"][0], ctx["dims"][1]
         kmask = ctx["kmask"]
         first, second = part in (None, 0), part in (None, 1)
         need0 = need_dvisn or "frontend" in ctx
         if first:
+            # gradient w.r.t. the language-layer output: CrossEncoder branch (+ LXRT answer branch)
+            d_lang, dxl = ctx.get("d_lang_l"), ctx.get("d_x_lang")
+            if d_lang is None:
+                d_lang = dxl
+            elif dxl is not None:
+                self._acc(d_lang, dxl)
             self._fork(self.s1)
             with self._on(self.s1):
-                d_lang = ctx["d_lang_l"]
                 for i in reversed(range(self.nl)):
                     d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
                 ids, seg, pre, mean, rstd, _, d_emb = ctx["emb"]
@@ -901,7 +930,10 @@ class Engine:
                 de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb, in_drop=d_emb)
                 ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
                          ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
-            d_visn = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True)
+            if "dkv_mem" in ctx:
+                d_visn = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True, residual=ctx.get("d_x_visn"))
+            else:
+                d_visn = ctx["d_x_visn"]
             r_range = range(self.nr - 1, (split if part == 0 else 0) - 1, -1)
         else:
             d_visn = ctx["d_visn_mid"]
@@ -913,7 +945,8 @@ class Engine:
             ctx["d_feat"] = self.frontend_bwd(ctx["frontend"], d_visn, need_dfeat=need_dvisn)
         if first:
             self._join(self.s1)
-        self._join(self.sw)
+        if join or second:
+            self._join(self.sw)
         if second:
             self._keep.clear()
         return d_visn

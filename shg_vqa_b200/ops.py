@@ -366,12 +366,16 @@ def match_from_logits(logits, labels, label_off, q_f, want_targets=True):
                 row_argmax=row_arg, target_classes=tgt)
 
 
-def set_loss_fwd(logits, m, eos_coef, out=None):
+def set_loss_fwd(logits, m, eos_coef, out=None, err_out=None):
+    """err_out: fp32 device scalar that counts frames the matcher refused (status != 0) and out-of-range target
+    classes — the inputs the reference raises on (see include/shgvqa.h)."""
     n_rows, n_cls = logits.shape
     if out is None:
         out = torch.zeros(4, device=logits.device, dtype=torch.float32)
+    status = m.get("status") if err_out is not None else None
     call("shg_set_loss_fwd", ptr(logits), int(logits.dtype == BF16), n_rows, n_cls, _ld(logits),
-         ptr(m["target_classes"]), ptr(m["row_lse"]), ptr(m["row_argmax"]), eos_coef, ptr(out), stream())
+         ptr(m["target_classes"]), ptr(m["row_lse"]), ptr(m["row_argmax"]), eos_coef, ptr(out), ptr(status),
+         status.numel() if status is not None else 0, ptr(err_out), stream())
     return out
 
 

@@ -44,6 +44,19 @@ def live_with_frontend(key):
     return live_in_hgqa_training(key)
 
 
+def live_in_vqa_training(key):
+    """Parameters that receive a gradient in --taskVQA training (tasks/agqaVQA.py: BCE on `logit` only): embeddings,
+    language / relation / cross layers, the LXRT pooler and logit_fc, plus the Conv3d front-end's own parameters."""
+    k = canonical_key(key)
+    dead = (".cross_attn_layer.self.", ".cross_attn_layer.cross_self.", ".cross_attn_layer.old.",
+            "pooler_dict.self.", "pooler_dict.cross_self.", "pooler_dict.no_cross.", "pooler_dict.old.")
+    if any(d in k for d in dead):
+        return False
+    if ".visn_fc." in k:
+        return ".visn_fc.conv." in k or k.endswith((".visn_fc.cls_token", ".visn_fc.position_encoding.pe.weight"))
+    return True
+
+
 def warmup_linear(x, warmup=0.002):
     """lxrt/optimization.py:38-43."""
     if x < warmup:
@@ -89,17 +102,20 @@ class HotPathTrainer:
     def __init__(self, device, task="hgqa", n_answers=171, n_rel_cls=457, n_act_cls=158, lr=1e-5, t_total=-1,
                  warmup=0.1, weight_decay=0.01, max_grad_norm=5.0, eos_coef=0.1, world_size=1, process_group=None,
                  live=None, dropout=False, dropout_seed=0, rank=0, frontend=False,
-                 backbone_grad=False):
+                 backbone_grad=False, global_ce_norm=False):
         self.device = torch.device(device)
         # frontend: the step starts from backbone features (inp['feat']) and trains the Conv3d front-end too;
         # backbone_grad: also return the gradient wrt those features (ctx['d_feat']) for a trainable backbone
         self.frontend, self.backbone_grad = bool(frontend), bool(backbone_grad)
         if live is None:
-            live = live_with_frontend if frontend else live_in_hgqa_training
+            if task != "hgqa":
+                live = live_in_vqa_training if frontend else (lambda k: live_in_vqa_training(k) and ".visn_fc." not in k)
+            else:
+                live = live_with_frontend if frontend else live_in_hgqa_training
+        self.task = task
         self.key_shapes = build_key_shapes(task, n_answers, n_rel_cls, n_act_cls)
         self.store = ParamStore(self.key_shapes, self.device, live=live)
         self.engine = Engine(self.store, task)
-        self.engine.join_wgrads_after_late = world_size > 1
         self.lr, self.t_total, self.warmup = lr, t_total, warmup
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-6           # BertAdam defaults (lxrt/optimization.py:63-64)
         self.wd, self.max_norm, self.eos = weight_decay, max_grad_norm, eos_coef
@@ -107,9 +123,17 @@ class HotPathTrainer:
         self.step_count = 0
         self.exp_avg = self.exp_avg_sq = None
         self.n_ans = n_answers
-        self.scal = torch.zeros(16, device=self.device, dtype=torch.float32)   # loss sums / grad sumsq
+        self.scal = torch.zeros(16, device=self.device, dtype=torch.float32)   # loss sums / grad sumsq / error count
+        self.scal_den = torch.zeros(8, device=self.device, dtype=torch.float32)   # globally reduced CE sums
+        self.global_ce_norm = bool(global_ce_norm)
         self.lr_dev = torch.zeros(1, device=self.device, dtype=torch.float32)   # device-resident lr (graph-safe)
-        self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else None
+        # lr crosses to the device through a ring of pinned slots, one event each: the host runs ahead of the GPU
+        # (lagged loss read), and a single slot could be overwritten before its queued H2D copy has read it
+        self._lr_ring = 8
+        cuda = self.device.type == "cuda"
+        self.lr_host = torch.zeros(self._lr_ring, dtype=torch.float32).pin_memory() if cuda else None
+        self._lr_events = [None] * self._lr_ring
+        self._lr_slot = 0
         self.graph = None
         self.copy_stream, self._staged = None, False
         self._loss_slots = None
@@ -161,9 +185,15 @@ class HotPathTrainer:
         rel_target_classes / act_target_classes (int32 [B*Q]) replace the matcher's scatter — used by the parity
         tests to hold the reference's assignment fixed.
         Returns (scalars tensor view, d_hg_logit, d_rel_logits, d_act_logits, match dicts).
-        scal[0]=qa loss, [1..4]=rel sums (w*nll, w, matched, correct), [5..8]=act sums."""
+        scal[0]=qa loss, [1..4]=rel sums (w*nll, w, matched, correct), [5..8]=act sums, [9]=grad sumsq,
+        [10]=number of frames / rows the matcher or the loss refused (NaN/-inf costs, > 32 targets, label out of
+        range — inputs the reference raises on); losses_from_scalars turns a non-zero count into a ValueError."""
         scal = self.scal
         scal.zero_()
+        if self.task != "hgqa":
+            # --taskVQA: BCEWithLogits(logit, target) * n_answers only (tasks/agqaVQA.py)
+            d_logit = ops.bce_logits(out["logit"], batch["target"], scal[0:1], 1.0, want_grad)
+            return scal, d_logit, None, None, []
         d_hg = ops.bce_logits(out["hg_logit"], batch["target"], scal[0:1], 1.0, want_grad)
         res = [d_hg]
         matches = []
@@ -172,15 +202,33 @@ class HotPathTrainer:
             m = ops.match_from_logits(lg, batch[fam + "_labels"], batch[fam + "_off"], q_f)
             if batch.get(fam + "_target_classes") is not None:
                 m = dict(m, target_classes=batch[fam + "_target_classes"])
-            ops.set_loss_fwd(lg, m, self.eos, out=scal[o:o + 4])
-            res.append(ops.set_loss_bwd(lg, m, self.eos, scal[o:o + 4], 1.0) if want_grad else None)
+            ops.set_loss_fwd(lg, m, self.eos, out=scal[o:o + 4], err_out=scal[10:11])
             matches.append(m)
+        gscale = 1.0
+        if self.global_ce_norm and self.world_size > 1:
+            # the reference's nn.DataParallel gathers the logits of all replicas and normalises the weighted CE by
+            # the GLOBAL sum of weights (tasks/agqaHGQA.py:127,223): all-reduce the two denominators (8 bytes) and
+            # undo the optimiser's 1/world average for these two losses
+            import torch.distributed as dist
+            den = self.scal_den
+            den[0:4].copy_(scal[1:5])
+            den[4:8].copy_(scal[5:9])
+            dist.all_reduce(den, group=self.pg)
+            gscale = float(self.world_size)
+        for i, (fam, o) in enumerate((("rel", 1), ("act", 5))):
+            sums = scal[o:o + 4] if gscale == 1.0 else self.scal_den[4 * i:4 * i + 4]
+            res.append(ops.set_loss_bwd(out[fam + "_logits"], matches[i], self.eos, sums, gscale) if want_grad else None)
         return scal, res[0], res[1], res[2], matches
 
     @staticmethod
     def losses_from_scalars(s):
         """Host-side view of the device sums (one small D2H read)."""
         s = s.detach().float().cpu()
+        if s.numel() > 10 and float(s[10]) != 0.0:
+            # scipy raises ValueError("matrix contains invalid numeric entries") / the reference's prob[:, tgt_ids]
+            # raises IndexError for these inputs (lxrt/matcher.py:73-79); the step's gradients are not to be trusted
+            raise ValueError("matching refused %d frame(s)/row(s) of this step: NaN or -inf logits, more than 32 "
+                             "targets in a frame, or a label outside [0, n_classes)" % int(s[10]))
         rel = float(s[1] / s[2]) if float(s[2]) > 0 else 0.0
         act = float(s[5] / s[6]) if float(s[6]) > 0 else 0.0
         rel_err = 100.0 - 100.0 * float(s[4] / s[3]) if float(s[3]) > 0 else 100.0
@@ -201,8 +249,15 @@ class HotPathTrainer:
 
     def _push_lr(self):
         """lr of this step → device scalar (async copy from pinned memory; outside any captured graph)."""
-        self.lr_host[0] = self.current_lr()
-        self.lr_dev.copy_(self.lr_host, non_blocking=True)
+        i = self._lr_slot
+        if self._lr_events[i] is not None:
+            self._lr_events[i].synchronize()              # the copy that last read this slot has executed
+        self.lr_host[i] = self.current_lr()
+        self.lr_dev.copy_(self.lr_host[i:i + 1], non_blocking=True)
+        ev = self._lr_events[i] or torch.cuda.Event()
+        ev.record()
+        self._lr_events[i] = ev
+        self._lr_slot = (i + 1) % self._lr_ring
 
     def optimizer_step(self, lr_on_device=False):
         st = self.store
@@ -232,24 +287,79 @@ class HotPathTrainer:
         if self.engine.dropout_on:
             self.engine.drop_seed.add_(1)
 
+    def _reduce_async(self, slices):
+        """Start the all-reduce of gradient-buffer slices whose contents are final once the kernels queued so far
+        (main stream and weight-gradient stream) have run.  The collective is issued from the weight-gradient
+        stream: NCCL's stream then waits for that stream's queue (ordered after the main stream's current point by
+        one event) while the main stream goes on with the backward — nothing drains."""
+        import torch.distributed as dist
+        eng = self.engine
+        cur = torch.cuda.current_stream()
+        if not eng.use_streams:
+            return [dist.all_reduce(self.store.grad[sl], group=self.pg, async_op=True) for sl in slices]
+        eng.sw.wait_event(cur.record_event())
+        with torch.cuda.stream(eng.sw):
+            return [dist.all_reduce(self.store.grad[sl], group=self.pg, async_op=True) for sl in slices]
+
     def train_step(self, inp, batch, lr_on_device=False):
+        """One training step.  Data-parallel runs (world_size > 1) overlap the path's only collective with the
+        backward: the gradient span is reduced in three buckets, each started as soon as its gradients are final —
+        (1) everything after the LXRT encoder (decoders, heads, CrossEncoder, query embeddings, hoisted K/V
+        weights) under the whole LXRT backward, (2) the language layers, embeddings and upper relation layers under
+        the lower relation layers, (3) the rest.  The same code path runs eagerly and under CUDA-graph capture
+        (the NCCL kernels become nodes of the step's graph on their own branch)."""
         self._advance_seed()
         out, ctx = self.engine.forward(inp, train=True)
         scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, batch)
-        self.engine.backward(ctx, d_hg, d_rel, d_act, need_dvisn=self.backbone_grad)
+        if self.task != "hgqa":
+            self.engine.backward(ctx, None, None, None, need_dvisn=self.backbone_grad, d_logit=d_hg)
+            if self.world_size > 1:
+                self.all_reduce_grads()
+        elif self.world_size == 1:
+            self.engine.backward(ctx, d_hg, d_rel, d_act, need_dvisn=self.backbone_grad)
+        else:
+            st = self.store
+            self.engine.backward_late_params(ctx, d_hg, d_rel, d_act)
+            works = self._reduce_async([st.bucket_late])
+            self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=0, join=False)
+            works += self._reduce_async(st.bucket_early_upper)
+            self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=1)
+            works += self._reduce_async(st.bucket_early_rest)
+            for w in works:
+                w.wait()                                   # stream-level: the optimiser waits for NCCL's stream
         self.d_feat = ctx.get("d_feat")      # gradient wrt the backbone features (backbone_grad runs)
-        self.all_reduce_grads()
         self.optimizer_step(lr_on_device)
         return out, scal
 
     # ------------------------------------------------------------------ CUDA-graph step
+    def _snapshot_state(self):
+        st, live = self.store, self.store.live_extent
+        return dict(master=st.master[live].clone(), m=self.exp_avg[live].clone(), v=self.exp_avg_sq[live].clone(),
+                    seed=self.engine.drop_seed.clone(), step=self.step_count)
+
+    def _restore_state(self, snap):
+        st, live = self.store, self.store.live_extent
+        st.master[live].copy_(snap["master"])
+        self.exp_avg[live].copy_(snap["m"])
+        self.exp_avg_sq[live].copy_(snap["v"])
+        self.engine.drop_seed.copy_(snap["seed"])
+        self.step_count = snap["step"]
+        st.grad.zero_()
+        st.refresh_shadow()
+        self.engine.refresh_derived()
+
     def capture(self, inp, batch, warmup=3):
-        """Capture one whole training step (≈830 launches on three streams, the NCCL all-reduce included) into a
-        CUDA graph over STATIC input buffers.  The eager path is launch-bound on the host (≈17 ms of Python/ctypes
-        enqueue per step vs ≈18 ms of GPU work); the replay is one launch.  lr is read from device memory so the
-        warm-up schedule keeps working; new batches are copied into the static buffers before each replay."""
+        """Capture one whole training step (≈650 launches on several streams; for world_size > 1 the three NCCL
+        all-reduces too) into ONE CUDA graph over STATIC input buffers.  The eager path is launch-bound on the
+        host; the replay is one launch.  lr is read from device memory so the warm-up schedule keeps working; new
+        batches are copied into the static buffers before each replay.
+        Capturing has no side effect on the training state: the eager steps that warm the allocator, the
+        TMA-descriptor cache and NCCL are real optimiser steps, so weights, Adam moments, the dropout seed and the
+        step count are snapshotted before and restored after (the reference's trajectory, tasks/agqaHGQA.py:390-392,
+        continues exactly where it was)."""
         self._ensure_opt_state()
         from . import _lib
+        snap = self._snapshot_state()
         l0 = _lib.launch_count
         self.train_step(inp, batch)
         self.launches_per_step = _lib.launch_count - l0
@@ -264,29 +374,12 @@ class HotPathTrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.graph_opt = None
-        if self.world_size == 1:
-            with torch.cuda.graph(self.graph):
-                self.static_out, self.static_scal = self.train_step(self.static_inp, self.static_batch,
-                                                                    lr_on_device=True)
-        else:
-            # data-parallel: [forward + loss + first half of backward] | async NCCL all-reduce of the gradients that
-            # are already final | [second half of backward] | all-reduce of the rest | [optimiser]
-            with torch.cuda.graph(self.graph):
-                self._advance_seed()
-                out, ctx = self.engine.forward(self.static_inp, train=True)
-                scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, self.static_batch)
-                self.engine.backward_late_params(ctx, d_hg, d_rel, d_act)
-                self.static_out, self.static_scal = out, scal
-            self.graph_bwd2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_bwd2, pool=self.graph.pool()):
-                self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=0)
-            self.graph_bwd3 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_bwd3, pool=self.graph.pool()):
-                self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=1)
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
-                self.optimizer_step(lr_on_device=True)
+        # thread_local: NCCL's watchdog thread keeps polling its events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.static_out, self.static_scal = self.train_step(self.static_inp, self.static_batch,
+                                                                lr_on_device=True)
+        self._restore_state(snap)
+        torch.cuda.synchronize()
         return self.graph
 
     def train_step_graph(self, inp=None, batch=None):
@@ -300,17 +393,6 @@ class HotPathTrainer:
                 self.static_batch[k].copy_(v, non_blocking=True)
         self._push_lr()
         self.graph.replay()
-        if self.graph_opt is not None:
-            import torch.distributed as dist
-            st = self.store
-            works = [dist.all_reduce(st.grad[st.bucket_late], group=self.pg, async_op=True)]   # under graph_bwd2/3
-            self.graph_bwd2.replay()                       # upper language / relation layers
-            works += [dist.all_reduce(st.grad[sl], group=self.pg, async_op=True) for sl in st.bucket_early_upper]
-            self.graph_bwd3.replay()                       # lower layers, embeddings (, front-end)
-            works += [dist.all_reduce(st.grad[sl], group=self.pg, async_op=True) for sl in st.bucket_early_rest]
-            for w in works:
-                w.wait()
-            self.graph_opt.replay()
         self.step_count += 1
         return self.static_out, self.static_scal
 

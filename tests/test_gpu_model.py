@@ -19,6 +19,16 @@ def rel_l2(a, b):
 
 
 @pytest.fixture(scope="module")
+def autocast_err():
+    """Errors of the oracle run under torch.autocast(bf16) against the same golden vectors (SURVEY.md §8c's
+    yardstick: "<= 2x the error of torch.autocast(bf16) on the same module"); tools/gen_autocast_baseline.py."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "autocast_bf16_err.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
 def run(oracle_weights, inputs_b2, golden_hgqa):
     from oracle import shg_oracle as so
     from shg_vqa_b200.trainer import HotPathTrainer, csr_targets
@@ -52,13 +62,17 @@ def run(oracle_weights, inputs_b2, golden_hgqa):
     return tr, out, scal.clone(), own
 
 
-def test_forward_activations_and_logits(run, golden_hgqa):
+def test_forward_activations_and_logits(run, golden_hgqa, autocast_err):
     tr, out, _, _ = run
     g = golden_hgqa
     lang_l = out["lang_l"].float().cpu().view(2, 40, 768)
     visn_r = out["visn_r"].float().cpu().view(2, 393, 768)
-    assert rel_l2(lang_l, torch.from_numpy(g["lang_l"])) <= 2e-2
-    assert rel_l2(visn_r[:, ::4], torch.from_numpy(g["visn_r"])) <= 2e-2
+    e_l, e_v = rel_l2(lang_l, torch.from_numpy(g["lang_l"])), rel_l2(visn_r[:, ::4], torch.from_numpy(g["visn_r"]))
+    print("activation rel-L2 vs the reference: lang_l %.4f (autocast bf16: %.4f), visn_r %.4f (autocast: %.4f)"
+          % (e_l, autocast_err["fwd_rel_l2"]["lang_l"], e_v, autocast_err["fwd_rel_l2"]["visn_r"]))
+    assert e_l <= 2e-2 and e_v <= 2e-2
+    # no worse than 2x what torch.autocast(bf16) does to the same stack
+    assert e_l <= 2 * autocast_err["fwd_rel_l2"]["lang_l"] and e_v <= 2 * autocast_err["fwd_rel_l2"]["visn_r"]
     for name in ("logit", "rel_logits", "act_logits", "hg_logit"):
         mine = out[name].float().cpu().reshape(g[name].shape)
         ref = torch.from_numpy(g[name])
@@ -106,8 +120,9 @@ def test_matcher_exact_on_reference_logits(golden_hgqa, inputs_b2):
             assert np.array_equal(cols[f, :k], g[fam + "_cols"][f, :k])
 
 
-def test_gradients(run, golden_hgqa):
+def test_gradients(run, golden_hgqa, autocast_err):
     tr, _, _, _ = run
+    ac = autocast_err["grad_norm_rel_err"]
     g = golden_hgqa
     st = tr.store
     names = [str(n) for n in g["grad_names"]]
@@ -129,10 +144,14 @@ def test_gradients(run, golden_hgqa):
             # These 8 tensors are fed ONLY by the gradient w.r.t. the per-query position input of the decoders,
             # i.e. by differences BETWEEN queries.  At this (random-init-like) operating point the decoder states
             # of different queries differ by 0.5 % (measured: |V - mean V| / |V| = 0.0055 in the self-attention
-            # values), which is the resolution of bf16 (2^-8), so that signal is quantisation-dominated for any bf16
-            # activation path; the kernels themselves reproduce torch-fp32 autograd on the same bf16 inputs to 0.3 %
-            # (tools/debug_dq.py, DESIGN.md "Numerics").  Bounded to a factor 2.5 here, 5 % everywhere else.
-            assert ref / 2.5 <= mine <= ref * 2.5, (n, mine, ref)
+            # values), which is the resolution of bf16 (2^-8), so that signal is quantisation-dominated for ANY bf16
+            # activation path: the oracle itself under torch.autocast(bf16) is off by 62 % / 31 % / 21 % / 13 % /
+            # 12 % / 6 % on them and by <= 1.3 % on every other tensor (tests/golden/autocast_bf16_err.json).
+            # SURVEY §8c's rule is the bound: no worse than 2x the autocast error (floor: the 5 % of the rest).
+            err = abs(mine - ref) / ref
+            bound = max(2.0 * ac[n], 5e-2)
+            print("   query-embed gradient %-55s err %.3f  autocast(bf16) %.3f  bound %.3f" % (n, err, ac[n], bound))
+            assert err <= bound, (n, mine, ref, err, ac[n])
             continue
         rel = abs(mine - ref) / max(ref, 1e-6)
         worst.append((rel, n, mine, float(ref)))
@@ -217,7 +236,7 @@ def test_compat_model_forward_from_backbone_features(oracle_weights, inputs_b2, 
     from shg_vqa_b200.compat import AGQAHotPath
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = False
-    model = AGQAHotPath(171, num_queries=128, num_classes=456, num_actions=157)
+    model = AGQAHotPath(171, num_queries=128, num_classes=456, num_actions=157).eval()
     model.load_state_dict(oracle_weights, strict=True)
     i = {k: v.to(dev) for k, v in inputs_b2.items() if torch.is_tensor(v)}
     logit, rel, act, hg_logit, attn = model(i["feat"], i["boxes"], i["input_ids"], i["input_mask"], i["segment_ids"],
@@ -239,7 +258,7 @@ def test_vqa_eval_forward_config4(oracle_weights, inputs_b2):
     from shg_vqa_b200.compat import AGQAHotPath
     dev = torch.device("cuda:0")
     gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vqa_b2.npz"))
-    model = AGQAHotPath(171, task="vqa")
+    model = AGQAHotPath(171, task="vqa").eval()
     sd = {k: v for k, v in oracle_weights.items() if k in model.key_shapes}
     assert len(sd) == 324
     model.load_state_dict(sd, strict=True)
@@ -291,3 +310,111 @@ def test_star_shaped_decoder_matcher_stress_config5():
     o = so.agqa_forward(w, sub)
     mine = out["rel_logits"].float().cpu().reshape(B, 128, 564)[:2]
     assert float((mine - o["rel_logits"]).abs().max()) <= 3e-2 * float(o["rel_logits"].abs().max())
+
+
+def test_answer_argmax_agreement_bs32(oracle_weights):
+    """north_star: "answer-argmax and loss agreement reported".  B = 32 synthetic clips through the CUDA path and
+    through the fp32 oracle (CPU): top-1 agreement of `hg_logit` and `logit`, overall and on the samples whose fp32
+    top-2 margin exceeds twice the logit tolerance (3e-2 * max|logit|) — there it must be 100 %; on the
+    rest (random-init logits are near-flat) a flip is within tolerance and the rate is only reported."""
+    from oracle import shg_oracle as so
+    from shg_vqa_b200.synthetic import make_inputs
+    from shg_vqa_b200.trainer import HotPathTrainer
+    dev = torch.device("cuda:0")
+    tr = HotPathTrainer(dev, frontend=True)
+    tr.load_state_dict(oracle_weights, strict=True)
+    raw = make_inputs(32, seed=4321, with_feat=True)
+    inp = {k: raw[k].to(dev) for k in ("feat", "input_ids", "input_mask", "segment_ids", "rel_segment_ids",
+                                       "act_segment_ids")}
+    out = tr.eval_step(inp)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = so.agqa_forward(oracle_weights, raw)
+    for name in ("hg_logit", "logit"):
+        r = ref[name]
+        mine = out[name].float().cpu().reshape(r.shape)
+        tol = 3e-2 * float(r.abs().max())
+        assert float((mine - r).abs().max()) <= tol, name
+        top2 = r.topk(2, dim=1).values
+        margin = top2[:, 0] - top2[:, 1]
+        agree = mine.argmax(1) == r.argmax(1)
+        clear = margin > 2 * tol
+        print("%s: answer-argmax agreement %d / %d overall; %d / %d on samples with fp32 top-2 margin > 2 x tol (%.4f)"
+              % (name, int(agree.sum()), len(agree), int(agree[clear].sum()), int(clear.sum()), 2 * tol))
+        assert bool(agree[clear].all())
+    # loss agreement at B = 32 (own matching on each side)
+    from shg_vqa_b200.trainer import csr_targets
+    batch = {"target": raw["target"].to(dev)}
+    batch["rel_labels"], batch["rel_off"] = csr_targets(raw["rel_labels"], dev)
+    batch["act_labels"], batch["act_off"] = csr_targets(raw["act_labels"], dev)
+    scal, _, _, _, _ = tr.loss_and_grads(out, batch, want_grad=False)
+    mine = tr.losses_from_scalars(scal)
+    want = so.hgqa_total_loss(ref, raw)
+    for k in ("qa", "rel_ce", "act_ce", "total"):
+        w = float(want[k])
+        print("loss %-6s cuda %.5f  oracle %.5f  rel err %.2e" % (k, mine[k], w, abs(mine[k] - w) / abs(w)))
+        assert abs(mine[k] - w) <= 1e-2 * abs(w), (k, mine[k], w)
+
+
+def test_matcher_end_to_end_on_peaked_logits():
+    """A trained-like operating point: every frame's targets have a clearly preferred query (logit margin >> bf16
+    resolution).  bf16 logits -> device matcher must then agree with fp32 logits -> the oracle's scipy-equivalent
+    solver on >= 99 % of the frames (at the random-init point of the golden run, near-tied costs flip legitimately
+    and agreement is only reported, test_matching_and_losses)."""
+    from oracle import shg_oracle as so
+    from shg_vqa_b200 import ops
+    from shg_vqa_b200.synthetic import make_inputs
+    from shg_vqa_b200.trainer import csr_targets
+    dev = torch.device("cuda:0")
+    B = 16
+    raw = make_inputs(B, seed=99, with_feat=False, visn_tokens=False)
+    g = torch.Generator().manual_seed(5)
+    for fam, q_f, n_cls in (("rel", 8, 457), ("act", 3, 158)):
+        labels = raw[fam + "_labels"]
+        lg = torch.randn(B * 16, q_f, n_cls, generator=g)
+        for f, lab in enumerate(labels):
+            perm = torch.randperm(q_f, generator=g)[:len(lab)]
+            for j, c in enumerate(lab.tolist()):
+                lg[f, perm[j], c] += 6.0 + 2.0 * float(torch.rand((), generator=g))
+        ref = so.hungarian_match(lg.view(B, 16 * q_f, n_cls), labels)
+        noisy = (lg * (1.0 + 2.0 ** -8 * torch.randn(lg.shape, generator=g))).to(torch.bfloat16).to(dev)
+        lab, off = csr_targets(labels, dev)
+        m = ops.match_from_logits(noisy.view(-1, n_cls), lab, off, q_f)
+        rows, cols, n = m["rows"].cpu().numpy(), m["cols"].cpu().numpy(), m["n_match"].cpu().numpy()
+        same = sum(np.array_equal(rows[f, :n[f]], r.numpy()) and np.array_equal(cols[f, :n[f]], c.numpy())
+                   for f, (r, c) in enumerate(ref))
+        print("%s: %d / %d frames identical on peaked logits" % (fam, same, len(ref)))
+        assert same >= 0.99 * len(ref), (fam, same, len(ref))
+
+
+def test_matcher_flags_bad_labels_and_nan(golden_hgqa, inputs_b2):
+    """A label >= n_cls (IndexError in the reference, matcher.py:73) and NaN logits (scipy ValueError) are never
+    dereferenced / never silently trained on: status -4 / -2, and the loss read raises."""
+    from shg_vqa_b200 import ops
+    from shg_vqa_b200.compat import HungarianMatcher
+    from shg_vqa_b200.trainer import HotPathTrainer, csr_targets
+    dev = torch.device("cuda:0")
+    lg = torch.from_numpy(golden_hgqa["rel_logits"]).to(dev)
+    labels = [l.clone() for l in inputs_b2["rel_labels"]]
+    f_bad = next(i for i, l in enumerate(labels) if len(l) > 0)
+    labels[f_bad][0] = 457                                      # one past the last class
+    lab, off = csr_targets(labels, dev)
+    m = ops.match_from_logits(lg.view(-1, 457), lab, off, 8)
+    st = m["status"].cpu()
+    assert int(st[f_bad]) == -4 and int((st != 0).sum()) == 1
+    scal = torch.zeros(16, device=dev)
+    ops.set_loss_fwd(lg.view(-1, 457), m, 0.1, out=scal[1:5], err_out=scal[10:11])
+    with pytest.raises(ValueError):
+        HotPathTrainer.losses_from_scalars(scal)
+    targets = [{"labels": [l.to(dev) for l in labels[b * 16:(b + 1) * 16]]} for b in range(2)]
+    with pytest.raises(IndexError):
+        HungarianMatcher(1, True, 16)({"pred_logits": lg}, targets)
+    # NaN logits in one frame
+    lg2 = lg.clone()
+    lg2.view(-1, 457)[f_bad * 8 + 1, 5] = float("nan")
+    lab, off = csr_targets(inputs_b2["rel_labels"], dev)
+    m = ops.match_from_logits(lg2.view(-1, 457), lab, off, 8)
+    assert int(m["status"].cpu()[f_bad]) == -2
+    targets = [{"labels": [l.to(dev) for l in inputs_b2["rel_labels"][b * 16:(b + 1) * 16]]} for b in range(2)]
+    with pytest.raises(ValueError):
+        HungarianMatcher(1, True, 16)({"pred_logits": lg2}, targets)

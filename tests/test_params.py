@@ -114,3 +114,40 @@ def test_data_parallel_buckets_tile_the_live_span():
         assert in_upper(e + "embeddings.word_embeddings.weight") and in_upper(e + "embeddings.LayerNorm.bias")
         assert not in_upper(e + "encoder.r_layers.1.output.dense.weight")
         assert not in_upper(e + "encoder.layer.0.output.dense.bias")
+
+
+def test_param_tree_mirrors_reference_module_names(key_shapes):
+    """compat.build_param_tree: the nn.Module view of the flat store has exactly the reference's state_dict keys in
+    the reference's order, its 576 de-duplicated parameters, aliases sharing one Parameter, and strict loading
+    writes through to the flat master buffer (what the engine and the fused optimiser read)."""
+    import torch
+    from shg_vqa_b200.compat import _Node, build_param_tree
+    from shg_vqa_b200.params import ParamStore, build_key_shapes, canonical_key
+    ks = build_key_shapes("hgqa", 171, 457, 158)
+    st = ParamStore(ks, "cpu", with_grad=True)
+    root = _Node()
+    params = build_param_tree(root, st, ks)
+    sd = root.state_dict()
+    assert list(sd) == list(key_shapes)
+    assert len(list(root.parameters())) == 576 == len(params)
+    named = dict(root.named_parameters(remove_duplicate=False))
+    e = "lxrt_encoder.model.bert.encoder."
+    assert named[e + "x_layers.0.visn_inter.dense.weight"] is named[e + "cross_attn_layer.cross.visn_inter.dense.weight"]
+    assert named[e + "x_layers.1.visn_inter.dense.weight"] is named[e + "cross_attn_layer.cross.visn_inter.dense.weight"]
+    assert hasattr(root.lxrt_encoder, "load") and root.lxrt_encoder.dim == 768
+    g = torch.Generator().manual_seed(3)
+    new = {}
+    for k, v in sd.items():
+        ck = canonical_key(k)
+        if ck not in new:
+            new[ck] = torch.randn(v.shape, generator=g) if v.is_floating_point() else v.clone()
+        new[k] = new[ck]
+    root.load_state_dict({"module." + k if False else k: v for k, v in new.items()}, strict=True)
+    for k in ("logit_fc.3.weight", e + "visn_fc.conv.4.weight", "rel_decoder.layers.2.self_attn.in_proj_weight"):
+        assert torch.equal(st.p(k), new[k]), k
+    # a gradient view attached to a Parameter aliases the flat gradient buffer
+    p = named["logit_fc.3.bias"]
+    p.grad = st.g("logit_fc.3.bias")
+    p.grad.fill_(2.0)
+    off, n, _ = st.offsets["logit_fc.3.bias"]
+    assert float(st.grad[off:off + n].sum()) == 2.0 * n

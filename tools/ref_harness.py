@@ -1,9 +1,11 @@
 """Import the UNMODIFIED reference (read-only at /root/reference) on CPU.
 
-Test infrastructure only.  Runs in the build container, never on the GPU box
-(/root/reference does not exist there).  Used by tools/gen_golden.py to emit the
-golden vectors under tests/golden/ and by tests/test_oracle_vs_reference.py
-(skipped when /root/reference is absent).
+Test infrastructure only.  Used by tools/gen_golden.py (build container, reads
+/root/reference) to emit the golden vectors under tests/golden/, and by
+tests/test_gpu_training_boundary.py::test_reference_train_loop_on_hot_path, which
+runs the reference's unmodified train loop on the GPU box from a copy staged by
+tools/stage_reference.py under baseline/_ref/ (git-ignored; the test skips when
+neither location exists).  Nothing in the product path imports this module.
 
 Recipe: set sys.argv to the README flags before importing
 src.param (param.py:201 parses at import); stub the unused third-party imports
@@ -16,7 +18,10 @@ import os
 import sys
 import types
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_ROOT = "/root/reference/AGQA"
+if not os.path.isdir(os.path.join(REF_ROOT, "src")):
+    REF_ROOT = os.path.join(_REPO, "baseline", "_ref", "AGQA")      # staged copy (tools/stage_reference.py)
 
 README_FLAGS = [
     "--llayers", "5", "--xlayers", "2", "--rlayers", "5", "--noCaps",
