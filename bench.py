@@ -8,15 +8,23 @@ A "step" is one full pass of the hot path over one synthetic AGQA-shaped batch (
 5 language + 5 relation layers, the 2 shared LXRT cross layers + pooler + answer head (forward only, as in the
 reference's --taskHGQA training), both 5-layer hypergraph decoders, heads, the hypergraph x question encoder,
 per-frame Hungarian matching, set loss + answer loss, the whole backward, the NCCL gradient all-reduce (N>1),
-grad-norm clipping and BertAdam.  The slow_r50 backbone and the Conv3d front-end stay on stock PyTorch and are
-OUTSIDE the measured path (SURVEY.md §8a V*, §2 #9): the step starts from the [B,393,768] visual tokens.
+grad-norm clipping and BertAdam.  The slow_r50 backbone stays on stock PyTorch and is OUTSIDE the measured path
+(SURVEY.md §8a V*, §2 #9): the headline step starts from the [B,393,768] visual tokens; the same step started from
+the backbone's features (through the Conv3d front-end kernels) and from raw clips (through a stock slow_r50) are
+reported beside it as `with_frontend` / `with_backbone`.
+
+Where the per-kernel numbers come from: CUPTI kernel records (torch.profiler) of ONE REPLAY of the captured step —
+pure device durations inside the real step, no host enqueue gaps — summed per kernel family; the per-shape table of
+the dominant family comes from CUPTI records of one eager step joined to the launch order through correlation
+ids.  `roofline.traffic` is parsed from the committed `ncu --set full` capture under profiles/ (never a constant).
 """
 import argparse
+import csv
+import glob
 import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -25,9 +33,18 @@ if ROOT not in sys.path:
 
 BATCH_PER_GPU = 32
 TRAIN_GFLOP_PER_CLIP = 199.3      # 3 x 62.29 (fwd+bwd blocks) + 12.45 (forward-only LXRT x-layers)
+FWD_GFLOP_PER_CLIP = 74.74
+METRIC = "train clips/sec at bs32/GPU (hot path)"
 WORKLOAD = ("AGQA taskHGQA hot-path train step, bs32/GPU, from [B,393,768] visual tokens + question ids: "
             "l5/r5/x2 LXRT stack, 2x5-layer hypergraph decoders, heads, CrossEncoder, per-frame Hungarian matching, "
-            "set+answer loss, backward, grad clip, BertAdam (slow_r50 excluded: stock PyTorch; the same step started from backbone features through the Conv3d front-end is reported as with_frontend)")
+            "set+answer loss, backward, grad clip, BertAdam (slow_r50 excluded: stock PyTorch; the same step started from "
+            "backbone features through the Conv3d front-end is reported as with_frontend)")
+
+
+def base_config(world):
+    """The workload description both arms (ours / --impl reference) print."""
+    return {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU * world, "per_gpu_batch": BATCH_PER_GPU,
+            "parallelism": "dp%d" % world}
 
 
 def read_peaks():
@@ -47,7 +64,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.stop_flag = index, None, False
+        self.index, self.proc = index, None
 
     def start(self):
         try:
@@ -79,22 +96,164 @@ class ClockSampler:
                 "power_w_max": max(float(s[2]) for s in samples), "samples": len(sm)}
 
 
-def make_batch(seed, pin):
+def make_batch(seed, pin, batch=BATCH_PER_GPU, **kw):
     import torch
     from shg_vqa_b200.synthetic import make_inputs
     from shg_vqa_b200.trainer import csr_from_padded
-    raw = make_inputs(BATCH_PER_GPU, seed=seed, with_feat=False, visn_tokens=True)
+    raw = make_inputs(batch, seed=seed, with_feat=False, visn_tokens=True, **kw)
     inp = {k: raw[k] for k in ("input_ids", "input_mask", "segment_ids", "rel_segment_ids", "act_segment_ids")}
     inp["visn_tokens"] = raw["visn_tokens"].reshape(-1, 768).to(torch.bfloat16)
-    batch = {"target": raw["target"]}
-    batch["rel_labels"], batch["rel_off"] = csr_from_padded(raw["rel_tokens"], raw["rel_lengths"])
-    batch["act_labels"], batch["act_off"] = csr_from_padded(raw["act_tokens"], raw["act_lengths"])
+    b = {"target": raw["target"]}
+    b["rel_labels"], b["rel_off"] = csr_from_padded(raw["rel_tokens"], raw["rel_lengths"])
+    b["act_labels"], b["act_off"] = csr_from_padded(raw["act_tokens"], raw["act_lengths"])
     if pin:
         inp = {k: v.contiguous().pin_memory() for k, v in inp.items()}
-        batch = {k: v.contiguous().pin_memory() for k, v in batch.items()}
-    return inp, batch
+        b = {k: v.contiguous().pin_memory() for k, v in b.items()}
+    return inp, b
 
 
+# ----------------------------------------------------------------------------------------- CUPTI kernel records
+# kernel-name fragment -> the C-ABI entry point that launches it (the key of the `kernels` table)
+FAMILIES = [("gemm_kernel", "shg_gemm"), ("gemm2_kernel", "shg_gemm"), ("attn_fwd", "shg_attn_fwd"),
+            ("attn_bwd", "shg_attn_bwd"), ("layernorm_fwd", "shg_layernorm_fwd_grouped"),
+            ("layernorm_bwd", "shg_layernorm_bwd_grouped"), ("colsum", "shg_colsum_accum"),
+            ("bert_adam", "shg_bert_adam_step"), ("grad_sumsq", "shg_grad_sumsq"), ("copy3d", "shg_copy3d"),
+            ("embed_scatter", "shg_embed_scatter_bwd"), ("embed_ln", "shg_embed_ln_fwd"), ("f32_to_bf16", "shg_f32_to_bf16"),
+            ("act_bwd", "shg_act_bwd"), ("match_from_logits", "shg_match_from_logits"), ("set_loss_fwd", "shg_set_loss_fwd"),
+            ("set_loss_bwd", "shg_set_loss_bwd"), ("bce_logits", "shg_bce_logits"), ("conv_gemm", "shg_conv3d"),
+            ("conv_wgrad", "shg_conv3d"), ("ncs_to_nsc", "shg_layout"), ("nsc_to_ncs", "shg_layout"),
+            ("frontend_", "shg_frontend"), ("add_rows", "shg_add_rows"), ("nccl", "nccl")]
+
+
+def family_of(kernel_name):
+    for frag, fam in FAMILIES:
+        if frag in kernel_name:
+            return fam
+    return "torch (memset / copies)"
+
+
+def cupti_records(fn):
+    """Runs fn() under torch.profiler; returns (kernel records sorted by start, launch-ordered correlation ids).
+    A kernel record is (start_us, dur_us, name, correlation id)."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    kernels, launches = [], []
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            if e.time_range.end > e.time_range.start and "memcpy" not in e.name.lower() and "memset" not in e.name.lower():
+                kernels.append((e.time_range.start, e.time_range.end - e.time_range.start, e.name, e.id))
+        elif e.name.startswith(("cudaLaunchKernel", "cuLaunchKernel")):
+            launches.append((e.time_range.start, e.id))
+    kernels.sort()
+    launches.sort()
+    return kernels, [cid for _, cid in launches]
+
+
+def kernel_table_from_replay(tr, work_by_entry):
+    """CUPTI durations of one graph replay summed per entry point + the step's concurrency profile."""
+    import torch
+    for _ in range(2):
+        tr.train_step_graph()
+    torch.cuda.synchronize()
+    kernels, _ = cupti_records(tr.train_step_graph)
+    agg = {}
+    for s, d, name, _ in kernels:
+        a = agg.setdefault(family_of(name), dict(launches=0, us=0.0))
+        a["launches"] += 1
+        a["us"] += d
+    t0, t1 = kernels[0][0], max(s + d for s, d, _, _ in kernels)
+    pts = sorted([(s, 1) for s, d, _, _ in kernels] + [(s + d, -1) for s, d, _, _ in kernels])
+    conc, last, hist = 0, t0, {}
+    for t, dd in pts:
+        if t > last:
+            hist[conc] = hist.get(conc, 0.0) + (t - last)
+        conc += dd
+        last = t
+    total = sum(a["us"] for a in agg.values())
+    # NCCL time that no compute kernel covers (the exposed part of the path's one collective)
+    ev = sorted([(s, 0, "nccl" in n) for s, d, n, _ in kernels] + [(s + d, 1, "nccl" in n) for s, d, n, _ in kernels])
+    n_nccl = n_comp = 0
+    last, nccl_us, exposed_us = t0, 0.0, 0.0
+    for t, end, is_nccl in ev:
+        if t > last:
+            if n_nccl:
+                nccl_us += t - last
+                if not n_comp:
+                    exposed_us += t - last
+        last = t
+        if is_nccl:
+            n_nccl += -1 if end else 1
+        else:
+            n_comp += -1 if end else 1
+    table = {}
+    for fam, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        w = work_by_entry.get(fam)
+        row = dict(launches=a["launches"], ms=round(a["us"] * 1e-3, 3), share=round(a["us"] / total, 3))
+        if w is not None and w["work"] > 0:
+            unit = 1e12 if w["kind"] == "tensor" else 1e9
+            row["rate"] = round(w["work"] / (a["us"] * 1e-6) / unit, 1)
+            row["unit"] = "TFLOP/s" if w["kind"] == "tensor" else "GB/s"
+            row["bound"] = w["kind"]
+        table[fam] = row
+    prof = {"kernels_in_replay": len(kernels), "span_ms": round((t1 - t0) * 1e-3, 3),
+            "sum_of_kernel_durations_ms": round(total * 1e-3, 3),
+            "ms_at_concurrency": {str(k): round(v * 1e-3, 3) for k, v in sorted(hist.items())}}
+    if nccl_us:
+        prof["nccl_active_ms"] = round(nccl_us * 1e-3, 3)
+        prof["nccl_exposed_ms"] = round(exposed_us * 1e-3, 3)
+    return table, prof
+
+
+def shape_table_from_eager(tr, inp, batch, entry):
+    """Per-shape times of `entry` (e.g. shg_gemm): CUPTI kernel durations of one EAGER step, attributed to the
+    calls through the launch order (correlation ids).  Returns [] if the join does not line up."""
+    from shg_vqa_b200 import _lib
+    prof = _lib.Profiler()
+    _lib.profiler = prof
+    try:
+        kernels, order = cupti_records(lambda: tr.train_step(inp, batch))
+    finally:
+        _lib.profiler = None
+    by_cid = {cid: (d, name) for _, d, name, cid in kernels if "shg::" in name}
+    ordered = [by_cid[c] for c in order if c in by_cid]
+    need = sum(r[5] for r in prof.calls)
+    if need != len(ordered):
+        return [], "launch-order join failed: %d kernels expected, %d recorded" % (need, len(ordered))
+    agg, i = {}, 0
+    for name, kind, work, tag, _, n_k in prof.calls:
+        d = sum(x[0] for x in ordered[i:i + n_k])
+        i += n_k
+        if name == entry:
+            a = agg.setdefault(tag, dict(calls=0, us=0.0, work=0.0, kind=kind))
+            a["calls"] += 1
+            a["us"] += d
+            a["work"] += work
+    return agg, None
+
+
+def ncu_traffic(pattern):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest committed `ncu --page raw --csv`
+    export matching profiles/<pattern>; (bytes, file, kernel name, duration_us) or None."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)), key=os.path.getmtime)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in reversed(files):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units, data = rows[0], rows[1], rows[2:]
+            ir, iw, ik, it = (hdr.index(c) for c in ("dram__bytes_read.sum", "dram__bytes_write.sum", "Kernel Name",
+                                                      "gpu__time_duration.sum"))
+            tot = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in data]
+            dur = [float(r[it]) * {"us": 1.0, "ms": 1e3, "ns": 1e-3}.get(units[it], 1.0) for r in data]
+            return sum(tot) / len(tot), os.path.relpath(path, ROOT), data[0][ik].split("(")[0], sum(dur) / len(dur)
+        except Exception:
+            continue
+    return None
+
+
+# ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -131,7 +290,7 @@ def run_ours(args):
         return float(t[0])
 
     # ---------------------------------------------------------------- device-resident throughput (`value`)
-    # the step (≈830 launches over three streams) is captured once into a CUDA graph and replayed
+    # the step (~650 launches over several streams, the NCCL all-reduces included) is captured once and replayed
     step_fn = (lambda: tr.train_step(inp, batch))
     if not args.eager:
         tr.capture(inp, batch)
@@ -149,116 +308,266 @@ def run_ours(args):
         out, scal = step_fn()
     e.record()
     barrier()
+    clocks = sampler.summary() if rank == 0 else None       # sampled over the timed region only
     launches = _lib.launch_count - l0
     if not args.eager:
-        launches = tr.launches_per_step * args.steps        # kernels inside the replayed graph(s)
+        launches = tr.launches_per_step * args.steps        # kernels inside the replayed graph
     ms_step = max_over_ranks(s.elapsed_time(e) / args.steps)
     losses = tr.losses_from_scalars(scal)
 
     # ---------------------------------------------------------------- end to end from pinned host buffers (`e2e`)
-    for _ in range(2):                              # untimed: staging buffers, copy stream, pinned loss slots
-        tr.train_step_host(h_inp, h_batch, next_inp=h_inp, next_batch=h_batch, lagged=True)
-    tr.drain_losses()
-    barrier()
-    t0 = time.perf_counter()
-    s.record()
-    n_read = 0
-    for _ in range(args.steps):
-        # H2D of this step's inputs + step + D2H of the loss sums, every step.  The H2D of the FOLLOWING step's inputs
-        # (the same pinned buffers here, a data loader's next batch in use) is started on a copy stream while this
-        # step computes, and each step's loss is read back asynchronously and handed out one call later (as a training
-        # loop that logs a lagged loss does): every step's inputs cross PCIe once and every step's result reaches the
-        # host inside the timed region.
-        n_read += tr.train_step_host(h_inp, h_batch, next_inp=h_inp, next_batch=h_batch, lagged=True) is not None
-    n_read += tr.drain_losses() is not None
-    assert n_read == args.steps, n_read
-    e.record()
-    barrier()
-    e2e_ms = max_over_ranks(max(s.elapsed_time(e), (time.perf_counter() - t0) * 1e3) / args.steps)
+    e2e_ms = None
+    if not args.eager:
+        for _ in range(2):                          # untimed: staging buffers, copy stream, pinned loss slots
+            tr.train_step_host(h_inp, h_batch, next_inp=h_inp, next_batch=h_batch, lagged=True)
+        tr.drain_losses()
+        barrier()
+        t0 = time.perf_counter()
+        s.record()
+        n_read = 0
+        for _ in range(args.steps):
+            # H2D of this step's inputs + step + D2H of the loss sums, every step.  The H2D of the FOLLOWING step's
+            # inputs (the same pinned buffers here, a data loader's next batch in use) is started on a copy stream
+            # while this step computes, and each step's loss is read back asynchronously and handed out one call
+            # later (as a training loop that logs a lagged loss does): every step's inputs cross PCIe once and every
+            # step's result reaches the host inside the timed region.
+            n_read += tr.train_step_host(h_inp, h_batch, next_inp=h_inp, next_batch=h_batch, lagged=True) is not None
+        n_read += tr.drain_losses() is not None
+        assert n_read == args.steps, n_read
+        e.record()
+        barrier()
+        e2e_ms = max_over_ranks(max(s.elapsed_time(e), (time.perf_counter() - t0) * 1e3) / args.steps)
 
-    # ---------------------------------------------------------------- live per-kernel timing for the roofline
-    barrier()
-    prof = _lib.Profiler()
+    # ---------------------------------------------------------------- data-parallel correctness (outside the timed region)
+    dp = dp_check(tr, dev, rank, world) if world > 1 else None
+
+    # ---------------------------------------------------------------- per-kernel numbers
+    # every rank runs the same replays / eager steps (the step contains collectives); rank 0 reports
+    peaks = read_peaks()
+    prof = _lib.Profiler()                          # algorithmic work per entry point: one eager step (times unused)
     _lib.profiler = prof
     tr.train_step(inp, batch)
-    agg = prof.summary()
-    by_tag = prof.by_tag()
     _lib.profiler = None
+    torch.cuda.synchronize()
+    work = prof.work_by_entry()
+    kernels, step_profile, shapes_note = {}, None, None
+    try:
+        kernels, step_profile = kernel_table_from_replay(tr, work) if not args.eager else ({}, None)
+    except Exception as ex:                         # CUPTI unavailable: say so instead of inventing numbers
+        shapes_note = "CUPTI kernel records unavailable (%s: %s)" % (type(ex).__name__, str(ex)[:120])
+        if world > 1:
+            raise
+    ranked = [(k, v) for k, v in kernels.items() if "rate" in v]
+    roof = {"bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}
+    top = max(ranked, key=lambda kv: kv[1]["ms"])[0] if ranked else "shg_gemm"
+    agg, err = shape_table_from_eager(tr, inp, batch, top)
+    line = None
+    if rank == 0:
+        if ranked:
+            name, a = top, kernels[top]
+            peak = peaks["tensor"] if a["bound"] == "tensor" else peaks["hbm"]
+            roof = dict(bound="tensor" if a["bound"] == "tensor" else "hbm", kernel=name, achieved=a["rate"], peak=peak,
+                        unit=a["unit"], frac=round(a["rate"] / peak, 3),
+                        peak_source=peaks["src"] + (" (sustained: kernel timed inside a long step)" if a["bound"] == "tensor" else ""),
+                        timing="CUPTI kernel durations of one graph replay, summed over the %d launches" % a["launches"],
+                        launches_per_step=a["launches"], share_of_kernel_time=a["share"],
+                        avg_launch_us=round(1e3 * a["ms"] / a["launches"], 2), traffic=None)
+            tfile = {"shg_gemm": "prof_gemm_plain_r*.raw.csv", "shg_attn_fwd": "prof_attn_fwd_r*.raw.csv",
+                     "shg_attn_bwd": "prof_attn_bwd_r*.raw.csv"}.get(name)
+            t = ncu_traffic(tfile) if tfile else None
+            if t:
+                roof["traffic"] = round(t[0])
+                roof["traffic_of"] = "%s, one launch of %s (%.1f us under ncu), dram__bytes_read.sum + dram__bytes_write.sum" % (
+                    t[1], t[2], t[3])
+            if err:
+                shapes_note = err
+            shapes = []
+            for tag, x in sorted(agg.items(), key=lambda kv: -kv[1]["us"])[:10] if agg else []:
+                unit = 1e12 if x["kind"] == "tensor" else 1e9
+                r = x["work"] / (x["us"] * 1e-6) / unit
+                shapes.append(dict(shape=tag, calls=x["calls"], avg_launch_us=round(x["us"] / x["calls"], 2),
+                                   achieved=round(r, 1), frac=round(r / peak, 3)))
+            roof["largest_shapes"] = shapes
+        if shapes_note:
+            roof["note"] = shapes_note
+        clips = BATCH_PER_GPU * world
+        cfg = base_config(world)
+        cfg.update({"dropout": "off" if args.no_dropout else "train mode: hidden/attention-prob 0.1, decoders 0.15, fused counter-based masks",
+                    "launch": "eager" if args.eager else "cuda-graph replay",
+                    "l2": "no flush needed: each step streams ~5 GB of parameters/moments/activations (>> 126 MB L2)",
+                    "hot_path_tflop_per_step_per_gpu": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3, 2)})
+        if world > 1:
+            cfg["collective"] = "fp32 NCCL all-reduce of the 191 M-element live gradient span in 3 buckets, captured in the step's graph"
+        line = {
+            "metric": METRIC, "value": round(clips / (ms_step * 1e-3), 2),
+            "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "model_flops_utilisation": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3 / (ms_step * 1e-3) / peaks["tensor"], 3),
+            "kernels": kernels,
+            "step_profile": step_profile,
+            "loss": {k: round(v, 4) for k, v in losses.items()},
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": round(clips / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d),
+                           "d2h_bytes_per_step": 64, "ms_per_step": round(e2e_ms, 3)}
+        if dp is not None:
+            line["dp_check"] = dp
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = read_peaks()
-    step_ms_prof = sum(a["ms"] for a in agg.values())
-    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-    name, a = top
-    if a["kind"] == "tensor":
-        achieved = a["work"] / (a["ms"] * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel=name, achieved=round(achieved, 1), peak=peaks["tensor"], unit="TFLOP/s",
-                    frac=round(achieved / peaks["tensor"], 3), traffic=None)
-    else:
-        achieved = a["work"] / (a["ms"] * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel=name, achieved=round(achieved, 1), peak=peaks["hbm"], unit="GB/s",
-                    frac=round(achieved / peaks["hbm"], 3), traffic=None)
-    roof.update(peak_source=peaks["src"] + (" (sustained: kernel timed inside a long step)" if a["kind"] == "tensor" else ""),
-                launches_per_step=a["calls"], share_of_step=round(a["ms"] / step_ms_prof, 3),
-                avg_launch_us=round(1e3 * a["ms"] / a["calls"], 2))
-    kernels = {}
-    for n, x in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-        rate = x["work"] / (x["ms"] * 1e-3) / (1e12 if x["kind"] == "tensor" else 1e9) if x["ms"] > 0 else 0.0
-        kernels[n] = dict(calls=x["calls"], ms=round(x["ms"], 3), share=round(x["ms"] / step_ms_prof, 3),
-                          rate=round(rate, 1), unit="TFLOP/s" if x["kind"] == "tensor" else "GB/s")
-
-    # the dominant entry point is 425 launches of very different sizes: its largest shapes, each against the same peak
-    # (traffic: dram__bytes_read+write per launch from the ncu --set full captures under profiles/, where taken)
-    ncu_traffic = {"12576x3072x768 NN": 104.2e6}
-    shapes = []
-    for (n, tag), x in sorted(by_tag.items(), key=lambda kv: -kv[1]["ms"]):
-        if n != name or len(shapes) >= 8:
-            continue
-        r = x["work"] / (x["ms"] * 1e-3) / (1e12 if a["kind"] == "tensor" else 1e9)
-        shapes.append(dict(shape=tag, calls=x["calls"], avg_launch_us=round(1e3 * x["ms"] / x["calls"], 2),
-                           achieved=round(r, 1), frac=round(r / (peaks["tensor"] if a["kind"] == "tensor" else peaks["hbm"]), 3),
-                           traffic=ncu_traffic.get(tag)))
-    roof["largest_shapes"] = shapes
-
-    clips = BATCH_PER_GPU * world
-    line = {
-        "metric": "train clips/sec at bs32/GPU (hot path)", "value": round(clips / (ms_step * 1e-3), 2),
-        "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": clips, "per_gpu_batch": BATCH_PER_GPU,
-                   "parallelism": "dp%d" % world, "dropout": "off" if args.no_dropout else
-                   "train mode: hidden/attention-prob 0.1, decoders 0.15, fused counter-based masks", "launch": "eager" if args.eager else "cuda-graph replay",
-                   "l2": "no flush needed: each step streams ~5 GB of parameters/moments/activations (>> 126 MB L2)",
-                   "hot_path_tflop_per_step_per_gpu": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3, 2)},
-        "e2e": {"value": round(clips / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": 64, "ms_per_step": round(e2e_ms, 3)},
-        "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
-        "roofline": roof,
-        "model_flops_utilisation": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3 / (ms_step * 1e-3) / peaks["tensor"], 3),
-        "kernels": kernels,
-        "loss": {k: round(v, 4) for k, v in losses.items()},
-    }
-    if world == 1 and not args.no_frontend:
-        del tr
-        torch.cuda.empty_cache()
-        line["with_frontend"] = measure_with_frontend(args, dev, peaks)
+    if world == 1 and not args.eager:
+        line["fwd_ms_per_batch"] = measure_forward(tr, inp, batch, args)
+    del tr
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_extras:
+        extras = {}
+        for name, fn in (("with_frontend", lambda: measure_wider(args, dev, peaks, backbone=False)),
+                         ("with_backbone", lambda: measure_wider(args, dev, peaks, backbone=True)),
+                         ("config4_vqa_eval_bs8", lambda: measure_config4(args, dev)),
+                         ("config5_star_bs64", lambda: measure_config5(args, dev)),
+                         ("gpu_eager_reference", lambda: gpu_eager_reference(dev, ms_step))):
+            try:
+                extras[name] = fn()
+            except Exception as ex:
+                extras[name] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+            torch.cuda.empty_cache()
+        line["with_frontend"] = extras.pop("with_frontend")
+        line["extra"] = extras
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_throughput(steps=2, warmup=1)
+        if not args.no_extras:
+            line["cpu_baseline"]["other_configs"] = cpu_other_configs()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def measure_with_frontend(args, dev, peaks):
-    """The same train step started one stage earlier: from the backbone's fp32 [B,2048,16,7,7]
-    features through the Conv3d front-end as tcgen05 implicit GEMM (forward, dgrad, both wgrads; its 97 M parameters
-    join the optimiser's live span).  Reported beside the headline, which keeps the hot-path definition."""
+def measure_forward(tr, inp, batch, args):
+    """BASELINE.json's second metric, `fwd ms/batch`: forward + matching + losses of the bs32 train batch (train
+    mode: dropout on, activations saved), captured and replayed; CUDA events over args.steps replays."""
     import torch
-    from shg_vqa_b200 import _lib
+    eng = tr.engine
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            out, ctx = eng.forward(inp, train=True)
+            tr.loss_and_grads(out, batch, want_grad=False)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out, ctx = eng.forward(inp, train=True)
+        tr.loss_and_grads(out, batch, want_grad=False)
+    for _ in range(3):
+        g.replay()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(args.steps):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / args.steps
+    peaks = read_peaks()
+    del g
+    return {"value": round(ms, 3), "unit": "ms", "what": "forward + device matching + losses, bs32, train mode, graph replay",
+            "tflops": round(FWD_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3 / (ms * 1e-3), 1),
+            "frac_of_sustained_tensor_peak": round(FWD_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3 / (ms * 1e-3) / peaks["tensor"], 3)}
+
+
+def dp_check(tr, dev, rank, world):
+    """Data-parallel numerics on the hardware, outside the timed region:
+    (1) after the captured steps every rank holds bit-identical weights;
+    (2) dropout off, global CE normalisation on (the reference's nn.DataParallel normalises the weighted CE over
+        the gathered batch, tasks/agqaHGQA.py:127,223): the all-reduced gradient of `world` shards of 4 clips / world
+        equals the single-process gradient of the concatenated batch."""
+    import torch
+    import torch.distributed as dist
+    from shg_vqa_b200.trainer import HotPathTrainer
+    live = tr.store.live_extent
+    w = tr.store.master[live]
+    digest = torch.stack([w.double().sum(), w.double().abs().sum(),
+                          w.view(torch.int32).to(torch.int64).sum().double()])
+    all_d = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(all_d, digest)
+    same = all(torch.equal(all_d[0], d) for d in all_d)
+    # gradient equivalence at a small per-rank batch (eager steps, no optimiser)
+    per = 4
+    chk = HotPathTrainer(dev, world_size=world, dropout=False, global_ce_norm=True, rank=rank)
+    chk.init_weights(seed=77)
+    shards = [make_batch(4321 + r, pin=False, batch=per) for r in range(world)]
+    inp = {k: v.to(dev) for k, v in shards[rank][0].items()}
+    bat = {k: v.to(dev) for k, v in shards[rank][1].items()}
+    out, ctx = chk.engine.forward(inp, train=True)
+    _, d_hg, d_rel, d_act, _ = chk.loss_and_grads(out, bat)
+    chk.engine.backward(ctx, d_hg, d_rel, d_act)
+    chk.all_reduce_grads()
+    torch.cuda.synchronize()
+    g_dp = chk.store.grad[chk.store.live_extent] / world
+    rel = None
+    if rank == 0:
+        one = HotPathTrainer(dev, world_size=1, dropout=False)
+        one.init_weights(seed=77)
+        cat_inp = {k: torch.cat([s[0][k] for s in shards]).to(dev) for k in shards[0][0]}
+        cat_bat = {"target": torch.cat([s[1]["target"] for s in shards]).to(dev)}
+        for fam in ("rel", "act"):
+            labs = [s[1][fam + "_labels"] for s in shards]
+            offs, base = [shards[0][1][fam + "_off"][:1]], 0
+            for s_ in shards:
+                o = s_[1][fam + "_off"]
+                offs.append(o[1:] + base)
+                base += int(o[-1])
+            cat_bat[fam + "_labels"] = torch.cat(labs).to(dev)
+            cat_bat[fam + "_off"] = torch.cat(offs).to(torch.int32).to(dev)
+        out, ctx = one.engine.forward(cat_inp, train=True)
+        _, d_hg, d_rel, d_act, _ = one.loss_and_grads(out, cat_bat)
+        one.engine.backward(ctx, d_hg, d_rel, d_act)
+        torch.cuda.synchronize()
+        g_one = one.store.grad[one.store.live_extent]
+        rel = float((g_dp.double() - g_one.double()).norm() / g_one.double().norm())
+        del one
+    del chk
+    torch.cuda.empty_cache()
+    res = {"weights_identical_across_ranks": bool(same), "ranks": world,
+           "reduced_grad_vs_single_process_rel_l2": rel,
+           "how": "%d clips per rank, dropout off, global CE normalisation; tolerance 1e-4 (fp32 split-K sums in a "
+                  "different order on a %dx larger M)" % (per, world)}
+    if rank == 0:
+        assert same, "ranks hold different weights after the captured steps"
+        assert rel is not None and rel <= 1e-4, "data-parallel gradient differs from the single-process one: %g" % rel
+    return res
+
+
+def _time_graph_step(tr, inp, batch, args):
+    import torch
+    tr.capture(inp, batch)
+    for _ in range(args.warmup):
+        tr.train_step_graph()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        out, scal = tr.train_step_graph()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / args.steps, scal
+
+
+def measure_wider(args, dev, peaks, backbone):
+    """The same train step started earlier.  backbone=False: from the backbone's fp32
+    [B,2048,16,7,7] features through the Conv3d front-end as tcgen05 implicit GEMM (forward, dgrad, both wgrads; its
+    97 M parameters join the optimiser's live span).  backbone=True (§8f-4, config 2 as written): from raw clips
+    [B,3,16,224,224] through a stock-PyTorch slow_r50 (local definition, bf16 autocast + channels_last_3d, frozen in
+    eval mode as STAR runs it, star.py:87-88) whose output feeds the same step."""
+    import torch
     from shg_vqa_b200.synthetic import make_inputs
     from shg_vqa_b200.trainer import HotPathTrainer, csr_from_padded
     tr = HotPathTrainer(dev, t_total=100000, warmup=0.1, lr=1e-5, dropout=not args.no_dropout,
@@ -270,65 +579,210 @@ def measure_with_frontend(args, dev, peaks):
     batch = {"target": raw["target"].to(dev)}
     batch["rel_labels"], batch["rel_off"] = [t.to(dev) for t in csr_from_padded(raw["rel_tokens"], raw["rel_lengths"])]
     batch["act_labels"], batch["act_off"] = [t.to(dev) for t in csr_from_padded(raw["act_tokens"], raw["act_lengths"])]
-    step_fn = (lambda: tr.train_step(inp, batch))
-    if not args.eager:
-        tr.capture(inp, batch)
-        step_fn = tr.train_step_graph
-    for _ in range(args.warmup):
-        step_fn()
+    ms, scal = _time_graph_step(tr, inp, batch, args)
+    losses = tr.losses_from_scalars(scal)
+    res = {"value": round(BATCH_PER_GPU / (ms * 1e-3), 2), "unit": "clips/s", "ms_per_step": round(ms, 3),
+           "loss_total": round(losses["total"], 4)}
+    if not backbone:
+        res["workload"] = ("same step from backbone features fp32 [32,2048,16,7,7]: + layout cast, Conv3d(2048->768,(5,3,3))"
+                           "+GELU, Conv3d(768->768)+GELU, cls/position/dropout, their backward (no gradient into the "
+                           "frozen-or-stock backbone), +97 M live parameters")
+        return res
+    from shg_vqa_b200.backbone import VideoBackbone
+    g = torch.Generator().manual_seed(5)
+    clip = torch.randn(BATCH_PER_GPU, 3, 16, 224, 224, generator=g).to(dev)
+    net = VideoBackbone("slow_r50", autocast=True, freeze=True).to(dev)
+
+    def encode():
+        return net.encode(clip)
+    for _ in range(2):
+        f = encode()
+    assert tuple(f.shape) == (BATCH_PER_GPU, 2048, 16, 7, 7), tuple(f.shape)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(args.steps):
-        out, scal = step_fn()
+        f = encode()
+        tr.static_inp["feat"].copy_(f)
+        tr.train_step_graph()
+    e.record()
+    torch.cuda.synchronize()
+    ms_all = s.elapsed_time(e) / args.steps
+    res.update({"workload": "config 2 as written: raw clips fp32 [32,3,16,224,224] -> stock-PyTorch slow_r50 (bf16 autocast, "
+                            "channels_last_3d, frozen/eval as star.py:87-88, random init) -> features -> the with_frontend step",
+                "value": round(BATCH_PER_GPU / (ms_all * 1e-3), 2), "ms_per_step": round(ms_all, 3),
+                "backbone_ms": round(ms_all - ms, 3), "hot_path_and_frontend_ms": round(ms, 3)})
+    return res
+
+
+def measure_config4(args, dev):
+    """Config 4: --taskVQA eval bs8 (tasks/agqa_model.py:185-192): features -> Conv3d front-end -> language /
+    relation / cross layers -> pooler -> answer head; no decoders, no matcher; no_grad; graph replay."""
+    import torch
+    from shg_vqa_b200.synthetic import make_inputs
+    from shg_vqa_b200.trainer import HotPathTrainer
+    tr = HotPathTrainer(dev, task="vqa", frontend=True)
+    tr.init_weights(seed=9595)
+    raw = make_inputs(8, seed=4, with_feat=True)
+    inp = {k: raw[k].to(dev) for k in ("feat", "input_ids", "input_mask", "segment_ids")}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            tr.eval_step(inp)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = tr.eval_step(inp)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        g.replay()
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / args.steps
-    prof = _lib.Profiler()
-    _lib.profiler = prof
-    tr.train_step(inp, batch)
-    tags = prof.by_tag()
-    _lib.profiler = None
-    convs = {}
-    for (n, tag), x in tags.items():
-        if n.startswith("shg_conv3d"):
-            r = x["work"] / (x["ms"] * 1e-3) / 1e12
-            convs[tag] = dict(ms=round(x["ms"], 3), tflops=round(r, 1), frac=round(r / peaks["tensor"], 3))
-    fe_flop = sum(x["work"] for (n, tag), x in tags.items() if n.startswith("shg_conv3d"))
-    losses = tr.losses_from_scalars(scal)
-    return {"workload": "same step from backbone features fp32 [32,2048,16,7,7]: + layout cast, Conv3d(2048->768,(5,3,3))"
-                        "+GELU, Conv3d(768->768)+GELU, cls/position/dropout, their backward (no gradient into the "
-                        "frozen-or-stock backbone), +97 M live parameters",
-            "value": round(BATCH_PER_GPU / (ms * 1e-3), 2), "unit": "clips/s", "ms_per_step": round(ms, 3),
-            "frontend_tflop_per_step": round(fe_flop / 1e12, 2), "conv_kernels": convs,
-            "loss_total": round(losses["total"], 4)}
+    return {"workload": "AGQA --taskVQA eval, bs8, from backbone features (Conv3d front-end + l5/r5/x2 + pooler + answer head), "
+                        "no_grad, graph replay", "value": round(8 / (ms * 1e-3), 1), "unit": "clips/s",
+            "fwd_ms_per_batch": round(ms, 3), "logit_shape": list(out["logit"].shape)}
 
 
-# -------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_throughput(steps, warmup, sample_clips=8):
-    """The reference's own algorithm on the host cores: oracle/shg_oracle.py (torch fp32 port, pinned against the
-    unmodified reference by tests/golden) — forward, scipy-equivalent matching (oracle/lsap.c), loss, backward —
-    on a bounded sample of the bs32 workload."""
+def measure_config5(args, dev):
+    """Config 5: STAR-shaped decoder + matcher stress, bs64, every frame full (1024 8x8 + 1024 3x3 LSAPs), class
+    counts 564 / 112 / 4 (star_model.py:19, star.py:90): the full train step, and the two matcher launches alone."""
+    import torch
+    from shg_vqa_b200 import ops
+    from shg_vqa_b200.trainer import HotPathTrainer
+    tr = HotPathTrainer(dev, n_answers=4, n_rel_cls=564, n_act_cls=112, t_total=100000, dropout=not args.no_dropout)
+    tr.init_weights(seed=9595)
+    h_inp, h_batch = make_batch(77, pin=False, batch=64, n_rel_cls=564, n_act_cls=112, n_ans=4, full_frames=True)
+    inp = {k: v.to(dev) for k, v in h_inp.items()}
+    batch = {k: v.to(dev) for k, v in h_batch.items()}
+    ms, scal = _time_graph_step(tr, inp, batch, args)
+    out = tr.static_out
+    # matcher alone (softmax stats + cost gather + 1024 LSAPs + target scatter), both families
+    for _ in range(3):
+        ops.match_from_logits(out["rel_logits"], batch["rel_labels"], batch["rel_off"], 8)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20):
+        ops.match_from_logits(out["rel_logits"], batch["rel_labels"], batch["rel_off"], 8)
+        ops.match_from_logits(out["act_logits"], batch["act_labels"], batch["act_off"], 3)
+    e.record()
+    torch.cuda.synchronize()
+    m_us = s.elapsed_time(e) / 20 * 1e3
+    n_bytes = out["rel_logits"].numel() * 4 + out["act_logits"].numel() * 4
+    return {"workload": "STAR-shaped (564/112/4 classes) train step, bs64, all 2048 frames full, graph replay",
+            "value": round(64 / (ms * 1e-3), 1), "unit": "clips/s", "ms_per_step": round(ms, 3),
+            "matcher_alone_us": round(m_us, 1), "matcher_lsaps": 2048,
+            "matcher_logit_bytes": int(n_bytes), "matcher_gbs": round(n_bytes / (m_us * 1e-6) / 1e9, 1),
+            "loss_total": round(tr.losses_from_scalars(scal)["total"], 4)}
+
+
+def gpu_eager_reference(dev, our_ms):
+    """SURVEY §8d's honest competitor: the reference's algorithm in stock eager PyTorch ON THE SAME B200 — the oracle
+    port (oracle/shg_oracle.py, pinned against the unmodified reference) with tensors on the GPU: forward, matching
+    (its CPU scipy-equivalent loop, as matcher.py:76-80 does), losses, autograd backward, clip_grad_norm_ and a
+    BertAdam step written with torch foreach ops; fp32 / TF32 / bf16 autocast; bs32, from visual tokens (the same
+    workload as the headline).  Baseline leg: the oracle is only timed here, never used by the product path."""
     import torch
     from oracle import shg_oracle as so
     from shg_vqa_b200.params import build_key_shapes
     from shg_vqa_b200.synthetic import make_inputs
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    ks = {k: [list(s), d] for k, (s, d) in build_key_shapes("hgqa").items()}
-    ks = {k: v for k, v in ks.items() if ".visn_fc.conv" not in k}          # front-end is outside the path
+    ks = {k: [list(s), d] for k, (s, d) in build_key_shapes("hgqa").items() if ".visn_fc.conv" not in k}
+    sd = so.make_state_dict(ks, seed=0)
+    leaves = {}
+    for k, v in sd.items():
+        ck = so.canonical_key(k)
+        if ck not in leaves:
+            leaves[ck] = v.to(dev).requires_grad_(v.is_floating_point())
+    full = {k: leaves[so.canonical_key(k)] for k in sd}
+    raw = make_inputs(BATCH_PER_GPU, seed=1234, with_feat=False, visn_tokens=True)
+    inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in raw.items()}
+    params = [t for t in leaves.values() if t.is_floating_point()]
+    m = [torch.zeros_like(t) for t in params]
+    v2 = [torch.zeros_like(t) for t in params]
+
+    def step(autocast):
+        for t in params:
+            t.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = so.agqa_forward(full, inp)
+        out = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in out.items()}
+        so.hgqa_total_loss(out, inp)["total"].backward()
+        live = [(t, a, b) for t, a, b in zip(params, m, v2) if t.grad is not None]
+        torch.nn.utils.clip_grad_norm_([t for t, _, _ in live], 5.0)
+        with torch.no_grad():
+            ts, gs = [t for t, _, _ in live], [t.grad for t, _, _ in live]
+            ms_, vs_ = [a for _, a, _ in live], [b for _, _, b in live]
+            torch._foreach_mul_(ms_, 0.9)
+            torch._foreach_add_(ms_, gs, alpha=0.1)
+            torch._foreach_mul_(vs_, 0.999)
+            torch._foreach_addcmul_(vs_, gs, gs, value=0.001)
+            den = torch._foreach_sqrt(vs_)
+            torch._foreach_add_(den, 1e-6)
+            upd = torch._foreach_div(ms_, den)
+            torch._foreach_add_(upd, ts, alpha=0.01)
+            torch._foreach_add_(ts, upd, alpha=-1e-5)
+    res = {}
+    for name, tf32, ac in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        step(ac)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            step(ac)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / n * 1e3
+        res[name] = {"ms_per_step": round(ms, 2), "clips_per_s": round(BATCH_PER_GPU / (ms * 1e-3), 1),
+                     "hot_path_speedup": round(ms / our_ms, 2)}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    res["what"] = ("oracle port of the reference's algorithm in stock eager PyTorch on this GPU: fwd + matching (CPU LSAP loop, "
+                   "as the reference) + loss + autograd bwd + clip + BertAdam (foreach), bs32 from visual tokens; wall clock "
+                   "over 3 steps after 1 warm-up")
+    return res
+
+
+# -------------------------------------------------------------------------------------- CPU reference arm
+def _oracle_leaves(task="hgqa", frontend=False):
+    import torch
+    from oracle import shg_oracle as so
+    from shg_vqa_b200.params import build_key_shapes
+    ks = {k: [list(s), d] for k, (s, d) in build_key_shapes(task).items()}
+    if not frontend:
+        ks = {k: v for k, v in ks.items() if ".visn_fc.conv" not in k}          # front-end is outside the path
     sd = so.make_state_dict(ks, seed=0)
     leaves = {}
     for k, v in sd.items():
         ck = so.canonical_key(k)
         if ck not in leaves:
             leaves[ck] = v.clone().requires_grad_(v.is_floating_point())
-    full = {k: leaves[so.canonical_key(k)] for k in sd}
-    inp = make_inputs(sample_clips, seed=1234, with_feat=False, visn_tokens=True)
+    return so, leaves, {k: leaves[so.canonical_key(k)] for k in sd}
 
+
+def cpu_reference_throughput(steps, warmup, sample_clips=BATCH_PER_GPU, budget_s=240.0):
+    """The reference's own algorithm on the host cores: oracle/shg_oracle.py (torch fp32 port, pinned against the
+    unmodified reference by tests/golden) — forward, scipy-equivalent matching (oracle/lsap.c), loss, backward,
+    clip_grad_norm_(5.) + BertAdam — on full bs32 batches of the headline workload (a smaller sample only if the
+    requested steps would not fit the time budget; said in `sample`)."""
+    import torch
+    from shg_vqa_b200.synthetic import make_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    so, leaves, full = _oracle_leaves()
     state = {}
 
-    def step():
+    def make(n):
+        return make_inputs(n, seed=1234, with_feat=False, visn_tokens=True)
+
+    def step(inp):
         for t in leaves.values():
             t.grad = None
         out = so.agqa_forward(full, inp)
@@ -343,28 +797,77 @@ def cpu_reference_throughput(steps, warmup, sample_clips=8):
                 v.mul_(0.999).addcmul_(t.grad, t.grad, value=0.001)
                 t.add_(m / (v.sqrt() + 1e-6) + 0.01 * t, alpha=-1e-5)
 
-    for _ in range(warmup):
-        step()
+    inp = make(sample_clips)
+    t0 = time.perf_counter()
+    step(inp)                                           # first (warm-up) step also sizes the run
+    t_first = time.perf_counter() - t0
+    if t_first * (steps + max(warmup, 1)) > budget_s and sample_clips > 8:
+        sample_clips = 8
+        inp = make(sample_clips)
+        step(inp)
+    for _ in range(max(warmup - 1, 0)):
+        step(inp)
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        step(inp)
     dt = (time.perf_counter() - t0) / steps
     return {"value": round(sample_clips / dt, 3), "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": "%d-clip batches of the same workload (fwd + matching + loss + bwd + clip + BertAdam, fp32, "
-                      "%d torch threads), %.2f s/step" % (sample_clips, cores, dt)}
+            "sample": "%d steps of %d-clip batches of the headline workload (fwd + matching + loss + bwd + clip + BertAdam, "
+                      "fp32, %d torch threads), %.2f s/step" % (steps, sample_clips, cores, dt)}
+
+
+def cpu_other_configs():
+    """SURVEY §8d's other CPU lines: config 1 (B=2 fwd+loss+bwd from backbone features), config 4 (--taskVQA eval
+    B=8) and the matcher alone at bs32 / bs64 (the reference's softmax -> gather -> .cpu() -> per-frame LSAP loop,
+    lxrt/matcher.py:59-80).  Median of 3 after 1 warm-up."""
+    import torch
+    from shg_vqa_b200.synthetic import make_inputs
+    res = {}
+
+    def med(fn, n=3):
+        fn()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2]
+    so, leaves, full = _oracle_leaves(frontend=True)
+    raw = make_inputs(2, seed=1234, with_feat=True)
+
+    def c1():
+        for t in leaves.values():
+            t.grad = None
+        so.hgqa_total_loss(so.agqa_forward(full, raw), raw)["total"].backward()
+    t = med(c1)
+    res["config1_b2_fwd_loss_bwd"] = {"s_per_iter": round(t, 3), "clips_per_s": round(2 / t, 2)}
+    raw8 = make_inputs(8, seed=4, with_feat=True)
+
+    def c4():
+        with torch.no_grad():
+            so.agqa_forward(full, raw8, task="vqa")
+    t = med(c4)
+    res["config4_vqa_eval_b8"] = {"s_per_iter": round(t, 3), "clips_per_s": round(8 / t, 2)}
+    g = torch.Generator().manual_seed(9)
+    for b, n_rel, n_act, full_frames in ((32, 457, 158, False), (64, 564, 112, True)):
+        r = make_inputs(b, seed=3, n_rel_cls=n_rel, n_act_cls=n_act, full_frames=full_frames, with_feat=False)
+        rel = torch.randn(b, 128, n_rel, generator=g)
+        act = torch.randn(b, 48, n_act, generator=g)
+        t = med(lambda: (so.hungarian_match(rel, r["rel_labels"]), so.hungarian_match(act, r["act_labels"])))
+        res["matcher_alone_bs%d" % b] = {"ms_per_iter": round(t * 1e3, 2), "lsaps": 2 * 16 * b}
+    return res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    base = cpu_reference_throughput(steps=steps, warmup=min(args.warmup, 1))
-    line = {"impl": "reference", "metric": "train clips/sec at bs32/GPU (hot path)", "value": base["value"],
-            "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": round(8 / base["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+    base = cpu_reference_throughput(steps=max(1, args.steps), warmup=max(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"],
+            "unit": "clips/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, args.warmup),
+            "ms_per_step": round(BATCH_PER_GPU / base["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": "cpu x%d threads" % base["cores"]},
+            "config": base_config(args.gpus),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -376,7 +879,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-frontend", action="store_true", help="skip the with_frontend measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip with_frontend / with_backbone / configs 4, 5 / GPU eager reference")
+    ap.add_argument("--no-frontend", dest="no_extras", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true", help="eval-style step (p = 0) for A/B timing")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")

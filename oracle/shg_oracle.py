@@ -166,7 +166,7 @@ def visual_front_end(sd, p, feat):
 def bert_embeddings(sd, p, ids, seg):
     """BertEmbeddings, modeling_capsbert.py:341-355."""
     # all three tables are nn.Embedding(padding_idx=0) (:331-333): row 0 never receives gradient
-    pos = torch.arange(ids.shape[1]).unsqueeze(0).expand_as(ids)
+    pos = torch.arange(ids.shape[1], device=ids.device).unsqueeze(0).expand_as(ids)
     e = (F.embedding(ids, sd[p + ".word_embeddings.weight"], padding_idx=0)
          + F.embedding(pos, sd[p + ".position_embeddings.weight"], padding_idx=0)
          + F.embedding(seg, sd[p + ".token_type_embeddings.weight"], padding_idx=0))
@@ -204,10 +204,10 @@ def hg_embeddings(sd, p, seg_ids):
     return _ln(sd, p + ".LayerNorm", e, LN_EPS_BERT)
 
 
-def block_causal_mask(n_frames, per_frame):
+def block_causal_mask(n_frames, per_frame, device=None):
     """entry.py:114-121: -inf where key frame > query frame, else 0."""
-    f = torch.arange(n_frames).repeat_interleave(per_frame)
-    m = torch.zeros(f.numel(), f.numel())
+    f = torch.arange(n_frames, device=device).repeat_interleave(per_frame)
+    m = torch.zeros(f.numel(), f.numel(), device=device)
     m[f[None, :] > f[:, None]] = float("-inf")
     return m
 
@@ -258,7 +258,7 @@ def cross_encoder(sd, p, lang, lang_mask, hg, hg_mask01, n_act=3, n_rel=8):
     hg = torch.cat([sd[p + ".cls_token"].expand(b, -1, -1), hg], dim=1)
     hmask = None
     if hg_mask01 is not None:
-        hmask = additive_key_mask(torch.cat([torch.ones(b, 1), hg_mask01.view(b, -1).float()], dim=1))
+        hmask = additive_key_mask(torch.cat([torch.ones(b, 1, device=hg.device), hg_mask01.view(b, -1).float()], dim=1))
     for _ in range(2):
         lang, hg = cross_layer(sd, p + ".cross_attn_layer.cross", lang, lang_mask, hg, hmask)
     return pooler2(sd, p + ".pooler_dict.cross", hg, lang)
@@ -279,10 +279,10 @@ def agqa_forward(sd, inp, task="hgqa", use_hg_mask=False, n_frames=16, n_rel=8, 
         return out
     memory = enc["visn_r"]                                                       # :218 (pre-cross features)
     rel_q = hg_embeddings(sd, "relation_query_embed", inp["rel_segment_ids"])    # :234
-    rel_out = decoder(sd, "rel_decoder", memory, block_causal_mask(n_frames, n_rel), rel_q)
+    rel_out = decoder(sd, "rel_decoder", memory, block_causal_mask(n_frames, n_rel, memory.device), rel_q)
     out["rel_logits"] = mlp_head(sd, "class_embed", rel_out)                     # :238
     act_q = hg_embeddings(sd, "action_query_embed", inp["act_segment_ids"])      # :244
-    act_out = decoder(sd, "action_decoder", memory, block_causal_mask(n_frames, n_act), act_q)
+    act_out = decoder(sd, "action_decoder", memory, block_causal_mask(n_frames, n_act, memory.device), act_q)
     out["act_logits"] = mlp_head(sd, "action_embed", act_out)                    # :249
     b = rel_out.shape[0]
     hg_in = torch.cat([act_out.view(b, n_frames, n_act, HID), rel_out.view(b, n_frames, n_rel, HID)], dim=2)  # :255-258
@@ -340,14 +340,14 @@ def frame_costs(logits, frame_labels, n_frames=16):
     b, q, _ = logits.shape
     q_f = q // n_frames
     prob = logits.flatten(0, 1).softmax(-1).view(b * n_frames, q_f, -1)
-    return [-prob[i][:, lab] for i, lab in enumerate(frame_labels)]
+    return [-prob[i][:, lab.to(prob.device)] for i, lab in enumerate(frame_labels)]
 
 
 def hungarian_match(logits, frame_labels, n_frames=16):
     """HungarianMatcher.forward per-frame branch, matcher.py:59-80."""
     res = []
     for c in frame_costs(logits, frame_labels, n_frames):
-        r, cc = lsap(c.detach().numpy())
+        r, cc = lsap(c.detach().cpu().numpy())        # the reference's `.cpu()` before scipy (matcher.py:76)
         res.append((torch.as_tensor(r.copy(), dtype=torch.int64), torch.as_tensor(cc.copy(), dtype=torch.int64)))
     return res
 
@@ -362,8 +362,9 @@ def set_loss(logits, frame_labels, indices, eos_coef=0.1, n_frames=16):
     lg = logits.reshape(b * n_frames, q_f, c)
     tgt = torch.zeros(b * n_frames, q_f, dtype=torch.int64)
     for f, (rows, cols) in enumerate(indices):
-        tgt[f, rows] = frame_labels[f][cols]
-    w = torch.ones(c)
+        tgt[f, rows] = frame_labels[f].cpu()[cols]
+    tgt = tgt.to(logits.device)
+    w = torch.ones(c, device=logits.device)
     w[0] = eos_coef
     loss = F.cross_entropy(lg.transpose(1, 2), tgt, w)
     fi = torch.cat([torch.full_like(r, f) for f, (r, _) in enumerate(indices)]) if indices else torch.zeros(0, dtype=torch.int64)
@@ -371,6 +372,7 @@ def set_loss(logits, frame_labels, indices, eos_coef=0.1, n_frames=16):
     if ri.numel() == 0:
         err = torch.tensor(100.0)
     else:
+        fi, ri = fi.to(logits.device), ri.to(logits.device)
         pred = lg[fi, ri].argmax(-1)
         err = 100.0 - (pred == tgt[fi, ri]).float().mean() * 100.0
     return loss, err, tgt

@@ -156,44 +156,56 @@ profiler = None     # set to a Profiler to time every call with CUDA events on t
 
 
 class Profiler:
-    """Per-entry-point CUDA-event timing on the current stream (bench.py's live roofline numbers)."""
+    """Book-keeping of every entry-point call while installed as `_lib.profiler`: name, roofline kind, algorithmic
+    work, shape tag and number of kernels the call launches (bench.py joins these, in order, with CUPTI kernel
+    records).  With time_events=True each call is also bracketed by CUDA events on the launching stream — those
+    times include the host's enqueue gaps and are only used by the exploratory tools/, never by bench.py."""
 
-    def __init__(self):
-        self.records = []      # (name, kind, work, start_event, end_event)
-        self.tags = []
+    def __init__(self, time_events=False):
+        self.time_events = time_events
+        self.calls = []        # [name, kind, work, tag, (start_event, end_event) | None, n_kernels]
+
+    def work_by_entry(self):
+        agg = {}
+        for name, kind, work, tag, _, n_k in self.calls:
+            key = "shg_conv3d" if name.startswith("shg_conv3d") else name
+            a = agg.setdefault(key, dict(kind=kind, calls=0, work=0.0))
+            a["calls"] += 1
+            a["work"] += work
+        return agg
+
+    def _timed(self, key_fn):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, kind, work, tag, ev, _ in self.calls:
+            a = agg.setdefault(key_fn(name, tag), dict(kind=kind, calls=0, ms=0.0, work=0.0))
+            a["calls"] += 1
+            a["ms"] += ev[0].elapsed_time(ev[1]) if ev is not None else 0.0
+            a["work"] += work
+        return agg
 
     def by_tag(self):
-        torch.cuda.synchronize()
-        agg = {}
-        for (name, kind, work, s, e), tag in zip(self.records, self.tags):
-            a = agg.setdefault((name, tag), dict(calls=0, ms=0.0, work=0.0))
-            a["calls"] += 1
-            a["ms"] += s.elapsed_time(e)
-            a["work"] += work
-        return agg
+        return self._timed(lambda name, tag: (name, tag))
 
     def summary(self):
-        torch.cuda.synchronize()
-        agg = {}
-        for name, kind, work, s, e in self.records:
-            a = agg.setdefault(name, dict(kind=kind, calls=0, ms=0.0, work=0.0))
-            a["calls"] += 1
-            a["ms"] += s.elapsed_time(e)
-            a["work"] += work
-        return agg
+        return self._timed(lambda name, tag: name)
 
 
 def call(name, *args, work=None):
-    """work = ("tensor", flops) | ("hbm", bytes): algorithmic work of this launch, for the roofline."""
+    """work = ("tensor", flops[, tag]) | ("hbm", bytes[, tag]): algorithmic work of this launch, for the roofline."""
     global launch_count
-    launch_count += LAUNCHES.get(name, 1)
+    n_k = LAUNCHES.get(name, 1)
+    launch_count += n_k
     if profiler is None:
         check(getattr(lib(), name)(*args))
         return
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
+    ev = None
+    if profiler.time_events:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     check(getattr(lib(), name)(*args))
-    e.record()
+    if ev is not None:
+        ev[1].record()
     kind, amount = (work[0], work[1]) if work is not None else ("hbm", 0.0)
-    profiler.records.append((name, kind, float(amount), s, e))
-    profiler.tags.append(work[2] if work is not None and len(work) > 2 else "")
+    tag = work[2] if work is not None and len(work) > 2 else ""
+    profiler.calls.append([name, kind, float(amount), tag, ev, n_k])

@@ -57,8 +57,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     return fn;
 }
 
-const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                 const uint32_t* box) {
+const CUtensorMap* get_tmap(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, int dtype) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> cache;
     int dev = 0;
@@ -70,7 +70,7 @@ const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims
     TmapKey key;
     memset(&key, 0, sizeof(key));
     key.w[0] = reinterpret_cast<uint64_t>(ptr);
-    key.w[1] = (uint64_t)rank | ((uint64_t)dev << 8);
+    key.w[1] = (uint64_t)rank | ((uint64_t)dev << 8) | ((uint64_t)dtype << 16);
     for (int i = 0; i < rank; ++i) {
         key.w[2 + i] = dims[i];
         key.w[7 + i] = i ? strides_bytes[i - 1] : 0;
@@ -103,7 +103,7 @@ const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims
         bx[i] = box[i];
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+    CUresult r = fn(m, dtype == kTmapF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

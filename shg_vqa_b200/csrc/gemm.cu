@@ -36,7 +36,7 @@ struct GemmParams {
     float mul_scale;
     DropCfg drop;
     int act, out_f32, accumulate;
-    int tma_store;          // bf16 D (and preact) leave through smem staging + TMA stores
+    int tma_store;          // kStoreDirect | kStoreBf16 | kStoreReduceF32 (see epilogue_tile)
     int splits, block_n, n_stages;
     int m_tiles, n_tiles, kb_total, kb_per_split;
     unsigned long long* dbg;   // optional phase timestamps of CTA 0 (tools/gemm_phases.py), normally null
@@ -62,24 +62,36 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     }
 }
 
-constexpr int kStageOutBytes = 2 * 16384;   // two [128 x 64] bf16 staging blocks for the TMA-store epilogue
+constexpr int kStageGroupBytes = 16384;          // one [128 x 64] bf16 or [128 x 32] fp32 staging block per warpgroup
+constexpr int kStageOutBytes = 4 * kStageGroupBytes;
 
-// One output tile's epilogue for one thread (= one output row; warp group `sub` of NSUB takes 64/NSUB columns of
-// every 64-column block).  `wait_accumulator` blocks until the tile's accumulator is complete in TMEM; HBM operands of
-// the first chunk are requested before it.
+// p.tma_store: how D leaves the SM
+constexpr int kStoreDirect = 0;   // st.global / atomics from registers (unaligned or plain-fp32 outputs)
+constexpr int kStoreBf16 = 1;     // bf16 D (and pre-activation copy): smem staging + TMA bulk store
+constexpr int kStoreReduceF32 = 2;   // fp32 accumulation (split-K weight gradients): smem staging + TMA bulk reduce-add
+
+// One output tile's epilogue for one warpgroup (4 warps = the 4 TMEM lane quarters = 128 output rows; thread = row).
+// The tile's column blocks (64 wide for bf16 outputs, 32 wide for fp32) are dealt round-robin to the FOUR epilogue
+// warpgroups, which run independently of each other: each has its own staging block, its own named barrier and its
+// own bulk-store group.  (Round 1 had all 16 warps cooperate on every 64-column block behind two 512-thread barriers
+// and one store-issuing thread: 0.8 us per block, 3.5 us for a 256-wide tile — longer than the 3.1 us main loop of a
+// K = 768 projection, so the epilogue, not the tensor core, paced those kernels.)
 //
-// bf16 outputs (D and the optional pre-activation copy) leave through shared memory: the 256 epilogue threads write a
-// [128 x 64] block 128B-swizzled (thread = row: 4 x 16 B, conflict-free), one thread hands it to a TMA store, two
-// blocks in flight.  A warp-level st.global of "thread = row" touches 32 different lines per instruction — at 256
-// columns per tile the LSU, not the tensor core, then sets the tile time; the bulk store moves whole lines and clips
-// the M / N tails itself.  fp32 outputs and split-K accumulation (atomics) keep the direct path.
-template <int NSUB, class WaitFn>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* sb, uint32_t t_row, int row, bool row_ok,
-                                              int m0, int n0, int sub, int etid, uint8_t* stg, const CUtensorMap* tm_d,
-                                              const CUtensorMap* tm_pre, uint32_t& nblk, void* dbase,
+// bf16 outputs: the 128 threads write a [128 x 64] block 128B-swizzled (thread = row: 16 B units, conflict-free), one
+// thread hands it to a TMA store that moves whole lines and clips the M / N tails.  fp32 accumulation (split-K weight
+// gradients): the same with [128 x 32] fp32 blocks and a TMA REDUCE-ADD (cp.reduce.async.bulk.tensor ... .add):
+// the L2 does the fp32 adds on whole lines instead of 16-byte atomics scattered over 32 rows per warp instruction.
+// `wait_accumulator` blocks until the tile's accumulator is complete in TMEM; HBM operands of the first chunk are
+// requested before it.
+template <class WaitFn>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* __restrict__ bias, uint32_t t_row,
+                                              int row, bool row_ok, int m0, int n0, int wg, int wtid, uint8_t* stg,
+                                              const CUtensorMap* tm_d, const CUtensorMap* tm_pre, void* dbase,
                                               WaitFn wait_accumulator) {
-    constexpr int COLS = 64 / NSUB;          // columns per thread and 64-column block (32 or 16)
-    constexpr int NV = COLS / 8;             // 16-byte bf16 vectors per thread and block
+    constexpr int CH = 16, NV = 2;               // register chunk: 16 columns = 2 x 16-byte bf16 vectors
+    const int mode = p.tma_store;
+    const int uw = mode == kStoreReduceF32 ? 32 : 64;          // unit block width
+    const bool staged = mode != kStoreDirect;
     const bool vec_ok_bf16 = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0);
     const bool vec_ok_f32 = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0);
     // the one bf16 side operand of the tile: the saved activation input/output (backward through an activation) or
@@ -87,190 +99,192 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
     const __nv_bfloat16* side_ptr = p.mul_aux ? p.mul_aux : p.residual;
     const int64_t ld_side = p.mul_aux ? p.ldd : p.ldr;
     const bool vec_ok_side = side_ptr && (ld_side % 8 == 0) && ((reinterpret_cast<uintptr_t>(side_ptr) & 15) == 0);
-    const bool staged = p.tma_store != 0;
     const int r_local = row - m0;
-    // COLS values of this thread's row -> its part of the staging block -> (one thread) bulk store of the block
-#define EPI_STAMP(i) do { if (p.dbg && etid == 0 && blockIdx.x == 0 && nblk == 1) p.dbg[i] = globaltimer_ns(); } while (0)
-    auto staged_store = [&](const float (&v)[COLS], const CUtensorMap* tm, int blk_col0, bool active) {
-        EPI_STAMP(10);
-        if (etid == 0) bulk_wait_read<1>();              // the store that last used this buffer has read it
-        asm volatile("bar.sync 1, %0;" ::"n"(NSUB * 128) : "memory");
-        EPI_STAMP(11);
-        uint8_t* buf = stg + (nblk & 1) * 16384;
-        if (active) {
-            uint8_t* dst = buf + r_local * 128;
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]), u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                *reinterpret_cast<uint4*>(dst + (((sub * NV + j) ^ (r_local & 7)) << 4)) = u;
-            }
-        }
-        EPI_STAMP(12);
-        fence_proxy_async_smem();
-        EPI_STAMP(13);
-        asm volatile("bar.sync 1, %0;" ::"n"(NSUB * 128) : "memory");
-        EPI_STAMP(14);
-        if (etid == 0) {
-            tma_store_2d(tm, buf, blk_col0, m0);
-            bulk_commit();
-        }
-        EPI_STAMP(15);
-        ++nblk;
-    };
+    uint8_t* buf = stg + wg * kStageGroupBytes;
+    const int bar_id = 1 + wg;
+    auto wg_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     // side operand of a chunk: requested from HBM ahead of its use (first chunk: before the accumulator wait)
     uint4 side[NV];
     auto prefetch = [&](int c) {
         const int col0 = n0 + c;
-        if (row_ok && col0 + COLS <= p.n && vec_ok_side) {
+        if (row_ok && col0 + CH <= p.n && vec_ok_side) {
             const uint4* src = reinterpret_cast<const uint4*>(side_ptr + (size_t)row * ld_side + col0);
 #pragma unroll
             for (int i = 0; i < NV; ++i) side[i] = __ldg(src + i);
         }
     };
-    prefetch(sub * COLS);
+    if (wg * uw < p.block_n) prefetch(wg * uw);
     wait_accumulator();
     tc_fence_after();
-    for (int blk0 = 0; blk0 < p.block_n; blk0 += 64) {
-        if (n0 + blk0 >= p.n) break;                     // uniform over the epilogue threads
-        const int c = blk0 + sub * COLS;
-        const int col0 = n0 + c;
-        const bool active = c < p.block_n && col0 < p.n;  // warp-uniform
-        if (!active && !staged) break;
-        float acc[COLS];
-        const bool full_chunk = col0 + COLS <= p.n;
-        const bool do_row = row_ok && active;
-        if (active) {
-            uint32_t raw[COLS];
-            __syncwarp();
-            EPI_STAMP(8);
-            if constexpr (COLS == 32) tmem_ld32(t_row + c, raw);
-            else tmem_ld16(t_row + c, raw);
-            tmem_ld_wait();
-            EPI_STAMP(9);
-#pragma unroll
-            for (int i = 0; i < COLS; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sb + c + i);
-                acc[i] = __uint_as_float(raw[i]) + b4.x, acc[i + 1] = __uint_as_float(raw[i + 1]) + b4.y;
-                acc[i + 2] = __uint_as_float(raw[i + 2]) + b4.z, acc[i + 3] = __uint_as_float(raw[i + 3]) + b4.w;
-            }
-        }
-        if (p.preact) {
+    const int n_pass = p.preact ? 2 : 1;          // the pre-activation copy is a pass of its own over the block
+    for (int blk0 = wg * uw; blk0 < p.block_n; blk0 += 4 * uw) {
+        if (n0 + blk0 >= p.n) break;               // uniform over the warpgroup
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const bool is_pre = p.preact && pass == 0;
             if (staged) {
-                staged_store(acc, tm_pre, n0 + blk0, active);
-            } else if (do_row) {
-                __nv_bfloat16* pr = p.preact + (size_t)row * p.ldd + col0;
-                if (full_chunk && vec_ok_bf16) {
+                if (wtid == 0) bulk_wait_read<0>();            // the store that last used this block has read it
+                wg_sync();
+            }
+            for (int c0 = 0; c0 < uw; c0 += CH) {
+                const int c = blk0 + c0;
+                const int col0 = n0 + c;
+                if (col0 >= p.n) break;                        // uniform; the bulk store clips those columns
+                const bool full_chunk = col0 + CH <= p.n;
+                float acc[CH];
+                {
+                    uint32_t raw[CH];
+                    __syncwarp();
+                    tmem_ld16(t_row + c, raw);
+                    tmem_ld_wait();
+                    if (bias) {
+                        if (full_chunk) {
 #pragma unroll
-                    for (int i = 0; i < COLS; i += 8) {
+                            for (int i = 0; i < CH; i += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+                                acc[i] = __uint_as_float(raw[i]) + b4.x, acc[i + 1] = __uint_as_float(raw[i + 1]) + b4.y;
+                                acc[i + 2] = __uint_as_float(raw[i + 2]) + b4.z, acc[i + 3] = __uint_as_float(raw[i + 3]) + b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CH; ++i)
+                                acc[i] = __uint_as_float(raw[i]) + (col0 + i < p.n ? __ldg(bias + col0 + i) : 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) acc[i] = __uint_as_float(raw[i]);
+                    }
+                }
+                if (!is_pre) {
+                    // activation first: only the accumulators (and the packed side operand) are live here, which
+                    // leaves the register allocator room to interleave the 32 independent GELU chains
+                    if (p.act == SHG_ACT_GELU_ERF) {
+                        gelu_erf_batch(acc);
+                    } else if (p.act != SHG_ACT_NONE) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) acc[i] = apply_act(acc[i], p.act);
+                    }
+                    float sv[CH];
+                    if (side_ptr) {
+                        if (row_ok && full_chunk && vec_ok_side) {
+#pragma unroll
+                            for (int i = 0; i < NV; ++i) {
+                                float2 f;
+                                f = unpack_bf16x2(side[i].x), sv[8 * i] = f.x, sv[8 * i + 1] = f.y;
+                                f = unpack_bf16x2(side[i].y), sv[8 * i + 2] = f.x, sv[8 * i + 3] = f.y;
+                                f = unpack_bf16x2(side[i].z), sv[8 * i + 4] = f.x, sv[8 * i + 5] = f.y;
+                                f = unpack_bf16x2(side[i].w), sv[8 * i + 6] = f.x, sv[8 * i + 7] = f.y;
+                            }
+                        } else {
+                            const __nv_bfloat16* sp = side_ptr + (size_t)row * ld_side + col0;
+#pragma unroll
+                            for (int i = 0; i < CH; ++i)
+                                sv[i] = (row_ok && col0 + i < p.n) ? __bfloat162float(sp[i]) : 0.f;
+                        }
+                        // next chunk of this warpgroup: the rest of the block, else its next block
+                        const int cn = c0 + CH < uw ? c + CH : blk0 + 4 * uw;
+                        if (cn < p.block_n) prefetch(cn);
+                    }
+                    if (p.mul_mode) {
+                        // backward through an activation: acc *= act'(aux) (aux = saved pre-activation for GELU,
+                        // saved output for ReLU)
+                        if (p.mul_mode == SHG_MUL_GELU_GRAD) {
+                            gelu_erf_grad_batch(acc, sv);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) acc[i] = sv[i] > 0.f ? acc[i] * p.mul_scale : 0.f;
+                        }
+                    }
+                    if (p.drop.p > 0.f) {
+                        // nn.Dropout on the projection output, before the residual add (BertAttOutput / BertOutput /
+                        // decoder dropout1-3 and the decoder FFN's inner dropout)
+                        const uint32_t key = drop_key(__ldg(p.drop.seed), p.drop.salt), th = drop_thresh(p.drop.p);
+                        const float inv_keep = 1.0f / (1.0f - p.drop.p);
+                        const uint64_t base = (uint64_t)row * (uint64_t)p.n + col0;     // col0 is even
+#pragma unroll
+                        for (int i = 0; i < CH; i += 2) {
+                            const uint32_t kb = drop_pair(key, (uint32_t)((base + i) >> 1), th);
+                            acc[i] = (kb & 1u) ? acc[i] * inv_keep : 0.f;
+                            acc[i + 1] = (kb & 2u) ? acc[i + 1] * inv_keep : 0.f;
+                        }
+                    }
+                    if (p.residual) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) acc[i] += sv[i];
+                    }
+                }
+                if (mode == kStoreBf16) {
+                    // [128 x 64] bf16 block: row r at r * 128 B, 16-byte unit u at (u ^ (r & 7))
+                    uint8_t* dst = buf + r_local * 128;
+                    const int u0 = c0 >> 3;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
                         uint4 u;
-                        u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
-                        u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
-                        *reinterpret_cast<uint4*>(pr + i) = u;
+                        u.x = pack_bf16x2(acc[8 * j], acc[8 * j + 1]), u.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
+                        u.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]), u.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(dst + (((u0 + j) ^ (r_local & 7)) << 4)) = u;
                     }
-                } else {
+                } else if (mode == kStoreReduceF32) {
+                    // [128 x 32] fp32 block: row r at r * 128 B, 16-byte unit (4 floats) u at (u ^ (r & 7))
+                    uint8_t* dst = buf + r_local * 128;
+                    const int u0 = c0 >> 2;
 #pragma unroll
-                    for (int i = 0; i < COLS; ++i)
-                        if (col0 + i < p.n) pr[i] = __float2bfloat16(acc[i]);
-                }
-            }
-        }
-        if (do_row || (staged && active)) {
-            // activation first: only the accumulators (and the packed side operand) are live here, which leaves the
-            // register allocator room to interleave the 32 independent GELU chains
-            if (p.act == SHG_ACT_GELU_ERF) {
-                gelu_erf_batch(acc);
-            } else if (p.act != SHG_ACT_NONE) {
+                    for (int j = 0; j < CH / 4; ++j)
+                        *reinterpret_cast<float4*>(dst + (((u0 + j) ^ (r_local & 7)) << 4)) =
+                            make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                } else if (row_ok) {
+                    if (is_pre) {
+                        __nv_bfloat16* pr = p.preact + (size_t)row * p.ldd + col0;
 #pragma unroll
-                for (int i = 0; i < COLS; ++i) acc[i] = apply_act(acc[i], p.act);
-            }
-            float sv[COLS];
-            if (side_ptr) {
-                if (row_ok && full_chunk && vec_ok_side) {
+                        for (int i = 0; i < CH; ++i)
+                            if (col0 + i < p.n) pr[i] = __float2bfloat16(acc[i]);
+                    } else if (p.accumulate) {
+                        float* o = reinterpret_cast<float*>(dbase) + (size_t)row * p.ldd + col0;
+                        if (full_chunk && vec_ok_f32) {
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        float2 f;
-                        f = unpack_bf16x2(side[i].x), sv[8 * i] = f.x, sv[8 * i + 1] = f.y;
-                        f = unpack_bf16x2(side[i].y), sv[8 * i + 2] = f.x, sv[8 * i + 3] = f.y;
-                        f = unpack_bf16x2(side[i].z), sv[8 * i + 4] = f.x, sv[8 * i + 5] = f.y;
-                        f = unpack_bf16x2(side[i].w), sv[8 * i + 6] = f.x, sv[8 * i + 7] = f.y;
+                            for (int i = 0; i < CH; i += 4)
+                                atomicAdd(reinterpret_cast<float4*>(o + i),
+                                          make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CH; ++i)
+                                if (col0 + i < p.n) atomicAdd(o + i, acc[i]);
+                        }
+                    } else if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(dbase) + (size_t)row * p.ldd + col0;
+                        if (full_chunk && vec_ok_f32) {
+#pragma unroll
+                            for (int i = 0; i < CH; i += 4)
+                                *reinterpret_cast<float4*>(o + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CH; ++i)
+                                if (col0 + i < p.n) o[i] = acc[i];
+                        }
+                    } else {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dbase) + (size_t)row * p.ldd + col0;
+                        if (full_chunk && vec_ok_bf16) {
+#pragma unroll
+                            for (int i = 0; i < CH; i += 8) {
+                                uint4 u;
+                                u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
+                                u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
+                                *reinterpret_cast<uint4*>(o + i) = u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CH; ++i)
+                                if (col0 + i < p.n) o[i] = __float2bfloat16(acc[i]);
+                        }
                     }
-                } else {
-                    const __nv_bfloat16* sp = side_ptr + (size_t)row * ld_side + col0;
-#pragma unroll
-                    for (int i = 0; i < COLS; ++i) sv[i] = (row_ok && col0 + i < p.n) ? __bfloat162float(sp[i]) : 0.f;
-                }
-                if (c + 64 < p.block_n) prefetch(c + 64);
-            }
-            if (p.mul_mode) {
-                // backward through an activation: acc *= act'(aux) (aux = saved pre-activation for GELU,
-                // saved output for ReLU)
-                if (p.mul_mode == SHG_MUL_GELU_GRAD) {
-                    gelu_erf_grad_batch(acc, sv);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < COLS; ++i) acc[i] = sv[i] > 0.f ? acc[i] * p.mul_scale : 0.f;
                 }
             }
-            if (p.drop.p > 0.f) {
-                // nn.Dropout on the projection output, before the residual add (BertAttOutput / BertOutput /
-                // decoder dropout1-3 and the decoder FFN's inner dropout)
-                const uint32_t key = drop_key(__ldg(p.drop.seed), p.drop.salt), th = drop_thresh(p.drop.p);
-                const float inv_keep = 1.0f / (1.0f - p.drop.p);
-                const uint64_t base = (uint64_t)row * (uint64_t)p.n + col0;     // col0 is even
-#pragma unroll
-                for (int i = 0; i < COLS; i += 2) {
-                    const uint32_t kb = drop_pair(key, (uint32_t)((base + i) >> 1), th);
-                    acc[i] = (kb & 1u) ? acc[i] * inv_keep : 0.f;
-                    acc[i + 1] = (kb & 2u) ? acc[i + 1] * inv_keep : 0.f;
-                }
-            }
-            if (p.residual) {
-#pragma unroll
-                for (int i = 0; i < COLS; ++i) acc[i] += sv[i];
-            }
-        }
-        if (staged) {
-            staged_store(acc, tm_d, n0 + blk0, active);
-        } else if (do_row) {
-            if (p.accumulate) {
-                float* o = reinterpret_cast<float*>(dbase) + (size_t)row * p.ldd + col0;
-                if (full_chunk && vec_ok_f32) {
-#pragma unroll
-                    for (int i = 0; i < COLS; i += 4)
-                        atomicAdd(reinterpret_cast<float4*>(o + i),
-                                  make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < COLS; ++i)
-                        if (col0 + i < p.n) atomicAdd(o + i, acc[i]);
-                }
-            } else if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(dbase) + (size_t)row * p.ldd + col0;
-                if (full_chunk && vec_ok_f32) {
-#pragma unroll
-                    for (int i = 0; i < COLS; i += 4)
-                        *reinterpret_cast<float4*>(o + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < COLS; ++i)
-                        if (col0 + i < p.n) o[i] = acc[i];
-                }
-            } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dbase) + (size_t)row * p.ldd + col0;
-                if (full_chunk && vec_ok_bf16) {
-#pragma unroll
-                    for (int i = 0; i < COLS; i += 8) {
-                        uint4 u;
-                        u.x = pack_bf16x2(acc[i], acc[i + 1]), u.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
-                        u.z = pack_bf16x2(acc[i + 4], acc[i + 5]), u.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
-                        *reinterpret_cast<uint4*>(o + i) = u;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < COLS; ++i)
-                        if (col0 + i < p.n) o[i] = __float2bfloat16(acc[i]);
+            if (staged) {
+                fence_proxy_async_smem();          // generic-proxy writes of the block -> visible to the TMA engine
+                wg_sync();
+                if (wtid == 0) {
+                    if (mode == kStoreReduceF32) tma_reduce_add_2d(tm_d, buf, n0 + blk0, m0);
+                    else tma_store_2d(is_pre ? tm_pre : tm_d, buf, n0 + blk0, m0);
+                    bulk_commit();
                 }
             }
         }
@@ -281,7 +295,8 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
-            const __grid_constant__ CUtensorMap tma_b2, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_d2,
+            const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stg = smem;                               // TMA-store staging (present only when p.tma_store)
@@ -294,7 +309,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2 stages][256], 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -396,28 +410,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue (warps 2..9)
-        // Two warps per TMEM lane quarter, each taking every other 32-column chunk; thread = one output row.
-        const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
-        const int sub = (warp - 2) >> 2;       // which 16 columns of each 64-column block
-        const int etid = (warp - 2) * 32 + lane;
+        // ---------------------------------------------------------------- epilogue (warps 2..17)
+        // Four warpgroups; warp w may touch TMEM lane quarter w % 4, so every group of four consecutive warps covers
+        // the 128 rows of the tile.  Each group takes every fourth column block and runs on its own (epilogue_tile).
+        const int quarter = warp & 3;
+        const int wg = (warp - 2) >> 2;
+        const int wtid = ((warp - 2) & 3) * 32 + lane;
         int as = 0;
-        uint32_t aphase = 0, nblk = 0;
+        uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int rem = tile % (p.m_tiles * p.n_tiles);
             const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * p.block_n;
             const int row = m0 + quarter * 32 + lane;
             const bool row_ok = row < p.m;
-            // bias of this tile -> shared memory (zero past N), while the main loop is still running
-            float* sb = s_bias + as * 256;
             const float* bias = m0 >= p.split_m ? p.bias2 : p.bias;
-            if (etid < 256) sb[etid] = (bias && n0 + etid < p.n) ? __ldg(bias + n0 + etid) : 0.f;
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            void* dbase = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group ? p.d2 : p.d;
-            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk, dbase,
-                          [&] { mbar_wait(tmem_full + as, aphase); if (etid == 0 && tile == (int)blockIdx.x) SHG_STAMP(3); });
-            if (etid == 0 && tile == (int)blockIdx.x) SHG_STAMP(4);
+            const bool second = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group;
+            epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
+                          second ? p.d2 : p.d,
+                          [&] { mbar_wait(tmem_full + as, aphase); if (wg == 0 && wtid == 0 && tile == (int)blockIdx.x) SHG_STAMP(3); });
+            if (wg == 0 && wtid == 0 && tile == (int)blockIdx.x) SHG_STAMP(4);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_relaxed(tmem_empty + as);
@@ -426,8 +438,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 aphase ^= 1;
             }
         }
-        if (etid == 0) bulk_wait_read<0>();            // staging must outlive the last bulk store's read
-        if (etid == 0) SHG_STAMP(5);
+        if (wtid == 0) bulk_wait_read<0>();            // staging must outlive the last bulk store's read
+        if (wg == 0 && wtid == 0) SHG_STAMP(5);
     }
     tc_fence_before();
     __syncthreads();
@@ -448,7 +460,8 @@ template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
-             const __grid_constant__ CUtensorMap tma_b2, const GemmParams p) {
+             const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_d2,
+             const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stg = smem;
@@ -462,7 +475,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -567,24 +579,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             }
         }
     } else {
-        const int quarter = warp & 3, sub = (warp - 2) >> 2;
-        const int etid = (warp - 2) * 32 + lane;
+        const int quarter = warp & 3;
+        const int wg = (warp - 2) >> 2;
+        const int wtid = ((warp - 2) & 3) * 32 + lane;
         int as = 0;
-        uint32_t aphase = 0, nblk = 0;
+        uint32_t aphase = 0;
         const uint32_t leader_empty0 = mapa_u32(smem_u32(tmem_empty), 0);
         for (int tile = pair; tile < total_tiles; tile += n_pairs) {
             const int rem = tile % (p.m_tiles * p.n_tiles);
             const int m0 = (rem / p.n_tiles) * 256 + rank * BM, n0 = (rem % p.n_tiles) * p.block_n;
             const int row = m0 + quarter * 32 + lane;
             const bool row_ok = row < p.m;
-            float* sb = s_bias + as * 256;
             const float* bias = m0 >= p.split_m ? p.bias2 : p.bias;
-            if (etid < 256) sb[etid] = (bias && n0 + etid < p.n) ? __ldg(bias + n0 + etid) : 0.f;
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiSub * 128) : "memory");
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
-            void* dbase = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group ? p.d2 : p.d;
-            epilogue_tile<kEpiSub>(p, sb, t_row, row, row_ok, m0, n0, sub, etid, stg, &tma_d, &tma_pre, nblk, dbase,
-                          [&] { mbar_wait(tmem_full + as, aphase); });
+            const bool second = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group;
+            epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
+                          second ? p.d2 : p.d, [&] { mbar_wait(tmem_full + as, aphase); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_empty0 + as * 8);
@@ -593,7 +603,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 aphase ^= 1;
             }
         }
-        if (etid == 0) bulk_wait_read<0>();
+        if (wtid == 0) bulk_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -728,10 +738,17 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     }
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
     const int stage_bytes = BM * BK * 2 + (pair ? bn / 2 : bn) * BK * 2;
-    const int bar_bytes = 1024 + 2048;   // barriers + TMEM slot + bias staging
-    // bf16 outputs with TMA-legal geometry leave through staged bulk stores
-    p.tma_store = (!p.out_f32 && a->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
-                   (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0) && !(a->block_n & 4096)) ? 1 : 0;
+    const int bar_bytes = 1024;          // barriers + TMEM slot
+    // how D leaves the SM (see epilogue_tile): bf16 outputs with TMA-legal geometry through staged bulk stores, fp32
+    // accumulation (split-K weight gradients) through staged bulk reduce-adds; | 4096 in block_n forces the direct path
+    const bool direct = (a->block_n & 4096) != 0;
+    p.tma_store = kStoreDirect;
+    if (!direct && !p.out_f32 && a->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
+        (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0))
+        p.tma_store = kStoreBf16;
+    else if (!direct && accumulate && a->ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
+             (!a->d2 || (reinterpret_cast<uintptr_t>(a->d2) & 15) == 0))
+        p.tma_store = kStoreReduceF32;
     const int out_bytes = p.tma_store ? kStageOutBytes : 0;
     int n_stages = (227 * 1024 - 1024 - bar_bytes - out_bytes) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
@@ -757,8 +774,8 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
         tb2 = get_tmap_bf16(a->b2, 2, dims, strides, box);     // same geometry as B
         if (!tb2) return SHG_ECUDA;
     }
-    const CUtensorMap *td = ta, *tpre = ta;          // placeholders when the staged store is off
-    if (p.tma_store) {
+    const CUtensorMap *td = ta, *tpre = ta, *td2 = ta;          // placeholders when the staged store is off
+    if (p.tma_store == kStoreBf16) {
         dims[0] = a->n, dims[1] = a->m, box[0] = 64, box[1] = BM;
         strides[0] = (uint64_t)a->ldd * 2;
         td = get_tmap_bf16(a->d, 2, dims, strides, box);
@@ -766,6 +783,16 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
         if (a->preact) {
             tpre = get_tmap_bf16(a->preact, 2, dims, strides, box);
             if (!tpre) return SHG_ECUDA;
+        }
+    } else if (p.tma_store == kStoreReduceF32) {
+        dims[0] = a->n, dims[1] = a->m, box[0] = 32, box[1] = BM;
+        strides[0] = (uint64_t)a->ldd * 4;
+        td = get_tmap(a->d, 2, dims, strides, box, kTmapF32);
+        if (!td) return SHG_ECUDA;
+        td2 = td;
+        if (a->d2) {
+            td2 = get_tmap(a->d2, 2, dims, strides, box, kTmapF32);
+            if (!td2) return SHG_ECUDA;
         }
     }
 
@@ -780,7 +807,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm2_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set2 = true;                                                                                  \
         }                                                                                                      \
-        shg::launch(gemm2_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, p);                                  \
+        shg::launch(gemm2_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p);                                  \
     } while (0)
     if (pair) {
         if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);
@@ -797,7 +824,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             cudaFuncSetAttribute(gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set = true;                                                                                  \
         }                                                                                                     \
-        shg::launch(gemm_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, p);                                  \
+        shg::launch(gemm_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p);                                  \
     } while (0)
     if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM_LAUNCH(false, false);
     else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM_LAUNCH(false, true);

@@ -110,6 +110,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                  "r"(smem_u32(src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// TMA reduce-add of a staged [box] fp32 tile into global memory: the adds happen in L2 on whole lines; clips at the edge.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest N bulk groups of this thread have finished READING their shared-memory source
 template <int N>
@@ -408,8 +415,13 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------- host: TMA descriptor cache
-// 2-D .. 5-D bf16 tensor maps with 128-byte swizzle (out-of-bounds elements read as zero), cached by (ptr, dims, strides, box).
-const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                 const uint32_t* box);
+// 2-D .. 5-D bf16 (or fp32) tensor maps with 128-byte swizzle (out-of-bounds elements read as zero), cached by (ptr, dims, strides, box).
+constexpr int kTmapBf16 = 0, kTmapF32 = 1;
+const CUtensorMap* get_tmap(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, int dtype);
+inline const CUtensorMap* get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                        const uint32_t* box) {
+    return get_tmap(ptr, rank, dims, strides_bytes, box, kTmapBf16);
+}
 
 }  // namespace shg

@@ -136,6 +136,8 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, batch, lq, lk, heads=12, sca
     call("shg_attn_bwd", a, stream(), work=("tensor", 10.0 * batch * heads * lq * lk * 64, "%dx%d" % (lq, lk)))
     if lq <= 128 and o32 is not None and ATTN_BWD_MERGE:
         _lib.launch_count -= 1          # single-query-tile problems take one merged launch instead of two
+        if _lib.profiler is not None:
+            _lib.profiler.calls[-1][5] = 1
 
 
 def layernorm_fwd(x, gamma, beta, eps, residual=None, addend=None, addend_rows=0, save_stats=False, group=None):

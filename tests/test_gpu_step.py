@@ -53,10 +53,14 @@ def test_graph_and_host_steps_match_eager():
 
     for mode in ("graph", "host", "host_prefetch", "host_lagged"):
         tr = _trainer(dev)
+        w0 = tr.store.master.clone()
         tr.capture(to_dev(a[0]), to_dev(a[1]), warmup=1)
-        tr.init_weights(seed=11)                      # capture ran real steps: restore weights and optimiser state
-        tr.exp_avg.zero_(), tr.exp_avg_sq.zero_(), tr.store.grad.zero_()
-        tr.step_count = 0
+        # capture() warms up with real optimiser steps but leaves NO trace of them: weights, Adam moments, the
+        # bf16 shadow, gradients and the step count are what they were (the trajectory must not drift)
+        assert torch.equal(tr.store.master, w0) and tr.step_count == 0
+        assert float(tr.exp_avg.abs().max()) == 0.0 and float(tr.exp_avg_sq.abs().max()) == 0.0
+        assert float(tr.store.grad.abs().max()) == 0.0
+        assert torch.equal(tr.store.shadow, w0[:tr.store.n_matrix].to(torch.bfloat16))
         seq = (a, b, a)
         got = []
         w1 = None
@@ -106,7 +110,7 @@ def test_split_second_backward_half_equals_unsplit():
         scal, d_hg, d_rel, d_act, _ = tr.loss_and_grads(out, batch)
         tr.engine.backward_late_params(ctx, d_hg, d_rel, d_act)
         if split_run:
-            tr.engine.backward_early_params(ctx, part=0)
+            tr.engine.backward_early_params(ctx, part=0, join=False)     # as the data-parallel schedule calls it
             tr.engine.backward_early_params(ctx, part=1)
         else:
             tr.engine.backward_early_params(ctx)
@@ -119,3 +123,29 @@ def test_split_second_backward_half_equals_unsplit():
         lo, hi = sl.start - tr.store.live_begin, sl.stop - tr.store.live_begin
         assert float(a[lo:hi].abs().max()) > 0                      # every bucket actually receives gradients
         assert float((a[lo:hi] - b[lo:hi]).norm() / a[lo:hi].norm()) <= 1e-4
+
+
+
+def test_lr_schedule_survives_host_run_ahead():
+    """The per-step learning rate crosses to the device through a ring of pinned slots (with a single
+    slot the host, which runs ahead of the GPU in the lagged mode, could rewrite it before its queued copy ran).
+    Twelve lagged replays with a steep warm-up schedule; after each call the device-resident lr is copied, in stream
+    order, into a log: every step must have used its own lr, and the step counter must end at twelve."""
+    from shg_vqa_b200.trainer import HotPathTrainer, warmup_linear
+    dev = torch.device("cuda:0")
+    h_inp, h_batch = _make(dev, 4)
+    inp = {k: v.to(dev) for k, v in h_inp.items()}
+    batch = {k: v.to(dev) for k, v in h_batch.items()}
+    tr = HotPathTrainer(dev, lr=1e-3, t_total=24, warmup=0.5, dropout=False)
+    tr.init_weights(seed=11)
+    tr.capture(inp, batch, warmup=1)
+    n = 12                                            # more steps than ring slots (8): slots are reused
+    log = torch.zeros(n, device=dev)
+    for i in range(n):
+        tr.train_step_host(h_inp, h_batch, next_inp=h_inp, next_batch=h_batch, lagged=True)
+        log[i:i + 1].copy_(tr.lr_dev, non_blocking=True)        # ordered after step i's replay, before step i+1's copy
+    tr.drain_losses()
+    torch.cuda.synchronize()
+    want = torch.tensor([1e-3 * warmup_linear(i / 24, 0.5) for i in range(n)])
+    assert tr.step_count == n
+    assert torch.allclose(log.cpu(), want, rtol=1e-6, atol=0), (log.cpu(), want)

@@ -106,10 +106,14 @@ def test_autograd_bridge_matches_trainer(oracle_weights):
             p.add_(m / (v.sqrt() + 1e-6) + 0.01 * p, alpha=-1e-3)
     tr.optimizer_step()
     torch.cuda.synchronize()
-    a, b = model.store.master[tr.store.live_extent.start:][:10], None
-    k = "rel_decoder.layers.2.linear1.weight"
-    same = (named[k].detach() - tr.store.p(k)).abs() <= 1e-6
-    assert float(same.float().mean()) >= 0.99, float(same.float().mean())
+    # BertAdam's first step is sign-like (0.1 g / (sqrt(0.001) |g| + 1e-6)): elements whose gradient is noise-level
+    # flip between the two runs (their loss gradients differ by a bf16 rounding), so compare the UPDATE's direction
+    for k in ("rel_decoder.layers.2.linear1.weight", "class_embed.3.weight",
+              "lxrt_encoder.model.bert.encoder.layer.3.output.dense.weight"):
+        d_bridge = (named[k].detach() - oracle_weights[k].to(dev)).flatten()
+        d_tr = (tr.store.p(k) - oracle_weights[k].to(dev)).flatten()
+        cos = float(d_bridge @ d_tr / (d_bridge.norm() * d_tr.norm()))
+        assert float(d_tr.abs().max()) > 0 and cos >= 0.98, (k, cos)
     # the next forward sees the updated weights (bf16 shadow refreshed from the master the optimiser wrote)
     model.eval()
     with torch.no_grad():
@@ -158,6 +162,8 @@ def test_vqa_training_backward_vs_oracle(oracle_weights):
     named = dict(model.named_parameters())
     worst = []
     for k, t in leaves.items():
+        if not t.is_floating_point():
+            continue
         if t.grad is None or float(t.grad.norm()) < 1e-6:
             assert named[k].grad is None or float(named[k].grad.norm()) < 5e-2, k
             continue

@@ -151,3 +151,20 @@ def test_param_tree_mirrors_reference_module_names(key_shapes):
     p.grad.fill_(2.0)
     off, n, _ = st.offsets["logit_fc.3.bias"]
     assert float(st.grad[off:off + n].sum()) == 2.0 * n
+
+
+def test_local_slow_r50_backbone_surface():
+    """The stock-PyTorch backbone outside the hot path: pytorchvideo's module names (so hub / reference checkpoints
+    load), 31.6 M parameters, res5 feature map with the temporal length preserved and 1/32 of the spatial size."""
+    import torch
+    from shg_vqa_b200.backbone import VideoBackbone
+    vb = VideoBackbone("slow_r50", freeze=True)
+    keys = list(vb.state_dict())
+    assert keys[0] == "backbone.blocks.0.conv.weight"
+    assert "backbone.blocks.3.res_blocks.5.branch2.conv_a.weight" in keys
+    assert vb.state_dict()["backbone.blocks.3.res_blocks.0.branch2.conv_a.weight"].shape == (256, 512, 3, 1, 1)
+    assert vb.state_dict()["backbone.blocks.1.res_blocks.0.branch2.conv_a.weight"].shape == (64, 64, 1, 1, 1)
+    assert abs(sum(p.numel() for p in vb.parameters()) - 31_634_496) == 0
+    assert isinstance(vb.backbone.blocks[-1], torch.nn.Identity)          # video_encoder.py:45
+    y = vb.encode(torch.randn(1, 3, 4, 64, 64))
+    assert tuple(y.shape) == (1, 2048, 4, 2, 2) and y.dtype == torch.float32 and not y.requires_grad

@@ -14,7 +14,7 @@ batch = {k: v.to(dev) for k, v in h_batch.items()}
 for _ in range(3):
     tr.train_step(inp, batch)
 torch.cuda.synchronize()
-prof = _lib.Profiler(); _lib.profiler = prof
+prof = _lib.Profiler(time_events=True); _lib.profiler = prof
 tr.train_step(inp, batch)
 agg = prof.by_tag()
 _lib.profiler = None
