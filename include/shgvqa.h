@@ -267,12 +267,14 @@ int shg_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
  * arrays; the "live" parameters (those that receive gradients — the reference skips p.grad is None) are given as
  * segments: seg_start[i] = offset of segment i, seg_prefix[i] = number of live elements before it (both multiples
  * of 4, device int64), total = live element count.
- * shg_grad_sumsq: out[0] += sum g^2.  shg_bert_adam_step: g' = g * grad_scale * min(1, max_norm/(|g*grad_scale|+1e-6))
+ * shg_grad_sumsq: out[0] = sum g^2, bit-reproducible (fixed-order two-stage sum: data-parallel replicas must derive
+ * the same clip coefficient from the same all-reduced gradients); workspace = 2048 floats, zero-initialised once by
+ * the caller, left zero-countered by every call.  shg_bert_adam_step: g' = g * grad_scale * min(1, max_norm/(|g*grad_scale|+1e-6))
  * (max_norm <= 0: no clipping), then the Adam update in place; refreshes the bf16 shadow (first n_shadow elements
  * of the flat space) and optionally zeroes the gradient for the next step.  lr_dev (device float, may be NULL)
  * overrides lr so that a captured CUDA graph follows the warm-up schedule. */
 int shg_grad_sumsq(const float* grad, const int64_t* seg_start, const int64_t* seg_prefix, int n_seg,
-                   int64_t total, float* out, void* stream);
+                   int64_t total, float* out, float* workspace, void* stream);
 int shg_bert_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow, int64_t n_shadow,
                        const int64_t* seg_start, const int64_t* seg_prefix, int n_seg, int64_t total,
                        const float* sumsq, float max_norm, float lr, const float* lr_dev, float b1, float b2, float eps,

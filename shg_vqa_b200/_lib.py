@@ -90,7 +90,7 @@ SIGNATURES = {
     "shg_act_bwd": [c_vp, c_vp, c_vp, c_i64, c_int, c_vp],
     "shg_bce_logits": [c_vp, c_i64, c_vp, c_int, c_int, c_f32, c_vp, c_vp, c_i64, c_vp],
     "shg_copy3d": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_int, c_vp],
-    "shg_grad_sumsq": [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp],
+    "shg_grad_sumsq": [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp],
     "shg_bert_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_f32, c_f32, c_vp,
                            c_f32, c_f32, c_f32, c_f32, c_f32, c_int, c_vp],
     "shg_f32_to_bf16": [c_vp, c_vp, c_i64, c_vp],

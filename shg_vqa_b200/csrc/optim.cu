@@ -9,11 +9,16 @@
 
 namespace shg {
 
-// sum of squares over the live segments -> out[0] (fp32 atomics on per-block partials)
+// sum of squares over the live segments -> out[0].  DETERMINISTIC: per-block partials go to `ws`, the last block to
+// arrive (counter in ws[kSumsqWs - 1]) adds them in a fixed order.  Data-parallel ranks hold identical all-reduced
+// gradients and must derive the identical clip coefficient from them — fp32 atomics across blocks would make the
+// norm, hence every moment and weight, differ between ranks in the last bits (measured: 60 M of 191 M moments after
+// three steps), and replicas would drift apart.
+constexpr int kSumsqWs = 2048;
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ g,
                                                         const int64_t* __restrict__ seg_start,
                                                         const int64_t* __restrict__ seg_prefix, int n_seg,
-                                                        int64_t total4, float* __restrict__ out) {
+                                                        int64_t total4, float* __restrict__ out, float* __restrict__ ws) {
     float acc = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = i * 4;
@@ -28,12 +33,30 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
     }
     acc = warp_sum(acc);
     __shared__ float red[8];
+    __shared__ int s_last;
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int w = 0; w < 8; ++w) s += red[w];
-        atomicAdd(out, s);
+        ws[blockIdx.x] = s;
+        __threadfence();
+        unsigned int* counter = reinterpret_cast<unsigned int*>(ws + kSumsqWs - 1);
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(ws + i);      // fixed order per thread
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        out[0] = s;
+        *reinterpret_cast<unsigned int*>(ws + kSumsqWs - 1) = 0u;       // ready for the next launch / graph replay
     }
 }
 
@@ -94,14 +117,16 @@ __global__ void __launch_bounds__(256) bert_adam_kernel(float* __restrict__ p, f
 extern "C" {
 
 int shg_grad_sumsq(const float* grad, const int64_t* seg_start, const int64_t* seg_prefix, int n_seg,
-                   int64_t total, float* out, void* stream) {
+                   int64_t total, float* out, float* workspace, void* stream) {
     using namespace shg;
     SHG_REQUIRE(total % 4 == 0 && n_seg >= 1, SHG_ESHAPE, "shg_grad_sumsq: total=%lld must be a multiple of 4",
                 (long long)total);
+    SHG_REQUIRE(workspace && out, SHG_EINVAL, "shg_grad_sumsq: workspace (2048 zero-initialised floats) and out are required");
     int64_t blocks = (total / 4 + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    static_assert(8 * kNumSMs < kSumsqWs - 1, "partials must fit the workspace");
     shg::launch(grad_sumsq_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, grad, seg_start, seg_prefix, n_seg, total / 4,
-                                                                     out);
+                                                                     out, workspace);
     return check_launch("shg_grad_sumsq");
 }
 

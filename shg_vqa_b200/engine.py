@@ -903,50 +903,71 @@ class Engine:
         # (the weight-gradient stream is NOT drained here: a data-parallel trainer issues the all-reduce of these
         # parameters from that stream, see HotPathTrainer._reduce_async; a single-GPU step lets it run on)
 
+    # The second half of the backward in steps, so that a data-parallel trainer can start the all-reduce of each
+    # group of gradients the moment it is final (HotPathTrainer.train_step): begin -> relation layers nr-1 .. 0 ->
+    # end.  backward_early_params() below runs them in sequence (optionally in two parts).
+    def backward_early_begin(self, ctx):
+        """Language layers + embeddings on the side stream (40 tokens per clip: they finish long before the relation
+        side); the hoisted K/V dgrad on the main stream leaves the gradient w.r.t. the relation-layer output."""
+        B = ctx["B"]
+        nl = ctx["dims"][0]
+        kmask = ctx["kmask"]
+        # gradient w.r.t. the language-layer output: CrossEncoder branch (+ LXRT answer branch)
+        d_lang, dxl = ctx.get("d_lang_l"), ctx.get("d_x_lang")
+        if d_lang is None:
+            d_lang = dxl
+        elif dxl is not None:
+            self._acc(d_lang, dxl)
+        self._fork(self.s1)
+        with self._on(self.s1):
+            for i in reversed(range(self.nl)):
+                d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
+            ids, seg, pre, mean, rstd, _, d_emb = ctx["emb"]
+            E = self.emb
+            de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb, in_drop=d_emb)
+            ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
+                     ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
+        if "dkv_mem" in ctx:
+            ctx["d_visn_mid"] = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True, residual=ctx.get("d_x_visn"))
+        else:
+            ctx["d_visn_mid"] = ctx["d_x_visn"]
+        ctx["_lang_pending"] = True
+
+    def backward_r_layer(self, ctx, i, need_dvisn=False):
+        B, nv = ctx["B"], ctx["dims"][1]
+        need0 = need_dvisn or "frontend" in ctx
+        ctx["d_visn_mid"] = self._bert_bwd(self.r_layers[i], ctx["R"][i], ctx["d_visn_mid"], B, nv, None,
+                                           need_dx=(i > 0 or need0))
+
+    def backward_lang_join(self, ctx):
+        """The main stream waits for the language side: its weight gradients are then queued on the wgrad stream."""
+        if ctx.pop("_lang_pending", False):
+            self._join(self.s1)
+
+    def backward_early_end(self, ctx, need_dvisn=False):
+        if "frontend" in ctx:
+            ctx["d_feat"] = self.frontend_bwd(ctx["frontend"], ctx["d_visn_mid"], need_dfeat=need_dvisn)
+        self.backward_lang_join(ctx)
+        self._join(self.sw)
+        self._keep.clear()
+        return ctx["d_visn_mid"]
+
     def backward_early_params(self, ctx, need_dvisn=False, part=None, split=2, join=True):
         """Second half: the hoisted K/V dgrad, relation layers (main stream), language layers and embeddings
-        (side stream).  part=None runs all of it; part=0 runs the whole language side (40 tokens per clip: it ends
-        long before the relation side) and the relation layers with index >= split — their gradients are then final
-        and the data-parallel schedule reduces them under part=1: the remaining relation layers and the Conv3d
-        front-end."""
-        B = ctx["B"]
-        nl, nv = ctx["dims"][0], ctx["dims"][1]
-        kmask = ctx["kmask"]
+        (side stream).  part=None runs all of it; part=0 runs the whole language side and the relation layers with
+        index >= split, part=1 the remaining relation layers and the Conv3d front-end."""
         first, second = part in (None, 0), part in (None, 1)
-        need0 = need_dvisn or "frontend" in ctx
         if first:
-            # gradient w.r.t. the language-layer output: CrossEncoder branch (+ LXRT answer branch)
-            d_lang, dxl = ctx.get("d_lang_l"), ctx.get("d_x_lang")
-            if d_lang is None:
-                d_lang = dxl
-            elif dxl is not None:
-                self._acc(d_lang, dxl)
-            self._fork(self.s1)
-            with self._on(self.s1):
-                for i in reversed(range(self.nl)):
-                    d_lang = self._bert_bwd(self.l_layers[i], ctx["L"][i], d_lang, B, nl, kmask)
-                ids, seg, pre, mean, rstd, _, d_emb = ctx["emb"]
-                E = self.emb
-                de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb, in_drop=d_emb)
-                ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
-                         ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
-            if "dkv_mem" in ctx:
-                d_visn = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True, residual=ctx.get("d_x_visn"))
-            else:
-                d_visn = ctx["d_x_visn"]
+            self.backward_early_begin(ctx)
             r_range = range(self.nr - 1, (split if part == 0 else 0) - 1, -1)
         else:
-            d_visn = ctx["d_visn_mid"]
             r_range = range(min(split, self.nr) - 1, -1, -1)
         for i in r_range:
-            d_visn = self._bert_bwd(self.r_layers[i], ctx["R"][i], d_visn, B, nv, None, need_dx=(i > 0 or need0))
-        ctx["d_visn_mid"] = d_visn
-        if second and "frontend" in ctx:
-            ctx["d_feat"] = self.frontend_bwd(ctx["frontend"], d_visn, need_dfeat=need_dvisn)
+            self.backward_r_layer(ctx, i, need_dvisn)
         if first:
-            self._join(self.s1)
-        if join or second:
-            self._join(self.sw)
+            self.backward_lang_join(ctx)
         if second:
-            self._keep.clear()
-        return d_visn
+            return self.backward_early_end(ctx, need_dvisn)
+        if join:
+            self._join(self.sw)
+        return ctx["d_visn_mid"]

@@ -224,11 +224,45 @@ class ParamStore:
         # relation layers (index >= split) are final after the first part of the second backward half and are
         # reduced under the rest of it
         self.bucket_early_upper, self.bucket_early_rest = self._split_early(mats, is_live, upper_from=2)
+        self.dp_groups = self._dp_groups(is_live)
         # optimiser segment table (one contiguous live span)
         self.n_seg = 1
         self.seg_start = torch.tensor([self.live_begin], dtype=torch.int64, device=self.device)
         self.seg_prefix = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._shadow_fresh = False
+
+    def _dp_groups(self, is_live):
+        """Live span -> {group: [slices]} for the overlapped data-parallel schedule (HotPathTrainer.train_step):
+        'late' (matrices of everything after the LXRT encoder: final after the first backward half), 'r0'..'r4' (one
+        relation layer's matrices each: final right after that layer's backward), 'lang' (language-layer matrices)
+        and 'emb' (BertEmbeddings tables): final once the language side stream has run, 'front' (Conv3d front-end),
+        'vec' (every bias / LayerNorm vector / token: final at the very end).  The groups tile the live span."""
+        import re
+        pat = re.compile(r"\.encoder\.(layer|r_layers)\.(\d+)\.")
+        groups = collections.OrderedDict()
+        order = sorted(self.live_keys, key=lambda k: self.offsets[k][0])
+        for i, k in enumerate(order):
+            off, n, shape = self.offsets[k]
+            end = self.offsets[order[i + 1]][0] if i + 1 < len(order) else self.live_end
+            m = pat.search(k)
+            if ".visn_fc." in k:
+                g = "front"
+            elif off >= self.n_matrix:
+                g = "emb" if k.startswith("lxrt_encoder.model.bert.embeddings.") and k.endswith("embeddings.weight") else "vec"
+            elif not k.startswith("lxrt_encoder."):
+                g = "late"
+            elif m and m.group(1) == "layer":
+                g = "lang"
+            elif m:
+                g = "r%d" % int(m.group(2))
+            else:
+                g = "late"           # LXRT cross layers / pooler when they are live (--taskVQA, x_grad)
+            lst = groups.setdefault(g, [])
+            if lst and lst[-1].stop == off:
+                lst[-1] = slice(lst[-1].start, end)
+            else:
+                lst.append(slice(off, end))
+        return groups
 
     def _split_early(self, mats, is_live, upper_from):
         """(upper, rest) slice lists over the early parameters.  upper = what is final after part 0 of the second

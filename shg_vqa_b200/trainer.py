@@ -125,6 +125,7 @@ class HotPathTrainer:
         self.n_ans = n_answers
         self.scal = torch.zeros(16, device=self.device, dtype=torch.float32)   # loss sums / grad sumsq / error count
         self.scal_den = torch.zeros(8, device=self.device, dtype=torch.float32)   # globally reduced CE sums
+        self.sumsq_ws = torch.zeros(2048, device=self.device, dtype=torch.float32)   # shg_grad_sumsq's partials + counter
         self.global_ce_norm = bool(global_ce_norm)
         self.lr_dev = torch.zeros(1, device=self.device, dtype=torch.float32)   # device-resident lr (graph-safe)
         # lr crosses to the device through a ring of pinned slots, one event each: the host runs ahead of the GPU
@@ -264,10 +265,9 @@ class HotPathTrainer:
         self._ensure_opt_state()
         lr = self.current_lr()
         sumsq = self.scal[9:10]
-        sumsq.zero_()
         n_live = st.n_live
         ops.call("shg_grad_sumsq", ops.ptr(st.grad), ops.ptr(st.seg_start), ops.ptr(st.seg_prefix), st.n_seg, n_live,
-                 ops.ptr(sumsq), ops.stream(), work=("hbm", 4.0 * n_live))
+                 ops.ptr(sumsq), ops.ptr(self.sumsq_ws), ops.stream(), work=("hbm", 4.0 * n_live))
         ops.call("shg_bert_adam_step", ops.ptr(st.master), ops.ptr(st.grad), ops.ptr(self.exp_avg),
                  ops.ptr(self.exp_avg_sq), ops.ptr(st.shadow), st.n_matrix, ops.ptr(st.seg_start),
                  ops.ptr(st.seg_prefix), st.n_seg, n_live, ops.ptr(sumsq), self.max_norm, lr,
@@ -303,11 +303,12 @@ class HotPathTrainer:
 
     def train_step(self, inp, batch, lr_on_device=False):
         """One training step.  Data-parallel runs (world_size > 1) overlap the path's only collective with the
-        backward: the gradient span is reduced in three buckets, each started as soon as its gradients are final —
-        (1) everything after the LXRT encoder (decoders, heads, CrossEncoder, query embeddings, hoisted K/V
-        weights) under the whole LXRT backward, (2) the language layers, embeddings and upper relation layers under
-        the lower relation layers, (3) the rest.  The same code path runs eagerly and under CUDA-graph capture
-        (the NCCL kernels become nodes of the step's graph on their own branch)."""
+        backward: the gradient span is reduced in groups (ParamStore.dp_groups), each started as soon as its
+        gradients are final — everything after the LXRT encoder (decoders, heads, CrossEncoder, hoisted K/V weights)
+        under the whole LXRT backward; each relation layer right after its own backward (the language layers and
+        embedding tables ride with relation layer 2); only relation layer 0 and the small vectors (30 MB) are left
+        for the end.  The same code path runs eagerly and under CUDA-graph capture (the NCCL kernels become nodes of
+        the step's graph on their own branch)."""
         self._advance_seed()
         out, ctx = self.engine.forward(inp, train=True)
         scal, d_hg, d_rel, d_act, _ = self.loss_and_grads(out, batch)
@@ -318,13 +319,22 @@ class HotPathTrainer:
         elif self.world_size == 1:
             self.engine.backward(ctx, d_hg, d_rel, d_act, need_dvisn=self.backbone_grad)
         else:
-            st = self.store
-            self.engine.backward_late_params(ctx, d_hg, d_rel, d_act)
-            works = self._reduce_async([st.bucket_late])
-            self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=0, join=False)
-            works += self._reduce_async(st.bucket_early_upper)
-            self.engine.backward_early_params(ctx, need_dvisn=self.backbone_grad, part=1)
-            works += self._reduce_async(st.bucket_early_rest)
+            # the path's only collective, overlapped: every group of gradients is reduced as soon as it is final
+            eng, grp = self.engine, self.store.dp_groups
+            eng.backward_late_params(ctx, d_hg, d_rel, d_act)
+            works = self._reduce_async(grp["late"])
+            eng.backward_early_begin(ctx)
+            for i in reversed(range(eng.nr)):
+                eng.backward_r_layer(ctx, i, self.backbone_grad)
+                if i == 0:
+                    break
+                slices = list(grp["r%d" % i])
+                if i == min(2, eng.nr - 1):
+                    eng.backward_lang_join(ctx)            # the 40-token language side finished long ago
+                    slices += grp["lang"] + grp["emb"]
+                works += self._reduce_async(slices)
+            eng.backward_early_end(ctx, self.backbone_grad)
+            works += self._reduce_async(grp["r0"] + grp.get("front", []) + grp["vec"])
             for w in works:
                 w.wait()                                   # stream-level: the optimiser waits for NCCL's stream
         self.d_feat = ctx.get("d_feat")      # gradient wrt the backbone features (backbone_grad runs)
@@ -381,6 +391,13 @@ class HotPathTrainer:
         self._restore_state(snap)
         torch.cuda.synchronize()
         return self.graph
+
+    def release(self):
+        """Drop the captured graph (it holds NCCL resources: destroy_process_group() blocks while it is alive)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
 
     def train_step_graph(self, inp=None, batch=None):
         """Replay the captured step; optional new inputs (device or pinned-host tensors) are copied in first.

@@ -61,11 +61,11 @@ def test_live_gradient_allreduce_and_sharding_world2():
     assert (n0, b0) == (n1, b1)
 
 
-def test_data_parallel_buckets_tile_the_live_span():
-    """The three all-reduce buckets of the overlapped data-parallel schedule (HotPathTrainer.train_step: late |
-    early-upper | early-rest) must cover the live gradient span exactly once — with and without the Conv3d
-    front-end — or a key-order change would silently leave gradients unreduced / reduced twice.  Also pins what
-    belongs to which bucket: nothing of the LXRT encoder is 'late', every language layer is 'upper'."""
+def test_data_parallel_groups_tile_the_live_span():
+    """The gradient groups of the overlapped data-parallel schedule (ParamStore.dp_groups, reduced by
+    HotPathTrainer.train_step as each becomes final) must cover the live gradient span exactly once — with and without
+    the Conv3d front-end — or a key-order change would silently leave gradients unreduced / reduced twice.  Also pins
+    what belongs where: nothing of the LXRT encoder is 'late', every relation layer is its own group."""
     import torch
     from shg_vqa_b200.params import ParamStore, build_key_shapes
     from shg_vqa_b200.trainer import live_in_hgqa_training, live_with_frontend
@@ -73,34 +73,29 @@ def test_data_parallel_buckets_tile_the_live_span():
     for live in (live_in_hgqa_training, live_with_frontend):
         st = ParamStore(ks, "cpu", with_grad=False, live=live)
         cover = torch.zeros(st.n_total, dtype=torch.int32)
-        for sl in [st.bucket_late] + list(st.bucket_early_upper) + list(st.bucket_early_rest):
-            cover[sl] += 1
+        for name, slices in st.dp_groups.items():
+            for sl in slices:
+                cover[sl] += 1
         assert int(cover[st.live_extent].min()) == 1 and int(cover[st.live_extent].max()) == 1
-        outside = cover.clone()
-        outside[st.live_extent] = 0
-        assert int(outside.sum()) == 0
+        assert int(cover.sum()) == st.n_live
+        want = {"late", "lang", "emb", "vec", "r0", "r1", "r2", "r3", "r4"} | ({"front"} if live is live_with_frontend else set())
+        assert set(st.dp_groups) == want
 
-        def bucket_of(key):
+        def group_of(key):
             off = st.offsets[key][0]
-            if st.bucket_late.start <= off < st.bucket_late.stop:
-                return "late"
-            if any(s.start <= off < s.stop for s in st.bucket_early_upper):
-                return "upper"
-            assert any(s.start <= off < s.stop for s in st.bucket_early_rest), key
-            return "rest"
+            return next(n for n, sls in st.dp_groups.items() if any(s.start <= off < s.stop for s in sls))
         e = "lxrt_encoder.model.bert.encoder."
-        assert bucket_of("rel_decoder.layers.0.linear1.weight") == "late"
-        assert bucket_of("hgq_encoder.cross_attn_layer.cross.lang_inter.dense.weight") == "late"
-        assert bucket_of("class_embed.3.weight") == "late"
+        assert group_of("rel_decoder.layers.0.linear1.weight") == "late"
+        assert group_of("hgq_encoder.cross_attn_layer.cross.lang_inter.dense.weight") == "late"
+        assert group_of("class_embed.3.weight") == "late" and group_of("class_embed.3.bias") == "vec"
         for i in range(5):
-            assert bucket_of(e + "layer.%d.intermediate.dense.weight" % i) == "upper"
-        for i in (2, 3, 4):
-            assert bucket_of(e + "r_layers.%d.output.dense.weight" % i) == "upper"
-        for i in (0, 1):
-            assert bucket_of(e + "r_layers.%d.output.dense.weight" % i) == "rest"
-        assert bucket_of("lxrt_encoder.model.bert.embeddings.word_embeddings.weight") == "upper"
+            assert group_of(e + "layer.%d.intermediate.dense.weight" % i) == "lang"
+            assert group_of(e + "r_layers.%d.output.dense.weight" % i) == "r%d" % i
+            assert group_of(e + "r_layers.%d.attention.self.query.weight" % i) == "r%d" % i
+            assert group_of(e + "r_layers.%d.output.LayerNorm.weight" % i) == "vec"
+        assert group_of("lxrt_encoder.model.bert.embeddings.word_embeddings.weight") == "emb"
         if live is live_with_frontend:
-            assert bucket_of(e + "visn_fc.conv.1.weight") == "rest"
+            assert group_of(e + "visn_fc.conv.1.weight") == "front"
         for k in st.live_keys:                      # no live tensor of the LXRT encoder may be reduced early
             if k.startswith("lxrt_encoder."):
-                assert bucket_of(k) != "late", k
+                assert group_of(k) != "late", k
