@@ -163,19 +163,10 @@ def kernel_table_from_replay(tr, work_by_entry, pre=None):
         tr.train_step_graph()
     torch.cuda.synchronize()
 
-    def two():                                   # the second replay is the one reported (ranks in lock-step by then)
-        tr.train_step_graph()
-        torch.cuda.synchronize()
-        tr.train_step_graph()
-    kernels, _ = cupti_records(two, pre)
-    # keep the kernels of the second replay: everything after the widest idle gap (the synchronize between the two)
-    run_end, best, cut = kernels[0][0] + kernels[0][1], -1.0, 0
-    for i in range(1, len(kernels)):
-        gap = kernels[i][0] - run_end
-        if gap > best:
-            best, cut = gap, i
-        run_end = max(run_end, kernels[i][0] + kernels[i][1])
-    kernels = kernels[cut:]
+    kernels, _ = cupti_records(tr.train_step_graph, pre)
+    # the barrier the ranks met at is itself a small NCCL kernel: it ends before the step's first compute kernel starts
+    first_compute = min(s for s, d, n, _ in kernels if "nccl" not in n)
+    kernels = [k for k in kernels if not ("nccl" in k[2] and k[0] + k[1] <= first_compute)]
     agg = {}
     for s, d, name, _ in kernels:
         a = agg.setdefault(family_of(name), dict(launches=0, us=0.0))

@@ -125,6 +125,13 @@ typedef struct {
      * d2 NULL = ordinary accumulation.  k_split % 64 == 0. */
     void* d2;
     int k_split;
+    /* optional scratch for the tail-split schedule of CTA-pair tiles (the tiles of a last, at most quarter-full wave
+     * are cut along K over the idle SMs; partial sums meet here): caller-owned device memory, 16-byte aligned, ALL ZERO
+     * on entry and left all zero on return, used by one launch at a time (one buffer per stream).  NULL / too small =
+     * plain schedule.  18 MB covers every shape (37 tiles x 2 x 128 x 256 fp32 + 1 KB of counters); the bs32 step
+     * needs 2.1 MB. */
+    void* workspace;
+    int64_t workspace_bytes;
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
 /* Debug aid: CTA 0 of subsequent shg_gemm launches writes 7 %globaltimer phase stamps to buf (8 x u64 device
@@ -160,6 +167,10 @@ typedef struct {
                                  k/32 = key k kept), so that the backward reads 1 bit instead of re-hashing per element */
 } shg_attn_args;
 int shg_attn_fwd(const shg_attn_args* args, void* stream);
+/* Key length from which shg_attn_fwd uses the chunked kernel (online softmax over 128-key chunks, two CTAs per SM)
+ * instead of the whole-row kernel; default 257 (the 393-token visual memory), also SHG_ATTN_FWD2_MIN_LK.  Both
+ * kernels give the same results within the tolerance stated in tests/test_gpu_kernels.py. */
+int shg_set_attn_fwd_chunked_min_lk(int min_lk);
 
 /* Backward of the above (autograd of lxrt/modeling_capsbert.py:394-417 / nn.MultiheadAttention).  Recomputes
  * the probabilities from q, k and the saved lse; d_o is the gradient of o; writes dq/dk/dv (bf16, same head

@@ -29,7 +29,8 @@ class GemmArgs(ctypes.Structure):
                 ("mul_aux", c_vp), ("mul_mode", c_int), ("mul_scale", c_f32),
                 ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp),
                 ("flags", c_int), ("splits", c_int), ("block_n", c_int),
-                ("b2", c_vp), ("bias2", c_vp), ("split_m", c_int), ("d2", c_vp), ("k_split", c_int)]
+                ("b2", c_vp), ("bias2", c_vp), ("split_m", c_int), ("d2", c_vp), ("k_split", c_int),
+                ("workspace", c_vp), ("workspace_bytes", c_i64)]
 
 
 class AttnArgs(ctypes.Structure):
@@ -65,6 +66,7 @@ SIGNATURES = {
     "shg_version": [],
     "shg_device_check": [c_int],
     "shg_set_attn_bwd_merge": [c_int],
+    "shg_set_attn_fwd_chunked_min_lk": [c_int],
     "shg_lsap_batched": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "shg_match_from_logits": [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_vp],
@@ -150,7 +152,7 @@ def check(rc):
 
 
 # kernels launched per entry point (for the bench's gpu_launches count)
-LAUNCHES = {"shg_attn_bwd": 2, "shg_version": 0, "shg_device_check": 0, "shg_set_attn_bwd_merge": 0}
+LAUNCHES = {"shg_attn_bwd": 2, "shg_version": 0, "shg_device_check": 0, "shg_set_attn_bwd_merge": 0, "shg_set_attn_fwd_chunked_min_lk": 0}
 launch_count = 0
 profiler = None     # set to a Profiler to time every call with CUDA events on the launching stream
 

@@ -261,6 +261,307 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 }
 
 // =====================================================================================================
+// Forward for long key sequences (Lk > 256: the 393 visual tokens): chunked, two CTAs per SM.
+//
+// The kernel above keeps the whole score row in TMEM (416 + 64 columns -> a 512-column allocation) and Q, K, V of the
+// head in shared memory (130 KB): ONE CTA per SM, whose phases — operand load, QK^T, max pass, exponential pass, PV,
+// store — run strictly one after the other (ncu r01c: tensor pipe 6 % active, issue slots 33 % used: latency-bound).
+// Here keys are processed in chunks of 128 with an online softmax, so a CTA needs 192 TMEM columns (S chunk + O
+// chunk -> a 256-column allocation) and 85 KB of shared memory (Q, one K chunk, one V chunk, one P chunk): TWO CTAs are
+// resident per SM and fill each other's bubbles.  Inside a CTA a ninth warp issues every TMA load and tcgen05.mma, and
+// issues S_{c+1} = Q.K_{c+1}^T BEFORE O_c = P_c.V_c, so the softmax of chunk c+1 also overlaps the PV product of
+// chunk c.  O is accumulated in REGISTERS (each PV product is a fresh [128 x 64] tile read back with tcgen05.ld):
+//   a_c = a_{c-1} * 2^(M_{c-1} - M_c) + P_c.V_c,   l_c = l_{c-1} * 2^(M_{c-1} - M_c) + rowsum(P_c),   out = a / l
+// with M_c the running row maximum (log2 domain), P_c = bf16(2^(s - M_c)) and rowsum taken over the ROUNDED values
+// the tensor core consumes, so the output stays an exact convex combination of V rows (see the kernel above).
+//   warps 0..7 : softmax — thread = (query row, half of the chunk's 128 key columns; half of O's 64 columns)
+//   warp  8    : TMA + MMA issuer (one lane)
+// =====================================================================================================
+constexpr int kFwd2Threads = 288;
+constexpr int kFwd2Chunk = 128;
+
+struct Fwd2Bars {
+    uint64_t q, k, v, s, sfree, p, pv;
+};
+
+template <bool HAS_KMASK, bool DROP>
+__global__ void __launch_bounds__(kFwd2Threads, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                 const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                 // 128 x 128 B
+    uint8_t* sK = smem + 16384;         // one chunk: 128 keys x 128 B
+    uint8_t* sV = smem + 32768;         // one chunk
+    uint8_t* sP = smem + 49152;         // one chunk: two [128 x 64] bf16 blocks
+    float* s_kmask = reinterpret_cast<float*>(smem + 81920);          // [448] additive key mask * log2(e)
+    float* s_red = s_kmask + 448;                                      // [2][128]
+    Fwd2Bars* bars = reinterpret_cast<Fwd2Bars*>(s_red + 256);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_ch = (p.lk + kFwd2Chunk - 1) / kFwd2Chunk;
+
+    if (tid == 0) {
+        mbar_init(&bars->q, 1);
+        mbar_init(&bars->k, 1);
+        mbar_init(&bars->v, 1);
+        mbar_init(&bars->s, 1);
+        mbar_init(&bars->sfree, 8);
+        mbar_init(&bars->p, 8);
+        mbar_init(&bars->pv, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_v);
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 256);
+    if (HAS_KMASK)
+        for (int k = tid; k < p.lk32; k += kFwd2Threads)
+            s_kmask[k] = k < p.lk ? p.key_mask[(size_t)b * p.lk + k] * 1.4426950408889634f : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_s = tmem, t_o = tmem + kFwd2Chunk;
+
+    if (warp == 8) {
+        // ---------------------------------------------------------------- TMA + MMA issuer
+        if (lane == 0) {
+            const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP);
+            const uint32_t idesc_o = make_idesc_bf16(128, kHeadDim, 0, 1);
+            mbar_expect_tx(&bars->q, 16384);
+            tma_load_3d(sQ, &tma_q, &bars->q, h * kHeadDim, q0, b);
+            mbar_expect_tx(&bars->k, 16384);
+            tma_load_3d(sK, &tma_k, &bars->k, h * kHeadDim, 0, b);
+            mbar_expect_tx(&bars->v, 16384);
+            tma_load_3d(sV, &tma_v, &bars->v, h * kHeadDim, 0, b);
+            // O_j = P_j . V_j (fresh tile), then V / P buffers are free: fetch the next V chunk
+            auto issue_pv = [&](int j) {
+                const int n16 = min(kFwd2Chunk, p.lk16 - j * kFwd2Chunk);
+                mbar_wait(&bars->p, j & 1);
+                mbar_wait(&bars->v, j & 1);
+                tc_fence_after();
+                for (int k = 0; k < n16; k += 16)
+                    umma_bf16(t_o, make_smem_desc(ap + (k >> 6) * 16384 + ((k & 63) >> 4) * 32, 16, 1024),
+                              make_smem_desc(av + k * 128, 8192, 1024), idesc_o, k > 0);
+                tc_commit(&bars->pv);
+                mbar_wait(&bars->pv, j & 1);
+                if (j + 1 < n_ch) {
+                    mbar_expect_tx(&bars->v, 16384);
+                    tma_load_3d(sV, &tma_v, &bars->v, h * kHeadDim, (j + 1) * kFwd2Chunk, b);
+                }
+            };
+            mbar_wait(&bars->q, 0);
+            for (int c = 0; c < n_ch; ++c) {
+                const int n16 = min(kFwd2Chunk, p.lk16 - c * kFwd2Chunk);
+                mbar_wait(&bars->k, c & 1);
+                if (c > 0) mbar_wait(&bars->sfree, (c - 1) & 1);       // every softmax warp is done with S_{c-1}
+                tc_fence_after();
+                const uint32_t idesc_s = make_idesc_bf16(128, n16, 0, 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(t_s, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(ak + ks * 32, 16, 1024),
+                              idesc_s, ks > 0);
+                tc_commit(&bars->s);
+                if (c > 0) issue_pv(c - 1);          // after S_c: the softmax of chunk c runs under this product
+                mbar_wait(&bars->s, c & 1);           // S_c complete: the K buffer is free
+                if (c + 1 < n_ch) {
+                    mbar_expect_tx(&bars->k, 16384);
+                    tma_load_3d(sK, &tma_k, &bars->k, h * kHeadDim, (c + 1) * kFwd2Chunk, b);
+                }
+            }
+            issue_pv(n_ch - 1);
+        }
+    } else {
+        // ---------------------------------------------------------------- softmax warps
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const int q = q0 + row;
+        const uint32_t t_row = (uint32_t(quarter * 32) << 16);
+        const bool rows_live = q0 + quarter * 32 < p.lq;       // warps past Lq (393 = 3 x 128 + 9) only keep the barriers going
+        const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
+        const float c1 = p.scale * 1.4426950408889634f;
+        uint32_t dkey = 0, dth = 0, row_pair0 = 0;
+        if (DROP) {
+            dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
+            row_pair0 = attn_row_pair0(b, p.heads, h, p.lq, q, p.lk);
+        }
+        if (!rows_live) {
+            // rows past Lq are never written below; the PV product still reads them: keep them finite (zero), so that no
+            // NaN is left behind in TMEM for whoever allocates these columns next
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(sP + half * 16384 + row * 128 + (j << 4)) = make_uint4(0, 0, 0, 0);
+        }
+        float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+        float o_acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+        for (int c = 0; c < n_ch; ++c) {
+            const int kc0 = c * kFwd2Chunk;                       // first key of the chunk
+            const int n16 = min(kFwd2Chunk, p.lk16 - kc0);        // columns the MMA produced
+            const int col0 = half * 64;                           // my columns of the chunk: [col0, col0 + 64)
+            const int n_mine = rows_live ? max(0, min(64, n16 - col0)) : 0;   // of those, how many exist (multiple of 16)
+            // dropout keep bits of my 64 columns, hashed BEFORE the wait for the scores: pure ALU work that fills issue
+            // slots the warp would otherwise spend stalled on the barrier (the hash is ~60 % of the pass's instructions)
+            uint32_t keep_w[2] = {0xffffffffu, 0xffffffffu};
+            if (DROP) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    uint32_t bits = 0;
+                    if (w * 32 < n_mine) {
+                        const uint32_t pb = row_pair0 + ((kc0 + col0 + w * 32) >> 1);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) bits |= drop_pair(dkey, pb + i, dth) << (2 * i);
+                    }
+                    keep_w[w] = bits;
+                }
+            }
+            mbar_wait(&bars->s, c & 1);
+            tc_fence_after();
+            // pass A: row maximum over my columns
+            float mx = -INFINITY;
+            for (int g = 0; g < n_mine; g += 32) {
+                uint32_t raw[32];
+                tmem_ld32(tmem + t_row + col0 + g, raw);
+                tmem_ld_wait();
+                const int k0 = kc0 + col0 + g;
+                if (!HAS_KMASK && k0 + 32 <= k_lim) {        // whole group visible, no mask: max commutes with the scale
+                    float m2 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m2 = fmaxf(m2, __uint_as_float(raw[i]));
+                    mx = fmaxf(mx, m2 * c1);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float t = __uint_as_float(raw[i]) * c1;
+                        if (HAS_KMASK) t += s_kmask[min(k0 + i, 447)];
+                        mx = fmaxf(mx, k0 + i < k_lim ? t : -INFINITY);
+                    }
+                }
+            }
+            s_red[half * 128 + row] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mx = fmaxf(s_red[row], s_red[128 + row]);
+            const float m_new = fmaxf(m_run, mx);
+            const float m_use = m_new == -INFINITY ? 0.f : m_new;
+            const float alpha = m_run == -INFINITY ? 0.f : ex2_approx(m_run - m_use);
+            // O_{c-1} (relative to M_{c-1}) joins the accumulator; the P / V buffers and the O tile are then free
+            if (c > 0) {
+                mbar_wait(&bars->pv, (c - 1) & 1);
+                tc_fence_after();
+                if (rows_live) {
+                    uint32_t ro[32];
+                    tmem_ld32(t_o + t_row + half * 32, ro);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha_prev, __uint_as_float(ro[i]));
+                }
+            }
+            alpha_prev = alpha;
+            // pass B: probabilities of my columns -> bf16 -> P block `half` (row = 128 B, 16-byte units swizzled)
+            float sum = 0.f;
+            uint8_t* prow = sP + half * 16384 + row * 128;
+            for (int g = 0; g < n_mine; g += 32) {
+                uint32_t raw[32];
+                tmem_ld32(tmem + t_row + col0 + g, raw);
+                tmem_ld_wait();
+                float pv[32];
+                const int k0 = kc0 + col0 + g;
+                if (k0 + 32 <= k_lim) {                   // whole group visible: no per-element predicate
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        pv[i] = ex2_approx(HAS_KMASK ? fmaf(__uint_as_float(raw[i]), c1, s_kmask[min(k0 + i, 447)] - m_use)
+                                                     : fmaf(__uint_as_float(raw[i]), c1, -m_use));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float t = fmaf(__uint_as_float(raw[i]), c1, -m_use);
+                        if (HAS_KMASK) t += s_kmask[min(k0 + i, 447)];
+                        pv[i] = k0 + i < k_lim ? ex2_approx(t) : 0.f;
+                    }
+                }
+                const uint32_t keep_bits = keep_w[g >> 5];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    u.x = pack_bf16x2(pv[8 * j], pv[8 * j + 1]), u.y = pack_bf16x2(pv[8 * j + 2], pv[8 * j + 3]);
+                    u.z = pack_bf16x2(pv[8 * j + 4], pv[8 * j + 5]), u.w = pack_bf16x2(pv[8 * j + 6], pv[8 * j + 7]);
+                    sum += (__uint_as_float(u.x << 16) + __uint_as_float(u.x & 0xffff0000u)) +
+                           (__uint_as_float(u.y << 16) + __uint_as_float(u.y & 0xffff0000u)) +
+                           (__uint_as_float(u.z << 16) + __uint_as_float(u.z & 0xffff0000u)) +
+                           (__uint_as_float(u.w << 16) + __uint_as_float(u.w & 0xffff0000u));
+                    if (DROP) {
+                        // bits 2i, 2i+1 of the word = keep flags of the packed pair i
+                        const uint32_t kb = keep_bits >> (8 * j);
+                        u.x &= (kb & 1u) * 0xffffu + ((kb >> 1) & 1u) * 0xffff0000u;
+                        u.y &= ((kb >> 2) & 1u) * 0xffffu + ((kb >> 3) & 1u) * 0xffff0000u;
+                        u.z &= ((kb >> 4) & 1u) * 0xffffu + ((kb >> 5) & 1u) * 0xffff0000u;
+                        u.w &= ((kb >> 6) & 1u) * 0xffffu + ((kb >> 7) & 1u) * 0xffff0000u;
+                    }
+                    *reinterpret_cast<uint4*>(prow + ((((g >> 3) + j) ^ (row & 7)) << 4)) = u;
+                }
+                if (DROP && p.drop_bits && q < p.lq)
+                    p.drop_bits[(((size_t)b * p.heads + h) * p.lq + q) * (p.lk32 >> 5) + ((kc0 + col0 + g) >> 5)] = keep_bits;
+            }
+            l_run = fmaf(l_run, alpha, sum);
+            m_run = m_new;
+            // S_c is consumed (TMEM) and P_c is in shared memory: hand both to the issuer
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bars->sfree);
+                mbar_arrive(&bars->p);
+            }
+        }
+        // last PV product
+        mbar_wait(&bars->pv, (n_ch - 1) & 1);
+        tc_fence_after();
+        if (rows_live) {
+            uint32_t ro[32];
+            tmem_ld32(t_o + t_row + half * 32, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha_prev, __uint_as_float(ro[i]));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // s_red: everyone has read the last chunk's maxima
+        s_red[half * 128 + row] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float sum = s_red[row] + s_red[128 + row];
+        const float inv = DROP ? 1.0f / (sum * (1.0f - p.drop.p)) : 1.0f / sum;
+        if (rows_live && q < p.lq) {
+            __nv_bfloat16* dst = p.o + ((size_t)b * p.lq + q) * p.ldo + h * kHeadDim + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                uint4 u;
+                u.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv), u.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+                u.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv), u.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+                *reinterpret_cast<uint4*>(dst + i) = u;
+            }
+            if (p.o_f32) {
+                float* df = p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(df + i) =
+                        make_float4(o_acc[i] * inv, o_acc[i + 1] * inv, o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+            }
+            // natural-log log-sum-exp of the scaled, masked scores
+            if (p.lse && half == 0)
+                p.lse[((size_t)b * p.heads + h) * p.lq + q] = (m_run + log2f(sum)) * 0.6931471805599453f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+// =====================================================================================================
 // Backward.  Two passes, each recomputing the probabilities from Q, K and the saved log-sum-exp:
 //   dq pass  : CTA = (128-query tile, head, batch); loops over 128-key chunks;   dQ  = scale * dS . K
 //   dkv pass : CTA = (128-key tile,  head, batch); loops over 128-query chunks;  dV  = P^T . dO,
@@ -656,7 +957,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     if (DROP == 1) dp = drop_keep(dkey, 2ull * row_pair0 + (uint32_t)(key0 + i), dth) ? dp * inv_keep : 0.f;
                     if (DROP == 2) dp = (keep_word >> i) & 1u ? dp * inv_keep : 0.f;
                     acc_p += pr;
-                    acc_pd = fmaf(pr, dp, acc_pd);
+                    // columns past the chunk's keys were never written by the S / dP products (stale TMEM, possibly
+                    // NaN): 0 * NaN must not reach the row sum
+                    acc_pd = fmaf(pr, i < n_vis ? dp : 0.f, acc_pd);
                 }
             } else {
                 uint32_t ds[16];
@@ -972,6 +1275,11 @@ static const CUtensorMap* head_tmap(const void* ptr, int64_t ld, int heads, int 
 
 }  // namespace shg
 
+static int g_fwd2_min_lk = -1;    // key length from which the chunked two-CTA-per-SM forward is used (default 257)
+extern "C" int shg_set_attn_fwd_chunked_min_lk(int min_lk) {
+    g_fwd2_min_lk = min_lk < 1 ? 1 : min_lk;
+    return SHG_OK;
+}
 static int g_attn_merge = -1;     // single-query-tile backward in one merged pass (default on; SHG_ATTN_MERGE=0: two passes)
 extern "C" int shg_set_attn_bwd_merge(int on) {
     g_attn_merge = on ? 1 : 0;
@@ -1023,6 +1331,33 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const bool drop = p.drop.p > 0.f;
     dim3 grid((a->lq + 127) / 128, a->heads, a->batch);
+    if (g_fwd2_min_lk < 0) {
+        const char* e = getenv("SHG_ATTN_FWD2_MIN_LK");
+        g_fwd2_min_lk = e ? atoi(e) : 257;
+    }
+    if (a->lk >= g_fwd2_min_lk) {
+        // long key sequences (the 393 visual tokens): chunked online-softmax kernel, two CTAs per SM
+        const CUtensorMap* tk2 = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, kFwd2Chunk);
+        const CUtensorMap* tv2 = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, kFwd2Chunk);
+        if (!tk2 || !tv2) return SHG_ECUDA;
+        const size_t smem2 = 81920 + (448 + 256) * 4 + sizeof(Fwd2Bars) + 16 + 1024;
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(attn_fwd2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+            cudaFuncSetAttribute(attn_fwd2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+            cudaFuncSetAttribute(attn_fwd2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+            cudaFuncSetAttribute(attn_fwd2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+            attr2 = true;
+        }
+        if (a->mask_mode == 1) {
+            if (drop) shg::launch(attn_fwd2_kernel<true, true>, grid, kFwd2Threads, smem2, s, *tq, *tk2, *tv2, p);
+            else shg::launch(attn_fwd2_kernel<true, false>, grid, kFwd2Threads, smem2, s, *tq, *tk2, *tv2, p);
+        } else {
+            if (drop) shg::launch(attn_fwd2_kernel<false, true>, grid, kFwd2Threads, smem2, s, *tq, *tk2, *tv2, p);
+            else shg::launch(attn_fwd2_kernel<false, false>, grid, kFwd2Threads, smem2, s, *tq, *tk2, *tv2, p);
+        }
+        return check_launch("shg_attn_fwd(chunked)");
+    }
     if (a->mask_mode == 1) {
         if (drop) shg::launch(attn_fwd_kernel<true, true>, grid, kAttnThreads, smem, s, *tq, *tk, *tv, p);
         else shg::launch(attn_fwd_kernel<true, false>, grid, kAttnThreads, smem, s, *tq, *tk, *tv, p);

@@ -44,7 +44,38 @@ struct GemmParams {
     const float* bias2;
     int kb_group;              // grouped split-K accumulation: splits starting at k-block >= kb_group add into d2
     void* d2;
+    // tail split (CTA-pair kernel): the tiles of the last, sparsely filled wave are cut along K into tail_s slices
+    // each, spread over the otherwise idle pairs; partial sums meet in `ws`, the last slice to arrive does the epilogue
+    int tail_first;            // first split tile (= number of whole tiles before it); INT_MAX: off
+    int tail_s, tail_kb;       // slices per split tile, k-blocks per slice
+    int total_items;           // whole tiles + split tiles * tail_s
+    float* ws;                 // [split tile][CTA rank][block_n / 4][128 rows] float4, all zero between launches
+    unsigned int* ws_cnt;      // [split tile][CTA rank] arrival counters, zero between launches
 };
+
+// work item `it` of the pair kernel -> output tile, k-block range, whether it is a K-slice of a split tile
+struct PairItem {
+    int tile, kb0, kb1;
+    bool partial;
+};
+template <bool TAIL>
+__device__ __forceinline__ PairItem pair_item(const GemmParams& p, int it) {
+    PairItem r;
+    if (!TAIL || it < p.tail_first) {
+        r.tile = it;
+        const int split = it / (p.m_tiles * p.n_tiles);
+        r.kb0 = split * p.kb_per_split;
+        r.kb1 = min(r.kb0 + p.kb_per_split, p.kb_total);
+        r.partial = false;
+    } else {
+        const int j = it - p.tail_first;
+        r.tile = p.tail_first + j / p.tail_s;
+        r.kb0 = (j % p.tail_s) * p.tail_kb;
+        r.kb1 = min(r.kb0 + p.tail_kb, p.kb_total);
+        r.partial = true;
+    }
+    return r;
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -87,7 +118,7 @@ template <class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* __restrict__ bias, uint32_t t_row,
                                               int row, bool row_ok, int m0, int n0, int wg, int wtid, uint8_t* stg,
                                               const CUtensorMap* tm_d, const CUtensorMap* tm_pre, void* dbase,
-                                              WaitFn wait_accumulator) {
+                                              float* sbias, WaitFn wait_accumulator, float4* ws_src = nullptr) {
     constexpr int CH = 16, NV = 2;               // register chunk: 16 columns = 2 x 16-byte bf16 vectors
     const int mode = p.tma_store;
     const int uw = mode == kStoreReduceF32 ? 32 : 64;          // unit block width
@@ -114,6 +145,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
         }
     };
     if (wg * uw < p.block_n) prefetch(wg * uw);
+    // bias of this warpgroup's column blocks -> its 64-float strip of shared memory (zero past N), while the main
+    // loop is still running: a per-chunk __ldg would put an L2 round trip on the epilogue's critical path
+    if (bias) {
+        if (wtid < 64) {
+            const int c = wg * uw + (wtid / uw) * 4 * uw + (wtid % uw);       // tile column of strip entry wtid
+            sbias[wtid] = (c < p.block_n && n0 + c < p.n) ? __ldg(bias + n0 + c) : 0.f;
+        }
+        wg_sync();
+    }
     wait_accumulator();
     tc_fence_after();
     const int n_pass = p.preact ? 2 : 1;          // the pre-activation copy is a pass of its own over the block
@@ -134,20 +174,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                 {
                     uint32_t raw[CH];
                     __syncwarp();
-                    tmem_ld16(t_row + c, raw);
-                    tmem_ld_wait();
+                    if (ws_src) {
+                        // split tile, last slice to arrive: the accumulator is the sum the slices left in the
+                        // workspace ([column / 4][row] float4: a warp reads 512 contiguous bytes); the last pass over
+                        // a chunk leaves zeros behind for the next launch
+                        const bool last_pass = pass == n_pass - 1;
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j) {
+                            float4* w4 = ws_src + (size_t)((c >> 2) + j) * 128 + r_local;
+                            const float4 v = __ldcg(w4);
+                            raw[4 * j] = __float_as_uint(v.x), raw[4 * j + 1] = __float_as_uint(v.y);
+                            raw[4 * j + 2] = __float_as_uint(v.z), raw[4 * j + 3] = __float_as_uint(v.w);
+                            if (last_pass) __stcg(w4, make_float4(0.f, 0.f, 0.f, 0.f));
+                        }
+                    } else {
+                        tmem_ld16(t_row + c, raw);
+                        tmem_ld_wait();
+                    }
                     if (bias) {
-                        if (full_chunk) {
+                        const float* sb = sbias + ((blk0 - wg * uw) / (4 * uw)) * uw + c0;
 #pragma unroll
-                            for (int i = 0; i < CH; i += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
-                                acc[i] = __uint_as_float(raw[i]) + b4.x, acc[i + 1] = __uint_as_float(raw[i + 1]) + b4.y;
-                                acc[i + 2] = __uint_as_float(raw[i + 2]) + b4.z, acc[i + 3] = __uint_as_float(raw[i + 3]) + b4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < CH; ++i)
-                                acc[i] = __uint_as_float(raw[i]) + (col0 + i < p.n ? __ldg(bias + col0 + i) : 0.f);
+                        for (int i = 0; i < CH; i += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(sb + i);
+                            acc[i] = __uint_as_float(raw[i]) + b4.x, acc[i + 1] = __uint_as_float(raw[i + 1]) + b4.y;
+                            acc[i + 2] = __uint_as_float(raw[i + 2]) + b4.z, acc[i + 3] = __uint_as_float(raw[i + 3]) + b4.w;
                         }
                     } else {
 #pragma unroll
@@ -309,6 +359,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 1024);   // [4 warpgroups][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -427,7 +478,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
             const bool second = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group;
             epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
-                          second ? p.d2 : p.d,
+                          second ? p.d2 : p.d, s_bias + wg * 64,
                           [&] { mbar_wait(tmem_full + as, aphase); if (wg == 0 && wtid == 0 && tile == (int)blockIdx.x) SHG_STAMP(3); });
             if (wg == 0 && wtid == 0 && tile == (int)blockIdx.x) SHG_STAMP(4);
             tc_fence_before();
@@ -456,7 +507,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 // element the pair pulls 1.5x fewer operand bytes through L2 than two independent 128 x block_n tiles — the
 // main-loop limiter of the K = 768 projections.  Accumulators: 128 lanes x block_n columns in each CTA's TMEM.
 // ---------------------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool TAIL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
@@ -475,6 +526,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 1024);   // [4 warpgroups][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -501,19 +553,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
-    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;     // m_tiles counts 256-row pair tiles here
+    const int total_tiles = p.total_items;                        // whole tiles (x splits) + K-slices of the split tiles
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-                const int split = tile / (p.m_tiles * p.n_tiles);
-                const int rem = tile - split * (p.m_tiles * p.n_tiles);
+            for (int it = pair; it < total_tiles; it += n_pairs) {
+                const PairItem w = pair_item<TAIL>(p, it);
+                const int rem = w.tile % (p.m_tiles * p.n_tiles);
                 const int m0 = (rem / p.n_tiles) * 256 + rank * BM;
                 const int n0 = (rem % p.n_tiles) * p.block_n + rank * half_n;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                const int kb0 = w.kb0, kb1 = w.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -545,10 +596,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             const uint32_t idesc = make_idesc_bf16(256, p.block_n, A_MN, B_MN);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-                const int split = tile / (p.m_tiles * p.n_tiles);
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            for (int it = pair; it < total_tiles; it += n_pairs) {
+                const PairItem w = pair_item<TAIL>(p, it);
+                const int kb0 = w.kb0, kb1 = w.kb1;
                 mbar_wait(tmem_empty + as, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256;
@@ -585,7 +635,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int as = 0;
         uint32_t aphase = 0;
         const uint32_t leader_empty0 = mapa_u32(smem_u32(tmem_empty), 0);
-        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        volatile int& s_last_slice = *reinterpret_cast<volatile int*>(tmem_slot + 2);
+        for (int it = pair; it < total_tiles; it += n_pairs) {
+            const PairItem w = pair_item<TAIL>(p, it);
+            const int tile = w.tile;
             const int rem = tile % (p.m_tiles * p.n_tiles);
             const int m0 = (rem / p.n_tiles) * 256 + rank * BM, n0 = (rem % p.n_tiles) * p.block_n;
             const int row = m0 + quarter * 32 + lane;
@@ -593,11 +646,57 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             const float* bias = m0 >= p.split_m ? p.bias2 : p.bias;
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
             const bool second = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group;
-            epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
-                          second ? p.d2 : p.d, [&] { mbar_wait(tmem_full + as, aphase); });
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_empty0 + as * 8);
+            const bool partial = TAIL && w.partial;
+            float4* ws4 = nullptr;
+            bool run_epilogue = true;
+            if (partial) {
+                // K-slice of a split tile: this CTA's 128 x block_n partial sums join the workspace ([column / 4][row]
+                // float4, so a warp's vector atomics cover 512 contiguous bytes); the slice that finds all the others
+                // arrived runs the tile's epilogue from the workspace and leaves it zeroed.
+                const int slot = (tile - p.tail_first) * 2 + (int)rank;
+                ws4 = reinterpret_cast<float4*>(p.ws) + (size_t)slot * (128 * (p.block_n >> 2));
+                const int r_local = quarter * 32 + lane;
+                mbar_wait(tmem_full + as, aphase);
+                tc_fence_after();
+                for (int blk0 = wg * 64; blk0 < p.block_n; blk0 += 256) {
+                    if (n0 + blk0 >= p.n) break;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        uint32_t raw[16];
+                        tmem_ld16(t_row + blk0 + c0, raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            atomicAdd(ws4 + (size_t)(((blk0 + c0) >> 2) + j) * 128 + r_local,
+                                      make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                  __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_empty0 + as * 8);      // the accumulator stage is free again
+                __threadfence();
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+                if (wg == 0 && wtid == 0) {
+                    const unsigned int n_before = atomicAdd(p.ws_cnt + slot, 1u);
+                    s_last_slice = n_before == (unsigned int)(p.tail_s - 1);
+                    if (s_last_slice) p.ws_cnt[slot] = 0u;
+                }
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+                run_epilogue = s_last_slice != 0;
+                if (run_epilogue) __threadfence();
+            }
+            if (run_epilogue)
+                epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
+                              second ? p.d2 : p.d, s_bias + wg * 64,
+                              [&] { if (!partial) mbar_wait(tmem_full + as, aphase); }, ws4);
+            if (!partial) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_empty0 + as * 8);
+            } else {
+                asm volatile("bar.sync 5, 512;" ::: "memory");                   // s_last_slice may be rewritten
+            }
             if (++as == 2) {
                 as = 0;
                 aphase ^= 1;
@@ -738,7 +837,7 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     }
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
     const int stage_bytes = BM * BK * 2 + (pair ? bn / 2 : bn) * BK * 2;
-    const int bar_bytes = 1024;          // barriers + TMEM slot
+    const int bar_bytes = 2048;          // barriers + TMEM slot + flag | per-warpgroup bias strips
     // how D leaves the SM (see epilogue_tile): bf16 outputs with TMA-legal geometry through staged bulk stores, fp32
     // accumulation (split-K weight gradients) through staged bulk reduce-adds; | 4096 in block_n forces the direct path
     const bool direct = (a->block_n & 4096) != 0;
@@ -796,18 +895,50 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
         }
     }
 
-    const int total = p.m_tiles * p.n_tiles * p.splits;
+    int total = p.m_tiles * p.n_tiles * p.splits;
+    p.tail_first = 0x7fffffff, p.tail_s = 0, p.tail_kb = 0, p.total_items = total, p.ws = nullptr, p.ws_cnt = nullptr;
+    if (pair && p.splits == 1 && !kgrouped && !accumulate && a->workspace && !(a->block_n & 16384)) {
+        // Tail split: with T tiles on P = 74 pair slots, the last wave holds only T % P tiles while the other pairs
+        // idle for a whole tile time — at M = 12576 (bs32 x 393 tokens) that is 2 of 150 (N = 768), 6 of 450 (N = 2304)
+        // and 8 of 600 (N = 3072) tiles: 3 waves for 2.03 waves of work.  When the last wave is at most a quarter
+        // full, its tiles are cut along K into S slices spread over the idle pairs (fp32 partial sums through L2).
+        const int slots = kNumSMs / 2;
+        const int rem = total % slots;
+        // Measured (profiles/gemm_tune_r02.txt, p256 vs p256notail): the split costs ~8 us per launch (fp32 atomics of
+        // the partial tiles through L2, a device-wide fence, the counter round trip and an epilogue fed from L2), so it
+        // pays only when a whole extra wave is long: K >= 2560 (12576x768x3072: 57.6 -> 54.0 us; 12576x768x15360:
+        // 255 -> 210 us) and loses at K = 768 (22.6 -> 29.2 us), where the plain schedule stays.
+        if (total > slots && rem > 0 && rem * 4 <= slots && p.kb_total >= 40) {
+            int S = slots / rem;
+            if (S > p.kb_total) S = p.kb_total;
+            const int per = (p.kb_total + S - 1) / S;
+            S = (p.kb_total + per - 1) / per;
+            const size_t need = 1024 + (size_t)rem * 2 * 128 * bn * sizeof(float);
+            if (S >= 2 && (size_t)a->workspace_bytes >= need && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0) {
+                p.tail_first = total - rem, p.tail_s = S, p.tail_kb = per;
+                p.total_items = p.tail_first + rem * S;
+                p.ws_cnt = reinterpret_cast<unsigned int*>(a->workspace);
+                p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + 1024);
+                total = p.total_items;
+            }
+        }
+    }
     int grid = total < kNumSMs ? total : kNumSMs;
     if (pair) grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
     cudaStream_t s = (cudaStream_t)stream;
-#define SHG_GEMM2_LAUNCH(AM, BMJ)                                                                              \
+#define SHG_GEMM2_LAUNCH_T(AM, BMJ, TL)                                                                        \
     do {                                                                                                       \
         static bool attr_set2 = false;                                                                         \
         if (!attr_set2) {                                                                                      \
-            cudaFuncSetAttribute(gemm2_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            cudaFuncSetAttribute(gemm2_kernel<AM, BMJ, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set2 = true;                                                                                  \
         }                                                                                                      \
-        shg::launch(gemm2_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p);                                  \
+        shg::launch(gemm2_kernel<AM, BMJ, TL>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p); \
+    } while (0)
+#define SHG_GEMM2_LAUNCH(AM, BMJ)                                                                              \
+    do {                                                                                                       \
+        if (p.tail_s > 0) SHG_GEMM2_LAUNCH_T(AM, BMJ, true);                                                   \
+        else SHG_GEMM2_LAUNCH_T(AM, BMJ, false);                                                               \
     } while (0)
     if (pair) {
         if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);

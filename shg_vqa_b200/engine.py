@@ -89,8 +89,15 @@ class Engine:
             cur.wait_event(st.record_event())
 
     def _on(self, st):
+        """Run the enclosed launches on side stream `st` (None: stay on the current stream), in that stream's GEMM
+        workspace lane (ops.workspace_lane)."""
         import contextlib
-        return torch.cuda.stream(st) if (self.use_streams and st is not None) else contextlib.nullcontext()
+        if not (self.use_streams and st is not None):
+            return contextlib.nullcontext()
+        stack = contextlib.ExitStack()
+        stack.enter_context(torch.cuda.stream(st))
+        stack.enter_context(ops.workspace_lane(1 if st is self.s1 else (2 if st is self.s2 else 3)))
+        return stack
 
     # ------------------------------------------------------------------ parameter handles
     def _lin(self, wkey, bkey=None):
@@ -282,7 +289,7 @@ class Engine:
             return
         self.sw.wait_event(torch.cuda.current_stream().record_event())
         self._keep.append((dy, x))
-        with torch.cuda.stream(self.sw):
+        with self._on(self.sw):
             ops.gemm(dy, x, a_t=True, b_t=True, out=lin.gw, accumulate=True)
             if bias:
                 ops.colsum_accum(dy, lin.gb)
@@ -293,7 +300,7 @@ class Engine:
             return
         self.sw.wait_event(torch.cuda.current_stream().record_event())
         self._keep.append((dy,))
-        with torch.cuda.stream(self.sw):
+        with self._on(self.sw):
             ops.colsum_accum(dy, gb)
 
     def _ffn_fwd(self, f1, f2, ln, a, save, act="gelu", eps=EPS_BERT, addend=None, p_out=0.0, p_inner=0.0):
@@ -464,7 +471,7 @@ class Engine:
             return
         self.sw.wait_event(torch.cuda.current_stream().record_event())
         self._keep.append((dy, x))
-        with torch.cuda.stream(self.sw):
+        with self._on(self.sw):
             ops.gemm(dy, x, a_t=True, b_t=True, out=A.gw, accumulate=True, d2=Bm.gw, k_split=split)
             if bias:
                 ops.colsum_accum(dy[:split], A.gb)

@@ -18,6 +18,43 @@ ATTN_BWD_MERGE = _os.environ.get("SHG_ATTN_MERGE", "1") != "0"     # mirrors the
 _PAIR_FLAG = {"0": 2048, "1": 1024}.get(_os.environ.get("SHG_GEMM_PAIR", ""), 0)   # debugging: forbid / force CTA-pair tiles
 
 
+# Scratch of the GEMM's tail-split schedule (include/shgvqa.h: shg_gemm_args.workspace).  A buffer may serve one launch
+# at a time, so there is one per CONCURRENCY LANE: the engine runs its launches on a main stream and three side streams
+# (language side, action side, weight gradients); launches of one lane are stream-ordered, launches of different lanes
+# overlap.  Lanes rather than stream ids, because the main lane is whatever stream is current (default stream, warm-up
+# stream, graph-capture stream).  `workspace_lane(i)` selects the lane for the calls made inside it.
+_GEMM_WS = {}
+_gemm_lane = 0
+GEMM_WS_BYTES = 1024 + 10 * 2 * 128 * 256 * 4         # up to 10 split tiles of 256 x 256 (the bs32 step needs 8)
+GEMM_TAIL_SPLIT = _os.environ.get("SHG_GEMM_TAIL_SPLIT", "1") != "0"
+
+
+class workspace_lane:
+    def __init__(self, lane):
+        self.lane = lane
+
+    def __enter__(self):
+        global _gemm_lane
+        self.prev, _gemm_lane = _gemm_lane, self.lane
+
+    def __exit__(self, *a):
+        global _gemm_lane
+        _gemm_lane = self.prev
+
+
+def _gemm_workspace(dev):
+    if not GEMM_TAIL_SPLIT:
+        return None
+    key = (dev.index, _gemm_lane)
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                     # first seen inside a graph capture: plain schedule for this launch
+        ws = torch.zeros(GEMM_WS_BYTES, device=dev, dtype=torch.uint8)
+        _GEMM_WS[key] = ws
+    return ws
+
+
 def _ld(t):
     assert t.dim() == 2 and t.stride(1) == 1, "row-major 2-D tensor (any leading dimension) expected"
     return t.stride(0)
@@ -71,6 +108,9 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
         assert accumulate and d2.dtype == torch.float32 and d2.shape == out.shape and _ld(d2) == _ld(out)
         assert 0 < k_split < k and splits == 0
         args.d2, args.k_split = ptr(d2), k_split
+    ws = _gemm_workspace(a.device) if (m > 256 * 74 // 2 and not accumulate) else None
+    if ws is not None:
+        args.workspace, args.workspace_bytes = ptr(ws), ws.numel()
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
     args.splits, args.block_n = splits, (block_n | _PAIR_FLAG if block_n == 0 and _PAIR_FLAG else block_n)
     call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k, "%dx%dx%d %s%s%s" % (m, n, k, "T" if a_t else "N", "T" if b_t else "N", " acc" if accumulate else "")))

@@ -316,10 +316,17 @@ def _attn_ref(q, k, v, b, lq, lk, scale, add_mask):
 @pytest.mark.parametrize("lq,lk,mode", [(40, 40, "key"), (393, 393, "none"), (40, 393, "none"), (393, 40, "key"),
                                         (128, 128, "causal8"), (128, 393, "none"), (48, 48, "causal3"),
                                         (48, 393, "none"), (40, 177, "key"), (177, 40, "key"), (1, 5, "none")])
-def test_attention_fwd_all_path_shapes(ops, lq, lk, mode):
-    """The ten (Lq, Lk, mask) problems of SURVEY §8d, read from packed QKV buffers in place.
-    Tolerance: 2e-2 of the output scale (bf16 P and bf16 output)."""
-    _attention_fwd_case(ops, lq, lk, mode)
+@pytest.mark.parametrize("chunked_from", [257, 1])
+def test_attention_fwd_all_path_shapes(ops, lq, lk, mode, chunked_from):
+    """The ten (Lq, Lk, mask) problems of SURVEY §8d, read from packed QKV buffers in place — through the default
+    dispatch (whole-row kernel up to 256 keys, chunked online-softmax kernel above) and with every shape forced
+    through the chunked kernel.  Tolerance: 2e-2 of the output scale (bf16 P and bf16 output)."""
+    from shg_vqa_b200 import _lib
+    _lib.check(_lib.lib().shg_set_attn_fwd_chunked_min_lk(chunked_from))
+    try:
+        _attention_fwd_case(ops, lq, lk, mode)
+    finally:
+        _lib.check(_lib.lib().shg_set_attn_fwd_chunked_min_lk(257))
 
 
 def _attention_fwd_case(ops, lq, lk, mode):

@@ -1,25 +1,42 @@
-"""Attention forward / backward timings at the path's shapes (CUDA events, L2 flushed). Not the bench."""
-import sys, os
+"""GPU time of the attention kernels at the path's (Lq, Lk) problems, B = 32, dropout on (as the bench step runs
+them): 16 back-to-back launches captured in a CUDA graph and replayed (no host launch latency).  Forward: whole-row
+kernel vs the chunked two-CTA-per-SM kernel; backward: as dispatched.  Not the bench."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from shg_vqa_b200 import ops
-from perf_probe import timeit, dev
+from shg_vqa_b200 import _lib, ops
+from gemm_probe import graph_time
 
+dev = torch.device("cuda:0")
 B = 32
 seed = torch.tensor([7], dtype=torch.int32, device=dev)
-for (lq, lk, fr) in [(393, 393, None), (128, 393, None), (48, 393, None), (128, 128, (8, 8)), (40, 40, None),
-                     (40, 393, None), (393, 40, None), (177, 40, None), (40, 177, None)]:
+DROP = None if "--nodrop" in sys.argv else (0.1, 3, seed)
+SHAPES = [(393, 393), (128, 393), (48, 393), (40, 393), (128, 128), (48, 48), (40, 40), (393, 40), (40, 177), (177, 40)]
+for lq, lk in SHAPES:
     q = torch.randn(B * lq, 2304, device=dev).to(torch.bfloat16)
     kv = torch.randn(B * lk, 2304, device=dev).to(torch.bfloat16)
+    frames = (8, 8) if (lq, lk) == (128, 128) else ((3, 3) if (lq, lk) == (48, 48) else None)
+    res = {}
+    for name, min_lk in (("whole-row", 100000), ("chunked", 1)):
+        if name == "whole-row" and lk > 416:
+            continue
+        _lib.check(_lib.lib().shg_set_attn_fwd_chunked_min_lk(min_lk))
+        f = lambda i: ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, frames=frames,
+                                        save_lse=True, drop=DROP)
+        res[name] = graph_time(f) * 1e3
+    _lib.check(_lib.lib().shg_set_attn_fwd_chunked_min_lk(257))
+    out, lse = ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, frames=frames, save_lse=True,
+                                 drop=DROP)
     d_o = torch.randn(B * lq, 768, device=dev).to(torch.bfloat16)
     dq = torch.empty(B * lq, 768, device=dev, dtype=torch.bfloat16)
     dk = torch.empty(B * lk, 768, device=dev, dtype=torch.bfloat16)
-    dv = torch.empty_like(dk)
-    fl = 4 * B * 12 * lq * lk * 64
-    line = "attn b=%d %4d x %4d:" % (B, lq, lk)
-    for drop in (None, (0.1, 3, seed)):
-        out, lse = ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, frames=fr, save_lse=True, drop=drop)
-        tf = timeit(lambda: ops.attention_fwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], B, lq, lk, frames=fr, save_lse=True, drop=drop))
-        tb = timeit(lambda: ops.attention_bwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], out, d_o, lse, dq, dk, dv, B, lq, lk, frames=fr, drop=drop))
-        line += "  %s fwd %6.1f us (%5.1f T/s)  bwd %6.1f us (%5.1f T/s)" % ("drop" if drop else "plain", tf * 1e3, fl / tf / 1e9, tb * 1e3, 2.5 * fl / tb / 1e9)
-    print(line)
+    dv = torch.empty(B * lk, 768, device=dev, dtype=torch.bfloat16)
+    fb = lambda i: ops.attention_bwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], out, d_o, lse, dq, dk, dv, B, lq, lk,
+                                     frames=frames, drop=DROP)
+    tb = graph_time(fb) * 1e3
+    fl = 4.0 * B * 12 * lq * lk * 64
+    print("%3d x %3d  fwd whole-row %7.1f us  chunked %7.1f us (%6.1f TF/s)   bwd %7.1f us (%6.1f TF/s)" % (
+        lq, lk, res.get("whole-row", float("nan")), res["chunked"], fl / res["chunked"] / 1e6, tb, 2.5 * fl / tb / 1e6),
+        flush=True)

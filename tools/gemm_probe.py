@@ -106,7 +106,7 @@ if __name__ == "__main__":
         for (m, n, k, mode) in shapes:
             res = {}
             cfgs = [("auto", 0)] + [("s%d" % bn, bn | 2048) for bn in (64, 128, 192, 256)] + \
-                   [("p%d" % bn, bn | 1024) for bn in (128, 192, 256)]
+                   [("p%d" % bn, bn | 1024) for bn in (128, 192, 256)] + [("p256notail", 256 | 1024 | 16384)]
             for name, flag in cfgs:
                 if name == "p192" and mode != "NN":
                     continue
