@@ -37,6 +37,7 @@ struct GemmParams {
     DropCfg drop;
     int act, out_f32, accumulate;
     int tma_store;          // kStoreDirect | kStoreBf16 | kStoreReduceF32 (see epilogue_tile)
+    int fast_epi;           // the launch qualifies for epilogue_tile_fast
     int splits, block_n, n_stages;
     int m_tiles, n_tiles, kb_total, kb_per_split;
     unsigned long long* dbg;   // optional phase timestamps of CTA 0 (tools/gemm_phases.py), normally null
@@ -156,6 +157,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
     }
     wait_accumulator();
     tc_fence_after();
+#define EPI_STAMP(i) do { if (p.dbg && wg == 0 && wtid == 0 && blockIdx.x == 0) p.dbg[i] = globaltimer_ns(); } while (0)
+    EPI_STAMP(8);
     const int n_pass = p.preact ? 2 : 1;          // the pre-activation copy is a pass of its own over the block
     for (int blk0 = wg * uw; blk0 < p.block_n; blk0 += 4 * uw) {
         if (n0 + blk0 >= p.n) break;               // uniform over the warpgroup
@@ -165,6 +168,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                 if (wtid == 0) bulk_wait_read<0>();            // the store that last used this block has read it
                 wg_sync();
             }
+            EPI_STAMP(9);
             for (int c0 = 0; c0 < uw; c0 += CH) {
                 const int c = blk0 + c0;
                 const int col0 = n0 + c;
@@ -191,6 +195,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                         tmem_ld16(t_row + c, raw);
                         tmem_ld_wait();
                     }
+                    if (c0 == 0) EPI_STAMP(10);
                     if (bias) {
                         const float* sb = sbias + ((blk0 - wg * uw) / (4 * uw)) * uw + c0;
 #pragma unroll
@@ -329,8 +334,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
                 }
             }
             if (staged) {
+                EPI_STAMP(11);
                 fence_proxy_async_smem();          // generic-proxy writes of the block -> visible to the TMA engine
+                EPI_STAMP(12);
                 wg_sync();
+                EPI_STAMP(13);
                 if (wtid == 0) {
                     if (mode == kStoreReduceF32) tma_reduce_add_2d(tm_d, buf, n0 + blk0, m0);
                     else tma_store_2d(is_pre ? tm_pre : tm_d, buf, n0 + blk0, m0);
@@ -341,7 +349,108 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
     }
 }
 
-template <bool A_MN, bool B_MN>
+// The common epilogues as a tight loop: bias (+ bf16 residual) -> bf16 through a staged TMA store, or fp32 partial
+// sums -> staged TMA reduce-add; no activation / dropout / pre-activation copy / activation-derivative operand (those
+// launches take epilogue_tile above).  Phase stamps of epilogue_tile on a single-tile CTA (tools/gemm_phases2.py,
+// 5632x768x768, 128x256 tile): 0.4 us between "accumulator visible" and the first chunk (staging-buffer wait +
+// warpgroup barrier AFTER the accumulator wait) and 0.49 us per 16-column chunk — one warp per scheduler walking a
+// dependent chain of ~60 instructions behind a dozen uniform branches on launch parameters, with the TMEM load latency
+// exposed every chunk.  Here the buffer wait and barrier are taken BEFORE the accumulator wait, the TMEM load of chunk
+// c+1 (and its residual vectors) is in flight while chunk c is converted, and the loop body has no mode branches.
+template <class WaitFn>
+__device__ __forceinline__ void epilogue_tile_fast(const GemmParams& p, const float* __restrict__ bias, uint32_t t_row,
+                                                   int row, bool row_ok, int m0, int n0, int wg, int wtid, uint8_t* stg,
+                                                   const CUtensorMap* tm_d, float* sbias, WaitFn wait_accumulator) {
+    const bool f32 = p.tma_store == kStoreReduceF32;
+    const int uw = f32 ? 32 : 64;
+    const int nch = uw >> 4;                     // 16-column chunks per block: 4 (bf16) or 2 (fp32)
+    const int r_local = row - m0;
+    uint8_t* buf = stg + wg * kStageGroupBytes;
+    uint8_t* dst = buf + r_local * 128;
+    const int swz = r_local & 7;
+    const int bar_id = 1 + wg;
+    auto wg_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+    const __nv_bfloat16* res = p.residual ? p.residual + (size_t)row * p.ldr + n0 : nullptr;
+    if (bias && wtid < 64) {
+        const int c = wg * uw + (wtid / uw) * 4 * uw + (wtid % uw);
+        sbias[wtid] = (c < p.block_n && n0 + c < p.n) ? __ldg(bias + n0 + c) : 0.f;
+    }
+    if (wtid == 0) bulk_wait_read<0>();          // this warpgroup's previous store has read the staging block
+    wg_sync();
+    wait_accumulator();
+    tc_fence_after();
+    int k_blk = 0;
+    for (int blk0 = wg * uw; blk0 < p.block_n; blk0 += 4 * uw, ++k_blk) {
+        if (n0 + blk0 >= p.n) break;             // uniform over the warpgroup
+        if (k_blk > 0) {
+            if (wtid == 0) bulk_wait_read<0>();
+            wg_sync();
+        }
+        uint32_t raw_a[16], raw_b[16];
+        tmem_ld16(t_row + blk0, raw_a);
+        // one 16-column chunk: wait for its TMEM load, put the next chunk's load and residual vectors in flight,
+        // convert, write the swizzled staging row
+        auto chunk = [&](int ci, const uint32_t(&rw)[16], uint32_t(&nxt)[16]) {
+            const int c = blk0 + ci * 16;
+            const bool live = n0 + c < p.n;      // else past N: the bulk store clips these columns
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+            if (res && row_ok && live) {         // residual of this chunk: in flight during the TMEM wait
+                r0 = __ldg(reinterpret_cast<const uint4*>(res + c));
+                r1 = __ldg(reinterpret_cast<const uint4*>(res + c) + 1);
+            }
+            tmem_ld_wait();
+            if (ci + 1 < nch) tmem_ld16(t_row + c + 16, nxt);        // next chunk's accumulators in flight
+            if (!live) return;
+            if (f32) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(dst + (((ci * 4 + j) ^ swz) << 4)) =
+                        make_uint4(rw[4 * j], rw[4 * j + 1], rw[4 * j + 2], rw[4 * j + 3]);
+                return;
+            }
+            const float* sb = sbias + k_blk * uw + ci * 16;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {        // 8 columns at a time: one 16-byte unit of the staging row
+                float a8[8];
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (bias) b0 = *reinterpret_cast<const float4*>(sb + 8 * j), b1 = *reinterpret_cast<const float4*>(sb + 8 * j + 4);
+                a8[0] = __uint_as_float(rw[8 * j]) + b0.x, a8[1] = __uint_as_float(rw[8 * j + 1]) + b0.y;
+                a8[2] = __uint_as_float(rw[8 * j + 2]) + b0.z, a8[3] = __uint_as_float(rw[8 * j + 3]) + b0.w;
+                a8[4] = __uint_as_float(rw[8 * j + 4]) + b1.x, a8[5] = __uint_as_float(rw[8 * j + 5]) + b1.y;
+                a8[6] = __uint_as_float(rw[8 * j + 6]) + b1.z, a8[7] = __uint_as_float(rw[8 * j + 7]) + b1.w;
+                if (res) {
+                    const uint4 rr = j ? r1 : r0;
+                    float2 f2;
+                    f2 = unpack_bf16x2(rr.x), a8[0] += f2.x, a8[1] += f2.y;
+                    f2 = unpack_bf16x2(rr.y), a8[2] += f2.x, a8[3] += f2.y;
+                    f2 = unpack_bf16x2(rr.z), a8[4] += f2.x, a8[5] += f2.y;
+                    f2 = unpack_bf16x2(rr.w), a8[6] += f2.x, a8[7] += f2.y;
+                }
+                uint4 u;
+                u.x = pack_bf16x2(a8[0], a8[1]), u.y = pack_bf16x2(a8[2], a8[3]);
+                u.z = pack_bf16x2(a8[4], a8[5]), u.w = pack_bf16x2(a8[6], a8[7]);
+                *reinterpret_cast<uint4*>(dst + (((ci * 2 + j) ^ swz) << 4)) = u;
+            }
+        };
+        chunk(0, raw_a, raw_b);
+        chunk(1, raw_b, raw_a);
+        if (nch > 2) {
+            chunk(2, raw_a, raw_b);
+            chunk(3, raw_b, raw_a);
+        }
+        fence_proxy_async_smem();                // generic-proxy writes of the block -> visible to the TMA engine
+        wg_sync();
+        if (wtid == 0) {
+            if (f32) tma_reduce_add_2d(tm_d, buf, n0 + blk0, m0);
+            else tma_store_2d(tm_d, buf, n0 + blk0, m0);
+            bulk_commit();
+        }
+    }
+}
+
+// (576 threads = 18 warps: the register file is allocated as if for 20, i.e. 96 registers per thread — a kernel built
+// with __maxnreg__(112) is refused at launch, "too many resources requested")
+template <bool A_MN, bool B_MN, bool FAST>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
@@ -477,9 +586,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const float* bias = m0 >= p.split_m ? p.bias2 : p.bias;
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
             const bool second = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split >= p.kb_group;
-            epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
-                          second ? p.d2 : p.d, s_bias + wg * 64,
-                          [&] { mbar_wait(tmem_full + as, aphase); if (wg == 0 && wtid == 0 && tile == (int)blockIdx.x) SHG_STAMP(3); });
+            auto wait_acc = [&] { mbar_wait(tmem_full + as, aphase); if (wg == 0 && wtid == 0 && tile == (int)blockIdx.x) SHG_STAMP(3); };
+            if constexpr (FAST)
+                epilogue_tile_fast(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d,
+                                   s_bias + wg * 64, wait_acc);
+            else
+                epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
+                              second ? p.d2 : p.d, s_bias + wg * 64, wait_acc);
             if (wg == 0 && wtid == 0 && tile == (int)blockIdx.x) SHG_STAMP(4);
             tc_fence_before();
             __syncwarp();
@@ -507,7 +620,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 // element the pair pulls 1.5x fewer operand bytes through L2 than two independent 128 x block_n tiles — the
 // main-loop limiter of the K = 768 projections.  Accumulators: 128 lanes x block_n columns in each CTA's TMEM.
 // ---------------------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN, bool TAIL>
+template <bool A_MN, bool B_MN, bool TAIL, bool FAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_pre,
@@ -686,10 +799,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 run_epilogue = s_last_slice != 0;
                 if (run_epilogue) __threadfence();
             }
-            if (run_epilogue)
-                epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
-                              second ? p.d2 : p.d, s_bias + wg * 64,
-                              [&] { if (!partial) mbar_wait(tmem_full + as, aphase); }, ws4);
+            auto wait_acc = [&] { if (!partial) mbar_wait(tmem_full + as, aphase); };
+            if (run_epilogue) {
+                if constexpr (FAST && !TAIL)
+                    epilogue_tile_fast(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d,
+                                       s_bias + wg * 64, wait_acc);
+                else
+                    epilogue_tile(p, bias, t_row, row, row_ok, m0, n0, wg, wtid, stg, second ? &tma_d2 : &tma_d, &tma_pre,
+                                  second ? p.d2 : p.d, s_bias + wg * 64, wait_acc, ws4);
+            }
             if (!partial) {
                 tc_fence_before();
                 __syncwarp();
@@ -848,6 +966,12 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     else if (!direct && accumulate && a->ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
              (!a->d2 || (reinterpret_cast<uintptr_t>(a->d2) & 15) == 0))
         p.tma_store = kStoreReduceF32;
+    // the tight epilogue (epilogue_tile_fast): staged output, bias / residual only; a residual must be vector-loadable
+    // in whole 16-column chunks.  | 32768 in block_n forces the general epilogue (A/B comparison)
+    p.fast_epi = (p.tma_store != kStoreDirect && !a->preact && a->act == SHG_ACT_NONE && !a->mul_aux && p.drop.p == 0.f &&
+                  !(a->block_n & 32768) && (p.tma_store == kStoreBf16 || !a->bias) &&
+                  (!a->residual || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 && a->n % 16 == 0)))
+                     ? 1 : 0;
     const int out_bytes = p.tma_store ? kStageOutBytes : 0;
     int n_stages = (227 * 1024 - 1024 - bar_bytes - out_bytes) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
@@ -926,19 +1050,20 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
     int grid = total < kNumSMs ? total : kNumSMs;
     if (pair) grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
     cudaStream_t s = (cudaStream_t)stream;
-#define SHG_GEMM2_LAUNCH_T(AM, BMJ, TL)                                                                        \
+#define SHG_GEMM2_LAUNCH_T(AM, BMJ, TL, FS)                                                                    \
     do {                                                                                                       \
         static bool attr_set2 = false;                                                                         \
         if (!attr_set2) {                                                                                      \
-            cudaFuncSetAttribute(gemm2_kernel<AM, BMJ, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            cudaFuncSetAttribute(gemm2_kernel<AM, BMJ, TL, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set2 = true;                                                                                  \
         }                                                                                                      \
-        shg::launch(gemm2_kernel<AM, BMJ, TL>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p); \
+        shg::launch(gemm2_kernel<AM, BMJ, TL, FS>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p); \
     } while (0)
 #define SHG_GEMM2_LAUNCH(AM, BMJ)                                                                              \
     do {                                                                                                       \
-        if (p.tail_s > 0) SHG_GEMM2_LAUNCH_T(AM, BMJ, true);                                                   \
-        else SHG_GEMM2_LAUNCH_T(AM, BMJ, false);                                                               \
+        if (p.tail_s > 0) SHG_GEMM2_LAUNCH_T(AM, BMJ, true, false);                                            \
+        else if (p.fast_epi) SHG_GEMM2_LAUNCH_T(AM, BMJ, false, true);                                         \
+        else SHG_GEMM2_LAUNCH_T(AM, BMJ, false, false);                                                        \
     } while (0)
     if (pair) {
         if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM2_LAUNCH(false, false);
@@ -948,14 +1073,19 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
         return check_launch("shg_gemm(pair)");
     }
 #undef SHG_GEMM2_LAUNCH
-#define SHG_GEMM_LAUNCH(AM, BMJ)                                                                              \
+#define SHG_GEMM_LAUNCH_F(AM, BMJ, FS)                                                                         \
     do {                                                                                                      \
         static bool attr_set = false;                                                                         \
         if (!attr_set) {                                                                                      \
-            cudaFuncSetAttribute(gemm_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            cudaFuncSetAttribute(gemm_kernel<AM, BMJ, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_set = true;                                                                                  \
         }                                                                                                     \
-        shg::launch(gemm_kernel<AM, BMJ>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p);                                  \
+        shg::launch(gemm_kernel<AM, BMJ, FS>, grid, kGemmThreads, smem, s, *ta, *tb, *td, *tpre, *tb2, *td2, p); \
+    } while (0)
+#define SHG_GEMM_LAUNCH(AM, BMJ)                                                                              \
+    do {                                                                                                      \
+        if (p.fast_epi) SHG_GEMM_LAUNCH_F(AM, BMJ, true);                                                     \
+        else SHG_GEMM_LAUNCH_F(AM, BMJ, false);                                                               \
     } while (0)
     if (!a->a_mn_major && !a->b_mn_major) SHG_GEMM_LAUNCH(false, false);
     else if (!a->a_mn_major && a->b_mn_major) SHG_GEMM_LAUNCH(false, true);

@@ -20,3 +20,5 @@ for (m, n, k, bn) in [(5632, 768, 768, 256), (5632, 768, 768, 128), (5632, 2048,
     t = buf.cpu().tolist()
     names = ["start", "setup done", "first operands", "accumulator done", "epilogue math done", "stores read", "exit"]
     print("%dx%dx%d bn%d events %.1f us: " % (m, n, k, bn, s.elapsed_time(e) * 1e3) + "  ".join("%s +%.2f" % (names[i], (t[i] - t[0]) / 1e3) for i in range(1, 7)))
+    en = ["acc visible", "block entry", "first tmem ld", "block staged", "proxy fence", "wg barrier"]
+    print("      epilogue of warpgroup 0 (+us since start): " + "  ".join("%s %.2f" % (en[i], (t[8 + i] - t[0]) / 1e3) for i in range(6)))
