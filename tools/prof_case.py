@@ -50,5 +50,36 @@ elif what in ("conv_fwd", "conv_wgrad", "conv_dgrad"):
             ops.conv3d_wgrad(dy, x, dw)
         else:
             ops.conv3d_dgrad(dy, wp, c_in)
+elif what == "ln":                         # LayerNorm forward + backward at the relation-layer size (12576 x 768)
+    rows, n = B * 393, 768
+    x = torch.randn(rows, n, device=dev).to(torch.bfloat16)
+    dy = torch.randn(rows, n, device=dev).to(torch.bfloat16)
+    g, b_ = torch.ones(n, device=dev), torch.zeros(n, device=dev)
+    dg, db, dxs = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for _ in range(3):
+        y, _, m, r = ops.layernorm_fwd(x, g, b_, 1e-12, save_stats=True)
+        ops.layernorm_bwd(dy, x, g, m, r, dg, db, dxsum=dxs, out_drop=DROP)
+elif what == "colsum":                     # bias gradient of the fused QKV projection: column sums of [12576, 2304]
+    x = torch.randn(B * 393, 2304, device=dev).to(torch.bfloat16)
+    out = torch.zeros(2304, device=dev)
+    for _ in range(3):
+        ops.colsum_accum(x, out)
+elif what == "match":                      # fused matcher on bs32 relation logits (512 frames x 8 queries x 457 classes)
+    import bench
+    from shg_vqa_b200.synthetic import make_inputs
+    from shg_vqa_b200.trainer import csr_from_padded
+    raw = make_inputs(B, seed=1234, with_feat=False)
+    lab, off = [t.to(dev) for t in csr_from_padded(raw["rel_tokens"], raw["rel_lengths"])]
+    lg = torch.randn(B * 128, 460, device=dev)[:, :457]
+    for _ in range(3):
+        m = ops.match_from_logits(lg, lab, off, 8)
+        ops.set_loss_fwd(lg, m, 0.1)
+elif what == "adam":                       # fused clip + BertAdam over the 191 M live parameters
+    from shg_vqa_b200.trainer import HotPathTrainer
+    tr = HotPathTrainer(dev, t_total=1000)
+    tr.init_weights()
+    tr.store.grad.normal_()
+    for _ in range(3):
+        tr.optimizer_step()
 torch.cuda.synchronize()
 print("done")
