@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) match_from_logits_kernel(
 
 // out[0] += sum w*nll, out[1] += sum w, out[2] += #matched, out[3] += #matched with argmax == label
 template <typename T>
-__global__ void __launch_bounds__(256) set_loss_fwd_kernel(const T* __restrict__ logits, int n_rows, int ld,
+__global__ void __launch_bounds__(1024) set_loss_fwd_kernel(const T* __restrict__ logits, int n_rows, int ld,
                                                           const int32_t* __restrict__ tgt,
                                                           const float* __restrict__ row_lse,
                                                           const int32_t* __restrict__ row_argmax, float eos_coef,
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) set_loss_fwd_kernel(const T* __restrict__
             if (row_argmax && row_argmax[r] == t) a3 += 1.f;
         }
     }
-    __shared__ float red[4][8];
+    __shared__ float red[4][32];
     a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2), a3 = warp_sum(a3);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) red[0][warp] = a0, red[1][warp] = a1, red[2][warp] = a2, red[3][warp] = a3;
@@ -335,13 +335,19 @@ int shg_set_loss_fwd(const void* logits, int logits_bf16, int n_rows, int n_cls,
                      const int32_t* target_classes, const float* row_lse, const int32_t* row_argmax, float eos_coef,
                      float* out, const int32_t* status, int n_frames, float* err_out, void* stream) {
     if (n_rows == 0) return SHG_OK;
-    const int blocks = (n_rows + 255) / 256 < 148 ? (n_rows + 255) / 256 : 148;
+    // up to 32768 rows (256 clips of 128 queries) ONE block sums in a fixed order: the weight sum out[1] divides every
+    // logit gradient, and a last-bit difference between two runs of the same step (atomic order over blocks) is
+    // amplified by the bf16 roundings of the backward into 1e-4-level gradient differences.  Larger inputs fall back
+    // to per-block partial sums combined with atomics.
+    const bool one_block = n_rows <= 32768;
+    const int threads = one_block ? 1024 : 256;
+    const int blocks = one_block ? 1 : ((n_rows + 255) / 256 < 148 ? (n_rows + 255) / 256 : 148);
     if (logits_bf16)
-        shg::launch(shg::set_loss_fwd_kernel<__nv_bfloat16>, blocks, 256, 0, (cudaStream_t)stream, 
+        shg::launch(shg::set_loss_fwd_kernel<__nv_bfloat16>, blocks, threads, 0, (cudaStream_t)stream, 
             (const __nv_bfloat16*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out,
             n_cls, status, n_frames, err_out);
     else
-        shg::launch(shg::set_loss_fwd_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, 
+        shg::launch(shg::set_loss_fwd_kernel<float>, blocks, threads, 0, (cudaStream_t)stream, 
             (const float*)logits, n_rows, ld_logits, target_classes, row_lse, row_argmax, eos_coef, out, n_cls, status,
             n_frames, err_out);
     return shg::check_launch("shg_set_loss_fwd");

@@ -181,10 +181,13 @@ class HotPathTrainer:
         return self.store.state_dict()
 
     # ------------------------------------------------------------------ loss on device
-    def loss_and_grads(self, out, batch, want_grad=True):
+    def loss_and_grads(self, out, batch, want_grad=True, ce_sums=None):
         """batch: target fp32 [B, n_ans]; rel_labels/rel_off, act_labels/act_off int32 CSR.  Optional
         rel_target_classes / act_target_classes (int32 [B*Q]) replace the matcher's scatter — used by the parity
-        tests to hold the reference's assignment fixed.
+        tests to hold the reference's assignment fixed.  ce_sums (fp32 [8] on the device: the relation and the action
+        (sum w*nll, sum w, matched, correct)) replaces this batch's own sums as the weighted-CE normaliser — the
+        data-parallel check uses it to give the single-process run the very denominators the ranks reduced (a
+        last-bit difference there is amplified by the bf16 roundings of the backward).
         Returns (scalars tensor view, d_hg_logit, d_rel_logits, d_act_logits, match dicts).
         scal[0]=qa loss, [1..4]=rel sums (w*nll, w, matched, correct), [5..8]=act sums, [9]=grad sumsq,
         [10]=number of frames / rows the matcher or the loss refused (NaN/-inf costs, > 32 targets, label out of
@@ -218,6 +221,8 @@ class HotPathTrainer:
             gscale = float(self.world_size)
         for i, (fam, o) in enumerate((("rel", 1), ("act", 5))):
             sums = scal[o:o + 4] if gscale == 1.0 else self.scal_den[4 * i:4 * i + 4]
+            if ce_sums is not None:
+                sums = ce_sums[4 * i:4 * i + 4]
             res.append(ops.set_loss_bwd(out[fam + "_logits"], matches[i], self.eos, sums, gscale) if want_grad else None)
         return scal, res[0], res[1], res[2], matches
 

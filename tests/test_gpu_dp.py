@@ -1,7 +1,8 @@
 """Data-parallel correctness on real hardware (needs >= 2 B200s; skipped otherwise): bench.py under torchrun with two
 ranks runs its `dp_check` — after the captured, NCCL-overlapped steps both ranks hold bit-identical weights, and the
 all-reduced gradient of two 4-clip shards equals the single-process gradient of the 8-clip batch (global CE
-normalisation, dropout off) to 1e-4 rel-L2."""
+normalisation with the ranks' reduced sums, dropout off) to 1e-4 rel-L2 (bench.py itself reports up to 1e-3 as ok:
+the bf16 noise floor of the backward at 4 and 8 ranks)."""
 import json
 import os
 import subprocess
@@ -24,6 +25,7 @@ def test_two_rank_step_keeps_replicas_identical_and_matches_single_process_gradi
     assert out.returncode == 0, out.stderr[-2000:]
     line = next(json.loads(l) for l in out.stdout.splitlines() if l.startswith("{"))
     dp = line["dp_check"]
+    assert dp["ok"] is True
     assert dp["weights_identical_across_ranks"] is True
     assert dp["reduced_grad_vs_single_process_rel_l2"] <= 1e-4
     assert line["n_gpus"] == 2 and line["value"] > 0
