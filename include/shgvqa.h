@@ -132,6 +132,11 @@ typedef struct {
      * needs 2.1 MB. */
     void* workspace;
     int64_t workspace_bytes;
+    /* 0 = one CTA per SM (148).  > 0 caps the persistent grid at this many CTAs (rounded down to an even count for
+     * CTA-pair tiles; the tail-split schedule is not used then).  The data-parallel step sets 148 - R while a
+     * collective that owns R SMs is in flight: a 148-CTA persistent grid would leave R of its CTAs waiting for an SM
+     * until the others have finished their share (two waves for one wave of work). */
+    int max_ctas;
 } shg_gemm_args;
 int shg_gemm(const shg_gemm_args* args, void* stream);
 /* Debug aid: CTA 0 of subsequent shg_gemm launches writes 7 %globaltimer phase stamps to buf (8 x u64 device

@@ -30,7 +30,7 @@ class GemmArgs(ctypes.Structure):
                 ("dropout_p", c_f32), ("dropout_salt", ctypes.c_uint32), ("dropout_seed", c_vp),
                 ("flags", c_int), ("splits", c_int), ("block_n", c_int),
                 ("b2", c_vp), ("bias2", c_vp), ("split_m", c_int), ("d2", c_vp), ("k_split", c_int),
-                ("workspace", c_vp), ("workspace_bytes", c_i64)]
+                ("workspace", c_vp), ("workspace_bytes", c_i64), ("max_ctas", c_int)]
 
 
 class AttnArgs(ctypes.Structure):

@@ -1021,7 +1021,9 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
 
     int total = p.m_tiles * p.n_tiles * p.splits;
     p.tail_first = 0x7fffffff, p.tail_s = 0, p.tail_kb = 0, p.total_items = total, p.ws = nullptr, p.ws_cnt = nullptr;
-    if (pair && p.splits == 1 && !kgrouped && !accumulate && a->workspace && !(a->block_n & 16384)) {
+    SHG_REQUIRE(a->max_ctas >= 0, SHG_EINVAL, "shg_gemm: max_ctas=%d", a->max_ctas);
+    const int cta_cap = a->max_ctas > 0 && a->max_ctas < kNumSMs ? (a->max_ctas < 2 ? 2 : a->max_ctas) : kNumSMs;
+    if (pair && p.splits == 1 && !kgrouped && !accumulate && a->workspace && !(a->block_n & 16384) && cta_cap == kNumSMs) {
         // Tail split: with T tiles on P = 74 pair slots, the last wave holds only T % P tiles while the other pairs
         // idle for a whole tile time — at M = 12576 (bs32 x 393 tokens) that is 2 of 150 (N = 768), 6 of 450 (N = 2304)
         // and 8 of 600 (N = 3072) tiles: 3 waves for 2.03 waves of work.  When the last wave is at most a quarter
@@ -1047,8 +1049,8 @@ extern "C" int shg_gemm(const shg_gemm_args* a, void* stream) {
             }
         }
     }
-    int grid = total < kNumSMs ? total : kNumSMs;
-    if (pair) grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
+    int grid = total < cta_cap ? total : cta_cap;
+    if (pair) grid = 2 * (total < cta_cap / 2 ? total : cta_cap / 2);
     cudaStream_t s = (cudaStream_t)stream;
 #define SHG_GEMM2_LAUNCH_T(AM, BMJ, TL, FS)                                                                    \
     do {                                                                                                       \

@@ -42,6 +42,24 @@ class workspace_lane:
         _gemm_lane = self.prev
 
 
+# Cap on the persistent GEMM grid (shg_gemm_args.max_ctas) for the calls made inside `gemm_cta_cap(n)`: the
+# data-parallel step leaves the SMs its in-flight all-reduce owns to NCCL (trainer.HotPathTrainer.train_step).
+_gemm_max_ctas = 0
+
+
+class gemm_cta_cap:
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        global _gemm_max_ctas
+        self.prev, _gemm_max_ctas = _gemm_max_ctas, self.n
+
+    def __exit__(self, *a):
+        global _gemm_max_ctas
+        _gemm_max_ctas = self.prev
+
+
 def _gemm_workspace(dev):
     if not GEMM_TAIL_SPLIT:
         return None
@@ -111,6 +129,7 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, act=None, residual=None, prea
     ws = _gemm_workspace(a.device) if (m > 256 * 74 // 2 and not accumulate) else None
     if ws is not None:
         args.workspace, args.workspace_bytes = ptr(ws), ws.numel()
+    args.max_ctas = _gemm_max_ctas
     args.flags = (GEMM_OUT_F32 if out.dtype == torch.float32 else 0) | (GEMM_ACCUMULATE if accumulate else 0)
     args.splits, args.block_n = splits, (block_n | _PAIR_FLAG if block_n == 0 and _PAIR_FLAG else block_n)
     call("shg_gemm", args, stream(), work=("tensor", 2.0 * m * n * k, "%dx%dx%d %s%s%s" % (m, n, k, "T" if a_t else "N", "T" if b_t else "N", " acc" if accumulate else "")))

@@ -9,6 +9,7 @@ NCCL all-reduce of the flat gradient buffer (one process per GPU, replacing
 nn.DataParallel's per-step scatter/replicate/gather).
 """
 import math
+import os
 
 import torch
 
@@ -127,6 +128,8 @@ class HotPathTrainer:
         self.scal_den = torch.zeros(8, device=self.device, dtype=torch.float32)   # globally reduced CE sums
         self.sumsq_ws = torch.zeros(2048, device=self.device, dtype=torch.float32)   # shg_grad_sumsq's partials + counter
         self.global_ce_norm = bool(global_ce_norm)
+        # persistent-GEMM grid while the step's all-reduce is in flight (0 = all 148 SMs); SHG_DP_GEMM_CTAS overrides
+        self.dp_gemm_ctas = int(os.environ.get("SHG_DP_GEMM_CTAS", "0"))
         self.lr_dev = torch.zeros(1, device=self.device, dtype=torch.float32)   # device-resident lr (graph-safe)
         # lr crosses to the device through a ring of pinned slots, one event each: the host runs ahead of the GPU
         # (lagged loss read), and a single slot could be overwritten before its queued H2D copy has read it
@@ -328,17 +331,20 @@ class HotPathTrainer:
             eng, grp = self.engine, self.store.dp_groups
             eng.backward_late_params(ctx, d_hg, d_rel, d_act)
             works = self._reduce_async(grp["late"])
-            eng.backward_early_begin(ctx)
-            for i in reversed(range(eng.nr)):
-                eng.backward_r_layer(ctx, i, self.backbone_grad)
-                if i == 0:
-                    break
-                slices = list(grp["r%d" % i])
-                if i == min(2, eng.nr - 1):
-                    eng.backward_lang_join(ctx)            # the 40-token language side finished long ago
-                    slices += grp["lang"] + grp["emb"]
-                works += self._reduce_async(slices)
-            eng.backward_early_end(ctx, self.backbone_grad)
+            # from here to the end of the backward an all-reduce is in flight most of the time and owns some SMs:
+            # the persistent GEMM grids leave those to it (include/shgvqa.h: shg_gemm_args.max_ctas)
+            with ops.gemm_cta_cap(self.dp_gemm_ctas):
+                eng.backward_early_begin(ctx)
+                for i in reversed(range(eng.nr)):
+                    eng.backward_r_layer(ctx, i, self.backbone_grad)
+                    if i == 0:
+                        break
+                    slices = list(grp["r%d" % i])
+                    if i == min(2, eng.nr - 1):
+                        eng.backward_lang_join(ctx)            # the 40-token language side finished long ago
+                        slices += grp["lang"] + grp["emb"]
+                    works += self._reduce_async(slices)
+                eng.backward_early_end(ctx, self.backbone_grad)
             works += self._reduce_async(grp["r0"] + grp.get("front", []) + grp["vec"])
             for w in works:
                 w.wait()                                   # stream-level: the optimiser waits for NCCL's stream
