@@ -206,6 +206,10 @@ int shg_attn_bwd(const shg_attn_bwd_args* args, void* stream);
 /* Problems with a single query tile (lq <= 128, o_f32 given) take ONE merged pass that also produces dk and dv
  * (default on; 0 restores the two-pass schedule, also SHG_ATTN_MERGE=0 in the environment). */
 int shg_set_attn_bwd_merge(int on);
+/* Problems with several query tiles (lq > 128, o_f32 given, lk <= 512) run the two passes on the second-generation
+ * kernels: 64-wide chunks, two CTAs per SM, the bf16 P / dS operands kept in tensor memory (default on; 0 restores
+ * the first-generation 128-wide kernels, also SHG_ATTN_BWD2=0 in the environment). */
+int shg_set_attn_bwd_chunked(int on);
 
 /* ------------------------------------------------------------------ LayerNorm family (HBM-bound)
  * y = LN(x (+ residual)) * gamma + beta, rows of width n (768 / 1536), statistics fp32.  Replaces

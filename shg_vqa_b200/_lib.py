@@ -66,6 +66,7 @@ SIGNATURES = {
     "shg_version": [],
     "shg_device_check": [c_int],
     "shg_set_attn_bwd_merge": [c_int],
+    "shg_set_attn_bwd_chunked": [c_int],
     "shg_set_attn_fwd_chunked_min_lk": [c_int],
     "shg_lsap_batched": [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "shg_match_from_logits": [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -152,7 +153,7 @@ def check(rc):
 
 
 # kernels launched per entry point (for the bench's gpu_launches count)
-LAUNCHES = {"shg_attn_bwd": 2, "shg_version": 0, "shg_device_check": 0, "shg_set_attn_bwd_merge": 0, "shg_set_attn_fwd_chunked_min_lk": 0}
+LAUNCHES = {"shg_attn_bwd": 2, "shg_version": 0, "shg_device_check": 0, "shg_set_attn_bwd_merge": 0, "shg_set_attn_bwd_chunked": 0, "shg_set_attn_fwd_chunked_min_lk": 0}
 launch_count = 0
 profiler = None     # set to a Profiler to time every call with CUDA events on the launching stream
 

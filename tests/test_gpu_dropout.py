@@ -144,11 +144,16 @@ def test_attention_dropout_fwd_bwd(ops, lq, lk, mode, p):
     dq2, dk2, dv2 = torch.zeros_like(dq), torch.zeros_like(dk), torch.zeros_like(dv)
     ops.attention_bwd(q, k, v, out, d_o, lse[0], dq2, dk2, dv2, b, lq, lk, key_mask=key_mask, frames=frames,
                       drop=drop)                                  # two-sweep delta route, mask re-hashed (no bit words)
+    dq3, dk3, dv3 = torch.zeros_like(dq), torch.zeros_like(dk), torch.zeros_like(dv)
+    ops.attention_bwd(q, k, v, out, d_o, (lse[0], lse[1], None), dq3, dk3, dv3, b, lq, lk, key_mask=key_mask,
+                      frames=frames, drop=drop)                   # fp32-O delta route, mask re-hashed (no bit words)
     ref.backward(d_o.float())
-    for name, got, got2, want in (("dq", dq, dq2, qf.grad), ("dk", dk, dk2, kf.grad), ("dv", dv, dv2, vf.grad)):
+    for name, got, got2, got3, want in (("dq", dq, dq2, dq3, qf.grad), ("dk", dk, dk2, dk3, kf.grad),
+                                        ("dv", dv, dv2, dv3, vf.grad)):
         tol = 3e-2 * want.abs().max().item() + 1e-6
         assert (got.float() - want).abs().max().item() <= tol, name
         assert (got2.float() - want).abs().max().item() <= tol, name + " (two-sweep)"
+        assert (got3.float() - want).abs().max().item() <= tol, name + " (re-hashed mask)"
 
 
 def test_embedding_dropout(ops):

@@ -360,7 +360,8 @@ def _attention_fwd_case(ops, lq, lk, mode):
 
 @pytest.mark.parametrize("lq,lk,mode", [(40, 40, "key"), (393, 393, "none"), (40, 393, "none"), (393, 40, "key"),
                                         (128, 128, "causal8"), (128, 393, "none"), (48, 48, "causal3"),
-                                        (48, 393, "none"), (40, 177, "none"), (177, 40, "key")])
+                                        (48, 393, "none"), (40, 177, "none"), (177, 40, "key"),
+                                        (256, 256, "causal8"), (200, 300, "key"), (393, 416, "none"), (130, 17, "none")])
 def test_attention_bwd_all_path_shapes(ops, lq, lk, mode):
     """dq/dk/dv against torch autograd of the fp32 attention on the same bf16 inputs; tolerance 3e-2 of each
     gradient's scale (P, dS and the outputs are bf16)."""

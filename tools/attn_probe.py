@@ -36,7 +36,10 @@ for lq, lk in SHAPES:
     fb = lambda i: ops.attention_bwd(q[:, :768], kv[:, 768:1536], kv[:, 1536:], out, d_o, lse, dq, dk, dv, B, lq, lk,
                                      frames=frames, drop=DROP)
     tb = graph_time(fb) * 1e3
+    _lib.check(_lib.lib().shg_set_attn_bwd_chunked(0))
+    tb_old = graph_time(fb) * 1e3
+    _lib.check(_lib.lib().shg_set_attn_bwd_chunked(1))
     fl = 4.0 * B * 12 * lq * lk * 64
-    print("%3d x %3d  fwd whole-row %7.1f us  chunked %7.1f us (%6.1f TF/s)   bwd %7.1f us (%6.1f TF/s)" % (
-        lq, lk, res.get("whole-row", float("nan")), res["chunked"], fl / res["chunked"] / 1e6, tb, 2.5 * fl / tb / 1e6),
+    print("%3d x %3d  fwd whole-row %7.1f us  chunked %7.1f us (%6.1f TF/s)   bwd %7.1f us (%6.1f TF/s)  first-gen bwd %7.1f us" % (
+        lq, lk, res.get("whole-row", float("nan")), res["chunked"], fl / res["chunked"] / 1e6, tb, 2.5 * fl / tb / 1e6, tb_old),
         flush=True)
