@@ -635,12 +635,12 @@ __device__ __forceinline__ uint64_t rows_b_desc(uint32_t tile, int ks) {
 // ---------------------------------------------------------------------------------------------------------
 // dq pass: ds_e = p_e * (dP_e * scale - delta * scale),  p_e = 2^(s_e * c1 [+ kmask_e] - lse)
 // DROP: 0 = no dropout, 1 = mask regenerated from the counter hash, 2 = mask read from the forward's keep-bit word
-template <bool KMASK, int DROP, bool VIS>
-__device__ __forceinline__ void dq_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&ds)[16],
+template <bool KMASK, int DROP, bool VIS, int N = 32>
+__device__ __forceinline__ void dq_group_math(const uint32_t (&rs)[N], const uint32_t (&rp)[N], uint32_t (&ds)[N / 2],
                                               float c1, float neg_lse, const float* km, int n_vis, float scale_keep,
                                               float nds, uint32_t dkey, uint32_t pair0, uint32_t dth, uint32_t bits) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < N; i += 2) {
         uint32_t dmask = 0xffffffffu;
         if (DROP == 1) dmask = drop_pair_mask(dkey, pair0 + (i >> 1), dth);
         float v2[2];
@@ -693,14 +693,14 @@ __device__ __forceinline__ void dqkv_group_math(const uint32_t (&rs)[32], const 
 }
 
 // dkv pass (thread = key row, 32 queries): p_e as above with per-query lse, pd_e = dropout(p)_e (-> dV), ds_e (-> dK)
-template <int DROP, bool VIS>
-__device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&pr)[16],
-                                               uint32_t (&ds)[16], float c1, float kbias, const float* lse, const float* del,
+template <int DROP, bool VIS, int N = 32>
+__device__ __forceinline__ void dkv_group_math(const uint32_t (&rs)[N], const uint32_t (&rp)[N], uint32_t (&pr)[N / 2],
+                                               uint32_t (&ds)[N / 2], float c1, float kbias, const float* lse, const float* del,
                                                int e_first, float scale_keep, float inv_keep, uint32_t dkey,
                                                uint32_t pair0, uint32_t pair_stride, uint32_t dth, uint32_t lane_mask,
                                                const uint32_t* bits, int bit) {
 #pragma unroll
-    for (int e = 0; e < 32; e += 4) {
+    for (int e = 0; e < N; e += 4) {
         const float4 l4 = *reinterpret_cast<const float4*>(lse + e);
         const float4 d4 = *reinterpret_cast<const float4*>(del + e);
         uint32_t bw[4] = {0, 0, 0, 0};
@@ -1268,18 +1268,39 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 
 // =====================================================================================================
 // Backward, second generation (problems with more than one query tile, fp32 O saved by the forward): the same two
-// passes, re-cut so that TWO CTAs share an SM and the bf16 P / dS operands never leave tensor memory.
-//   * 256 threads (thread = tile row x one 32-column half of a 64-wide chunk) and 64-key / 64-query chunks: 84 KB of
-//     shared memory and 256 TMEM columns per CTA.  The first generation (512 threads, 128-wide chunks, 197 KB, 512
-//     columns, one CTA per SM) spent 35 % of its issue slots spinning on mbarriers — every chunk is a chain
-//     MMA -> tcgen05.ld -> exponentials -> operand tile -> MMA, and one CTA has nothing else to run meanwhile.
-//   * the dS (dq pass) and P^T / dS^T (dkv pass) tiles go registers -> tcgen05.st -> TMEM and feed the accumulating
-//     products as TMEM A operands (tcgen05.mma [d], [a], b-desc): no swizzled shared-memory tile, no proxy fence.
-//   * 393 keys are 7 chunks of 64 (448 columns computed, the last chunk 16 wide) instead of 4 of 128 (400 of 512).
+// passes, re-cut so that TWO CTAs share an SM, each CTA runs TWO independent half-chunk pipelines, and the bf16
+// P / dS operands never leave tensor memory.
+//   * The first generation (512 threads, 128-wide chunks, 197 KB, 512 TMEM columns, one CTA per SM) spent 35 % of its
+//     issue slots at barriers: every chunk is a chain MMA -> tcgen05.ld -> exponentials -> operand tile -> MMA with two
+//     block-wide barriers, the MMA / TMA issue sits on one math thread's path, and one CTA has nothing else to run.
+//   * Here a chunk is 64 keys (dq pass) / 64 queries (dkv pass), cut into two 32-wide halves.  Warps 0-3 own half 0,
+//     warps 4-7 half 1 (thread = tile row x 32 columns), warp 8 issues every TMA load and tcgen05.mma.  A half's score
+//     products, its exponentials and its accumulating products form their own chain, linked to the issuer by two
+//     mbarriers (values loaded / operand stored) — no block-wide barrier inside the loop; while one half does its
+//     exponentials the tensor core runs the other half's (and the other CTA's) products.
+//   * the dS (dq pass) and P^T / dS^T (dkv pass) operands go registers -> tcgen05.st -> TMEM and feed the accumulating
+//     products as TMEM A operands (tcgen05.mma [d], [a], b-desc): no swizzled shared-memory tile, no proxy fence.  In the
+//     dkv pass they overwrite the first half of the very score columns their warp has just read (256 TMEM columns per
+//     CTA: S^T 64 | dP^T 64 | dK 64 | dV 64); the next score products into those columns are issued behind the products
+//     that read them, on the same in-order tensor pipe.
+//   * 393 keys are 7 chunks of 64 (400 of 448 columns useful, the last chunk 16 wide) instead of 4 of 128 (400 of 512).
+//   84 KB (dq) / 92 KB (dkv) of shared memory and 256 TMEM columns per CTA, 288 threads, <= 112 registers.
 // =====================================================================================================
-constexpr int kB2Threads = 256;
+constexpr int kB2Threads = 288;
 constexpr int kB2Chunk = 64;
 constexpr int kB2TileBytes = 81920;     // 2 x 16 KB resident tiles + 3 stages x 2 x 8 KB streamed chunks
+constexpr int kB2MaxLen = 512;          // longest lq / lk these kernels take (per-row vectors staged in shared memory)
+
+struct B2Bars {
+    uint64_t res;          // the CTA's resident tiles landed
+    uint64_t chunk[3];     // streamed chunk stage landed
+    uint64_t s[2];         // half h: score products of the current chunk complete
+    uint64_t ld[2];        // half h: its four warps hold the score values in registers
+    uint64_t st[2];        // half h: its four warps have stored the bf16 operand
+    uint64_t acc[2];       // dq pass, half h: the dQ product of a chunk retired
+    uint64_t done;         // every product retired
+    uint32_t tmem_slot;
+};
 
 template <int DROP>
 __global__ void __launch_bounds__(kB2Threads, 2)
@@ -1294,184 +1315,218 @@ attn_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     uint8_t* sV = smem + 57344;               // 3 x 8 KB
     float* s_part = reinterpret_cast<float*>(smem + kB2TileBytes);   // [2 halves][128 rows]
     float* s_kmask = s_part + 256;                                     // [512] key mask x log2(e)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kmask + 512);
-    uint64_t* bar_q = bars;          // Q + dO landed
-    uint64_t* bar_kv = bars + 1;     // [3]
-    uint64_t* bar_s = bars + 4;      // S and dP of the current chunk complete
-    uint64_t* bar_dq = bars + 5;     // dQ product of a chunk retired (frees the dS columns and the chunk's K/V buffer)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    B2Bars* bars = reinterpret_cast<B2Bars*>(s_kmask + kB2MaxLen);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_kc = (p.lk + kB2Chunk - 1) / kB2Chunk;
 
-    if (tid == 0) {
-        mbar_init(bar_q, 1);
-        mbar_init(bar_kv, 1), mbar_init(bar_kv + 1, 1), mbar_init(bar_kv + 2, 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_dq, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128, t_ds = tmem + 192;   // dS: bf16 pairs, 32 columns
-    const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
-    auto chunk_n16 = [&](int j) { return (min(kB2Chunk, p.lk - j * kB2Chunk) + 15) & ~15; };
-
-    auto issue_s = [&](int j) {   // S = Q K_j^T ; dP = dO V_j^T
-        const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
-        const uint32_t bk = smem_u32(sK + (j % 3) * 8192), bv = smem_u32(sV + (j % 3) * 8192);
-        const uint32_t idesc_s = make_idesc_bf16(128, chunk_n16(j), 0, 0);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(t_s, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(bk + ks * 32, 16, 1024), idesc_s, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(t_dp, make_smem_desc(ado + ks * 32, 16, 1024), make_smem_desc(bv + ks * 32, 16, 1024), idesc_s, ks > 0);
-        tc_commit(bar_s);
-    };
     auto load_kv = [&](int j) {
         const int st = j % 3;
-        mbar_expect_tx(bar_kv + st, 16384);
-        tma_load_3d(sK + st * 8192, &tma_k, bar_kv + st, h * kHeadDim, j * kB2Chunk, b);
-        tma_load_3d(sV + st * 8192, &tma_v, bar_kv + st, h * kHeadDim, j * kB2Chunk, b);
+        mbar_expect_tx(&bars->chunk[st], 16384);
+        tma_load_3d(sK + st * 8192, &tma_k, &bars->chunk[st], h * kHeadDim, j * kB2Chunk, b);
+        tma_load_3d(sV + st * 8192, &tma_v, &bars->chunk[st], h * kHeadDim, j * kB2Chunk, b);
     };
-
-    if (tid == 0) {
-        mbar_expect_tx(bar_q, 32768);
-        tma_load_3d(sQ, &tma_q, bar_q, h * kHeadDim, q0, b);
-        tma_load_3d(sdO, &tma_do, bar_q, h * kHeadDim, q0, b);
+    if (tid == 256) {
+        // the issuing thread initialises the barriers and starts the first loads at once: they overlap the TMEM
+        // allocation and the other warps' first global reads
+        mbar_init(&bars->res, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&bars->chunk[i], 1);
+        for (int i = 0; i < 2; ++i)
+            mbar_init(&bars->s[i], 1), mbar_init(&bars->ld[i], 4), mbar_init(&bars->st[i], 4), mbar_init(&bars->acc[i], 1);
+        mbar_init(&bars->done, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&bars->res, 32768);
+        tma_load_3d(sQ, &tma_q, &bars->res, h * kHeadDim, q0, b);
+        tma_load_3d(sdO, &tma_do, &bars->res, h * kHeadDim, q0, b);
         load_kv(0);
         if (n_kc > 1) load_kv(1);
         if (n_kc > 2) load_kv(2);
-        mbar_wait(bar_q, 0);
-        mbar_wait(bar_kv, 0);
-        tc_fence_after();
-        issue_s(0);
     }
-    __syncwarp();
-
-    const int row = (warp & 3) * 32 + lane, half = warp >> 2;     // half: which 32 columns of the 64-wide chunk
-    const int q = q0 + row;
-    const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
-    const float* kmask = p.mask_mode == 1 ? p.key_mask + (size_t)b * p.lk : nullptr;
-    const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
-    const float c1 = p.scale * kLog2e;
-    const float my_lse = q < p.lq ? p.lse[((size_t)b * p.heads + h) * p.lq + q] * kLog2e : INFINITY;
-    uint32_t dkey = 0, dth = 0, row_pair0 = 0;
-    float inv_keep = 1.f;
-    if (DROP) {
-        dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
-        row_pair0 = attn_row_pair0(b, p.heads, h, p.lq, q, p.lk), inv_keep = 1.f / (1.f - p.drop.p);
-    }
-    if (kmask)
-        for (int k = tid; k < 512; k += kB2Threads) s_kmask[k] = k < p.lk ? kmask[k] * kLog2e : 0.f;
-    float neg_delta_scaled;
-    {
-        // delta = rowsum(dO o O_f32) (see attn_bwd_dq_kernel): each of the row's two threads takes 32 head columns
-        float part = 0.f;
-        if (q < p.lq) {
-            const float4* po = reinterpret_cast<const float4*>(p.o_f32 + ((size_t)b * p.lq + q) * p.ldof + h * kHeadDim + half * 32);
-            const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)b * p.lq + q) * p.lddo + h * kHeadDim + half * 32);
+    // delta = rowsum(dO o O_f32) (see attn_bwd_dq_kernel): each of the row's two threads takes 32 head columns.  The
+    // global reads are issued before anything else so that their latency overlaps the set-up and the first products.
+    float delta_part = 0.f, my_lse = INFINITY;
+    if (warp < 8) {
+        const int row_ = (warp & 3) * 32 + lane, half_ = warp >> 2, q_ = q0 + row_;
+        if (q_ < p.lq) {
+            my_lse = __ldg(p.lse + ((size_t)b * p.heads + h) * p.lq + q_) * kLog2e;
+            const float4* po = reinterpret_cast<const float4*>(p.o_f32 + ((size_t)b * p.lq + q_) * p.ldof + h * kHeadDim + half_ * 32);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)b * p.lq + q_) * p.lddo + h * kHeadDim + half_ * 32);
+            uint4 g[4];
+            float4 o[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[i] = __ldg(pd + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __ldg(po + i);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint4 g = __ldg(pd + i);
-                const float4 o0 = __ldg(po + 2 * i), o1 = __ldg(po + 2 * i + 1);
+                const float4 o0 = o[2 * i], o1 = o[2 * i + 1];
                 float2 y;
-                y = unpack_bf16x2(g.x), part = fmaf(o0.x, y.x, fmaf(o0.y, y.y, part));
-                y = unpack_bf16x2(g.y), part = fmaf(o0.z, y.x, fmaf(o0.w, y.y, part));
-                y = unpack_bf16x2(g.z), part = fmaf(o1.x, y.x, fmaf(o1.y, y.y, part));
-                y = unpack_bf16x2(g.w), part = fmaf(o1.z, y.x, fmaf(o1.w, y.y, part));
+                y = unpack_bf16x2(g[i].x), delta_part = fmaf(o0.x, y.x, fmaf(o0.y, y.y, delta_part));
+                y = unpack_bf16x2(g[i].y), delta_part = fmaf(o0.z, y.x, fmaf(o0.w, y.y, delta_part));
+                y = unpack_bf16x2(g[i].z), delta_part = fmaf(o1.x, y.x, fmaf(o1.y, y.y, delta_part));
+                y = unpack_bf16x2(g[i].w), delta_part = fmaf(o1.z, y.x, fmaf(o1.w, y.y, delta_part));
             }
         }
-        s_part[half * 128 + row] = part;
-        __syncthreads();
-        const float my_delta = s_part[row] + s_part[128 + row];
-        neg_delta_scaled = -my_delta * p.scale;
-        if (half == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
     }
+    if (warp == 0) tmem_alloc(&bars->tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_slot;
+    const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128, t_ds = tmem + 192;   // dS: bf16 pairs, 2 x 16 columns
+    // keys of chunk j that half hh covers, rounded up to the MMA granule (0: the half has nothing to do)
+    auto half_n16 = [&](int j, int hh) { return max(0, min(32, ((min(kB2Chunk, p.lk - j * kB2Chunk) + 15) & ~15) - 32 * hh)); };
 
-    const bool rows_live = q0 + (warp & 3) * 32 < p.lq;
-    const float scale_keep = p.scale * inv_keep;
-    const int c = half * 32;
-    for (int j = 0; j < n_kc; ++j) {
-        const int n16 = chunk_n16(j);
-        const bool live = rows_live && c < n16;     // warp-uniform
-        uint32_t keep_word = 0;
-        if (DROP == 2 && live && q < p.lq)          // requested ahead of the wait for the score products
-            keep_word = __ldg(p.drop_bits + (((size_t)b * p.heads + h) * p.lq + q) * (size_t)((p.lk + 31) >> 5) + j * 2 + half);
-        mbar_wait(bar_s, j & 1);
-        tc_fence_after();
-        uint32_t rs[32], rp[32];
-        if (live) {
-            tmem_ld32(t_s + t_row + c, rs);
-            tmem_ld32(t_dp + t_row + c, rp);
-            tmem_ld_wait();
-        }
-        tc_fence_before();
-        __syncthreads();                            // every thread holds its S/dP values: the TMEM tiles are free
-        if (tid == 0) {
+    if (warp == 8) {
+        // ------------------------------------------------------------------ issuer: TMA loads and every product
+        if (lane == 0) {
+            const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
+            auto issue_s = [&](int j, int hh) {   // S = Q K_j^T ; dP = dO V_j^T  for the 32 keys of half hh
+                const int n = half_n16(j, hh);
+                if (n == 0) return;
+                const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
+                const uint32_t bk = smem_u32(sK + (j % 3) * 8192) + hh * 4096, bv = smem_u32(sV + (j % 3) * 8192) + hh * 4096;
+                const uint32_t idesc_s = make_idesc_bf16(128, n, 0, 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(t_s + hh * 32, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(bk + ks * 32, 16, 1024), idesc_s, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(t_dp + hh * 32, make_smem_desc(ado + ks * 32, 16, 1024), make_smem_desc(bv + ks * 32, 16, 1024), idesc_s, ks > 0);
+                tc_commit(&bars->s[hh]);
+            };
+            mbar_wait(&bars->res, 0);
+            mbar_wait(&bars->chunk[0], 0);
             tc_fence_after();
-            if (j + 1 < n_kc) {                     // the next chunk's score products run under this chunk's exponentials
-                mbar_wait(bar_kv + (j + 1) % 3, ((j + 1) / 3) & 1);
-                tc_fence_after();
-                issue_s(j + 1);
+            issue_s(0, 0), issue_s(0, 1);
+            bool first = true;
+            for (int j = 0; j < n_kc; ++j) {
+                if (j + 1 < n_kc) {
+                    mbar_wait(&bars->chunk[(j + 1) % 3], ((j + 1) / 3) & 1);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (half_n16(j, hh) == 0) continue;
+                        mbar_wait(&bars->ld[hh], j & 1);        // the half's S/dP columns have been read
+                        tc_fence_after();
+                        issue_s(j + 1, hh);
+                    }
+                }
+                if (j >= 1 && j + 2 < n_kc) {
+                    // K/V buffer (j - 1) % 3 is free once both halves' dQ products of chunk j - 1 retired
+                    mbar_wait(&bars->acc[0], (j - 1) & 1);
+                    mbar_wait(&bars->acc[1], (j - 1) & 1);
+                    load_kv(j + 2);
+                }
+                const uint32_t bk = smem_u32(sK + (j % 3) * 8192);
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int n = half_n16(j, hh);
+                    if (n == 0) continue;
+                    mbar_wait(&bars->st[hh], j & 1);            // the half's dS operand is in tensor memory
+                    tc_fence_after();
+                    for (int ks = 0; ks < (n >> 4); ++ks) {
+                        umma_bf16_ts(t_dq, t_ds + hh * 16 + ks * 8, rows_b_desc(bk, 2 * hh + ks), idesc_dq, first ? 0u : 1u);
+                        first = false;
+                    }
+                    tc_commit(&bars->acc[hh]);
+                }
             }
-            if (j >= 1 && j + 2 < n_kc) {
-                mbar_wait(bar_dq, (j - 1) & 1);     // K/V buffer (j - 1) % 3 is free once dQ_{j-1} retired
-                load_kv(j + 2);
-            }
-        }
-        if (live) {
-            const int key0 = j * kB2Chunk + c;
-            const int n_vis = k_lim - key0;            // visible columns of this group (may be <= 0 or >= 32)
-            uint32_t ds[16];
-            const uint32_t pair0 = row_pair0 + (uint32_t)(key0 >> 1);
-            const float* km = s_kmask + key0;
-            if (__all_sync(0xffffffffu, n_vis >= 32)) {
-                if (kmask) dq_group_math<true, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
-                else dq_group_math<false, DROP, true>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
-            } else {
-                if (kmask) dq_group_math<true, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
-                else dq_group_math<false, DROP, false>(rs, rp, ds, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, keep_word);
-            }
-            if (j >= 1) {
-                mbar_wait(bar_dq, (j - 1) & 1);     // the previous dQ product has read the dS columns
-                tc_fence_after();
-            }
-            tmem_st16(t_ds + t_row + half * 16, ds);
-            tmem_st_wait();
-        }
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t bk = smem_u32(sK + (j % 3) * 8192);
-            for (int ks = 0; ks < (n16 >> 4); ++ks)
-                umma_bf16_ts(t_dq, t_ds + ks * 8, rows_b_desc(bk, ks), idesc_dq, (j > 0 || ks > 0) ? 1u : 0u);
-            tc_commit(bar_dq);
+            tc_commit(&bars->done);
         }
         __syncwarp();
-    }
-    mbar_wait(bar_dq, (n_kc - 1) & 1);
-    tc_fence_after();
-    {
-        uint32_t raw[32];
-        tmem_ld32(t_dq + t_row + half * 32, raw);
-        tmem_ld_wait();
-        if (q < p.lq) {
-            __nv_bfloat16* dst = p.dq + ((size_t)b * p.lq + q) * p.lddq + h * kHeadDim + half * 32;
+    } else {
+        // ------------------------------------------------------------------ math warps
+        const int row = (warp & 3) * 32 + lane, half = warp >> 2;     // half: which 32 keys of the 64-key chunk
+        const int q = q0 + row;
+        const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
+        const float* kmask = p.mask_mode == 1 ? p.key_mask + (size_t)b * p.lk : nullptr;
+        const int k_lim = p.mask_mode == 2 ? min(p.lk, (q / p.q_per_frame + 1) * p.k_per_frame) : p.lk;
+        const float c1 = p.scale * kLog2e;
+        uint32_t dkey = 0, dth = 0, row_pair0 = 0;
+        float inv_keep = 1.f;
+        if (DROP) {
+            dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
+            row_pair0 = attn_row_pair0(b, p.heads, h, p.lq, q, p.lk), inv_keep = 1.f / (1.f - p.drop.p);
+        }
+        if (kmask)
+            for (int k = tid; k < kB2MaxLen; k += 256) s_kmask[k] = k < p.lk ? kmask[k] * kLog2e : 0.f;
+        s_part[half * 128 + row] = delta_part;
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight math warps (the issuer does not take part)
+        const float my_delta = s_part[row] + s_part[128 + row];
+        const float neg_delta_scaled = -my_delta * p.scale;
+        if (half == 0 && q < p.lq) p.delta[((size_t)b * p.heads + h) * p.lq + q] = my_delta;
+        const bool rows_live = q0 + (warp & 3) * 32 < p.lq;
+        const float scale_keep = p.scale * inv_keep;
+        const int c = half * 32;
+        for (int j = 0; j < n_kc; ++j) {
+            const int n16 = half_n16(j, half);
+            if (n16 == 0) break;                        // only the last chunk can be short
+            uint32_t keep_word = 0;
+            if (DROP == 2 && rows_live && q < p.lq)     // requested ahead of the wait for the score products
+                keep_word = __ldg(p.drop_bits + (((size_t)b * p.heads + h) * p.lq + q) * (size_t)((p.lk + 31) >> 5) + j * 2 + half);
+            mbar_wait(&bars->s[half], j & 1);
+            tc_fence_after();
+            uint32_t ds0[8], ds1[8];
+            const int key0 = j * kB2Chunk + c;
+            // two 16-column batches keep the live registers under 112
+            auto batch = [&](const int sb, uint32_t(&dsb)[8]) {
+                uint32_t rs[16], rp[16];
+                if (rows_live) {
+                    tmem_ld16(t_s + t_row + c + 16 * sb, rs);
+                    tmem_ld16(t_dp + t_row + c + 16 * sb, rp);
+                    tmem_ld_wait();
+                }
+                if (sb == 1) {
+                    // the half's score columns are in registers: the issuer may overwrite them with the next chunk's
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_relaxed(&bars->ld[half]);
+                }
+                if (rows_live) {
+                    const int n_vis = k_lim - key0 - 16 * sb;      // visible columns of this batch (may be <= 0 or >= 16)
+                    const uint32_t pair0 = row_pair0 + (uint32_t)((key0 + 16 * sb) >> 1);
+                    const float* km = s_kmask + key0 + 16 * sb;
+                    const uint32_t kw = keep_word >> (16 * sb);
+                    if (__all_sync(0xffffffffu, n_vis >= 16)) {
+                        if (kmask) dq_group_math<true, DROP, true, 16>(rs, rp, dsb, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, kw);
+                        else dq_group_math<false, DROP, true, 16>(rs, rp, dsb, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, kw);
+                    } else {
+                        if (kmask) dq_group_math<true, DROP, false, 16>(rs, rp, dsb, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, kw);
+                        else dq_group_math<false, DROP, false, 16>(rs, rp, dsb, c1, -my_lse, km, n_vis, scale_keep, neg_delta_scaled, dkey, pair0, dth, kw);
+                    }
+                }
+            };
+            batch(0, ds0);
+            batch(1, ds1);
+            if (j >= 1) {
+                mbar_wait(&bars->acc[half], (j - 1) & 1);   // the half's previous dQ product has read its dS columns
+                tc_fence_after();
+            }
+            if (rows_live) {
+                tmem_st8(t_ds + t_row + half * 16, ds0);
+                tmem_st8(t_ds + t_row + half * 16 + 8, ds1);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(&bars->st[half]);
+        }
+        mbar_wait(&bars->done, 0);
+        tc_fence_after();
+        {
+            uint32_t raw[32];
+            tmem_ld32(t_dq + t_row + half * 32, raw);
+            tmem_ld_wait();
+            if (q < p.lq) {
+                __nv_bfloat16* dst = p.dq + ((size_t)b * p.lq + q) * p.lddq + h * kHeadDim + half * 32;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
-                u.y = pack_bf16x2(__uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
-                u.z = pack_bf16x2(__uint_as_float(raw[i + 4]), __uint_as_float(raw[i + 5]));
-                u.w = pack_bf16x2(__uint_as_float(raw[i + 6]), __uint_as_float(raw[i + 7]));
-                *reinterpret_cast<uint4*>(dst + i) = u;
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+                    u.y = pack_bf16x2(__uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+                    u.z = pack_bf16x2(__uint_as_float(raw[i + 4]), __uint_as_float(raw[i + 5]));
+                    u.w = pack_bf16x2(__uint_as_float(raw[i + 6]), __uint_as_float(raw[i + 7]));
+                    *reinterpret_cast<uint4*>(dst + i) = u;
+                }
             }
         }
     }
@@ -1483,10 +1538,7 @@ attn_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     }
 }
 
-// dkv pass: CTA = (128-key tile, head, batch), 64-query chunks.  S^T / dP^T of a chunk land in TMEM columns [0,64) /
-// [64,128); after every thread has read its values the bf16 P^T / dS^T operands are stored over the first 32 columns
-// of the same two regions, the accumulating products (dV += P^T dO_i, dK += dS^T Q_i) read them from there, and the
-// next chunk's score products are issued behind them on the same (in-order) tensor pipe.
+// dkv pass: CTA = (128-key tile, head, batch), 64-query chunks, half = 32 queries.
 template <int DROP>
 __global__ void __launch_bounds__(kB2Threads, 2)
 attn_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_do,
@@ -1498,186 +1550,187 @@ attn_bwd2_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     uint8_t* sV = smem + 16384;               // 16 KB
     uint8_t* sQ = smem + 32768;               // 3 x 8 KB  [64 queries x 64]
     uint8_t* sdO = smem + 57344;              // 3 x 8 KB
-    float* s_lse = reinterpret_cast<float*>(smem + kB2TileBytes);      // [4][64] ring over query chunks
-    float* s_delta = s_lse + 256;                                        // [4][64]
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_delta + 256);       // [4][4 key words][64 queries] keep-bit words
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bits + 1024);
-    uint64_t* bar_kv = bars;
-    uint64_t* bar_q = bars + 1;      // [3]
-    uint64_t* bar_s = bars + 4;      // everything issued up to and including the score products of a chunk retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    float* s_lse = reinterpret_cast<float*>(smem + kB2TileBytes);      // [512] lse x log2(e) of every query (+inf past lq)
+    float* s_delta = s_lse + kB2MaxLen;                                  // [512] delta x scale
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_delta + kB2MaxLen); // [4 key words][512 queries] keep-bit words
+    B2Bars* bars = reinterpret_cast<B2Bars*>(s_bits + 4 * kB2MaxLen);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_qc = (p.lq + kB2Chunk - 1) / kB2Chunk;
 
-    if (tid == 0) {
-        mbar_init(bar_kv, 1);
-        mbar_init(bar_q, 1), mbar_init(bar_q + 1, 1), mbar_init(bar_q + 2, 1);
-        mbar_init(bar_s, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t t_s = tmem, t_dp = tmem + 64, t_dk = tmem + 128, t_dv = tmem + 192;
-    const uint32_t idesc_acc = make_idesc_bf16(128, kHeadDim, 0, 1);
-    auto chunk_n16 = [&](int i) { return (min(kB2Chunk, p.lq - i * kB2Chunk) + 15) & ~15; };
-
-    auto issue_s = [&](int i) {   // S^T = K Q_i^T ; dP^T = V dO_i^T ; the commit also covers every product issued before
-        const uint32_t idesc_s = make_idesc_bf16(128, chunk_n16(i), 0, 0);
-        const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
-        const uint32_t bq = smem_u32(sQ + (i % 3) * 8192), bd = smem_u32(sdO + (i % 3) * 8192);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(t_s, make_smem_desc(ak + ks * 32, 16, 1024), make_smem_desc(bq + ks * 32, 16, 1024), idesc_s, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(t_dp, make_smem_desc(av + ks * 32, 16, 1024), make_smem_desc(bd + ks * 32, 16, 1024), idesc_s, ks > 0);
-        tc_commit(bar_s);
-    };
     auto load_q = [&](int i) {
         const int st = i % 3;
-        mbar_expect_tx(bar_q + st, 16384);
-        tma_load_3d(sQ + st * 8192, &tma_q, bar_q + st, h * kHeadDim, i * kB2Chunk, b);
-        tma_load_3d(sdO + st * 8192, &tma_do, bar_q + st, h * kHeadDim, i * kB2Chunk, b);
+        mbar_expect_tx(&bars->chunk[st], 16384);
+        tma_load_3d(sQ + st * 8192, &tma_q, &bars->chunk[st], h * kHeadDim, i * kB2Chunk, b);
+        tma_load_3d(sdO + st * 8192, &tma_do, &bars->chunk[st], h * kHeadDim, i * kB2Chunk, b);
     };
-    // per-query vectors of a chunk: global -> register at the top of an iteration, register -> shared memory at its
-    // end, two chunks ahead of their use (see attn_bwd_dkv_kernel)
-    const int nw = (p.lk + 31) >> 5;
-    auto fetch_vec = [&](int i, float& v, uint32_t& w) {
-        const int qq = i * kB2Chunk + (tid & 63);
-        const size_t base = ((size_t)b * p.heads + h) * p.lq;
-        v = 0.f, w = 0u;
-        if (tid < 64) v = qq < p.lq ? __ldg(p.lse + base + qq) * kLog2e : INFINITY;
-        else if (tid < 128) v = qq < p.lq ? __ldg(p.delta + base + qq) * p.scale : 0.f;       // pre-scaled
-        if (DROP == 2) {
-            const int ql = i * kB2Chunk + (tid >> 2), kw = (k0 >> 5) + (tid & 3);
-            if (ql < p.lq && kw < nw) w = __ldg(p.drop_bits + (base + ql) * nw + kw);
-        }
-    };
-    auto stash_vec = [&](int i, float v, uint32_t w) {
-        if (tid < 64) s_lse[(i & 3) * 64 + tid] = v;
-        else if (tid < 128) s_delta[(i & 3) * 64 + (tid - 64)] = v;
-        if (DROP == 2) s_bits[(i & 3) * 256 + (tid & 3) * 64 + (tid >> 2)] = w;
-    };
-    if (tid == 0) {
-        mbar_expect_tx(bar_kv, 32768);
-        tma_load_3d(sK, &tma_k, bar_kv, h * kHeadDim, k0, b);
-        tma_load_3d(sV, &tma_v, bar_kv, h * kHeadDim, k0, b);
+    if (tid == 256) {
+        // barriers and the first loads by the issuing thread, under the staging of the per-query vectors below
+        mbar_init(&bars->res, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&bars->chunk[i], 1);
+        for (int i = 0; i < 2; ++i)
+            mbar_init(&bars->s[i], 1), mbar_init(&bars->ld[i], 4), mbar_init(&bars->st[i], 4), mbar_init(&bars->acc[i], 1);
+        mbar_init(&bars->done, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&bars->res, 32768);
+        tma_load_3d(sK, &tma_k, &bars->res, h * kHeadDim, k0, b);
+        tma_load_3d(sV, &tma_v, &bars->res, h * kHeadDim, k0, b);
         load_q(0);
         if (n_qc > 1) load_q(1);
         if (n_qc > 2) load_q(2);
-        mbar_wait(bar_kv, 0);
-        mbar_wait(bar_q, 0);
-        tc_fence_after();
-        issue_s(0);
     }
+    if (warp == 0) tmem_alloc(&bars->tmem_slot, 256);
     {
-        float v;
-        uint32_t w;
-        fetch_vec(0, v, w), stash_vec(0, v, w);
-        if (n_qc > 1) fetch_vec(1, v, w), stash_vec(1, v, w);
-    }
-    __syncthreads();
-
-    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
-    const int key = k0 + row;
-    const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
-    const float c1 = p.scale * kLog2e;
-    const float kbias = (p.mask_mode == 1 && key < p.lk) ? p.key_mask[(size_t)b * p.lk + key] * kLog2e : 0.f;
-    const int q_first = p.mask_mode == 2 ? (key / p.k_per_frame) * p.q_per_frame : 0;
-    const bool key_ok = key < p.lk;
-    uint32_t dkey = 0, dth = 0, lane_mask = 0, pair_stride = 0, col_pair0 = 0;
-    float inv_keep = 1.f;
-    if (DROP) {
-        if (DROP == 1) dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
-        inv_keep = 1.f / (1.f - p.drop.p);
-        lane_mask = (key & 1) ? 0xffff0000u : 0x0000ffffu;
-        pair_stride = attn_row_pair0(0, p.heads, 0, p.lq, 1, p.lk);
-        col_pair0 = attn_row_pair0(b, p.heads, h, p.lq, 0, p.lk) + (uint32_t)(key >> 1);
-    }
-
-    const bool rows_live = k0 + (warp & 3) * 32 < p.lk;
-    const float scale_keep = p.scale * inv_keep;
-    const int c = half * 32;
-    for (int i = 0; i < n_qc; ++i) {
-        float nxt_v = 0.f;
-        uint32_t nxt_w = 0u;
-        if (i + 2 < n_qc) fetch_vec(i + 2, nxt_v, nxt_w);
-        const int n16 = chunk_n16(i);
-        const bool live = rows_live && c < n16;     // warp-uniform
-        mbar_wait(bar_s, i & 1);                    // S^T_i / dP^T_i complete — and with them dK/dV of chunk i - 1
-        tc_fence_after();
-        if (tid == 0 && i >= 1 && i + 2 < n_qc) load_q(i + 2);      // buffer (i - 1) % 3 was last read by dK/dV_{i-1}
-        uint32_t rs[32], rp[32];
-        if (live) {
-            tmem_ld32(t_s + t_row + c, rs);
-            tmem_ld32(t_dp + t_row + c, rp);
-            tmem_ld_wait();
+        // per-query vectors of this (batch, head), staged once
+        const size_t base = ((size_t)b * p.heads + h) * p.lq;
+        const int nw = (p.lk + 31) >> 5;
+        for (int i = tid; i < kB2MaxLen; i += kB2Threads) {
+            s_lse[i] = i < p.lq ? __ldg(p.lse + base + i) * kLog2e : INFINITY;
+            s_delta[i] = i < p.lq ? __ldg(p.delta + base + i) * p.scale : 0.f;
         }
-        tc_fence_before();
-        __syncthreads();                            // every thread holds its values: the operand columns may be written
-        if (live) {
-            tc_fence_after();
-            const float* lse_i = s_lse + (i & 3) * 64 + c;
-            const float* del_i = s_delta + (i & 3) * 64 + c;
-            const uint32_t* bits_i = s_bits + (i & 3) * 256 + (row >> 5) * 64 + c;
-            uint32_t pr[16], ds[16];
-            const int e_first = key_ok ? q_first - (i * kB2Chunk + c) : 32;
-            const uint32_t pair0 = col_pair0 + (uint32_t)(i * kB2Chunk + c) * pair_stride;
-            if (__all_sync(0xffffffffu, e_first <= 0))
-                dkv_group_math<DROP, true>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask, bits_i, row & 31);
-            else
-                dkv_group_math<DROP, false>(rs, rp, pr, ds, c1, kbias, lse_i, del_i, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask, bits_i, row & 31);
-            tmem_st16(t_s + t_row + half * 16, pr);
-            tmem_st16(t_dp + t_row + half * 16, ds);
-            tmem_st_wait();
-        }
-        if (i + 2 < n_qc) stash_vec(i + 2, nxt_v, nxt_w);     // slot (i + 2) & 3 was last read two chunks ago
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t bq = smem_u32(sQ + (i % 3) * 8192), bd = smem_u32(sdO + (i % 3) * 8192);
-            for (int ks = 0; ks < (n16 >> 4); ++ks)
-                umma_bf16_ts(t_dv, t_s + ks * 8, rows_b_desc(bd, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-            for (int ks = 0; ks < (n16 >> 4); ++ks)
-                umma_bf16_ts(t_dk, t_dp + ks * 8, rows_b_desc(bq, ks), idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-            if (i + 1 < n_qc) {
-                mbar_wait(bar_q + (i + 1) % 3, ((i + 1) / 3) & 1);
-                tc_fence_after();
-                issue_s(i + 1);
-            } else {
-                tc_commit(bar_s);
+        if (DROP == 2)
+            for (int i = tid; i < 4 * kB2MaxLen; i += kB2Threads) {
+                const int ql = i >> 2, kw = (k0 >> 5) + (i & 3);
+                s_bits[(i & 3) * kB2MaxLen + ql] = (ql < p.lq && kw < nw) ? __ldg(p.drop_bits + (base + ql) * nw + kw) : 0u;
             }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_slot;
+    const uint32_t t_s = tmem, t_dp = tmem + 64, t_dk = tmem + 128, t_dv = tmem + 192;
+    auto half_n16 = [&](int i, int hh) { return max(0, min(32, ((min(kB2Chunk, p.lq - i * kB2Chunk) + 15) & ~15) - 32 * hh)); };
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc_acc = make_idesc_bf16(128, kHeadDim, 0, 1);
+            auto issue_s = [&](int i, int hh) {   // S^T = K Q_i^T ; dP^T = V dO_i^T  for the 32 queries of half hh
+                const int n = half_n16(i, hh);
+                if (n == 0) return;
+                const uint32_t idesc_s = make_idesc_bf16(128, n, 0, 0);
+                const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
+                const uint32_t bq = smem_u32(sQ + (i % 3) * 8192) + hh * 4096, bd = smem_u32(sdO + (i % 3) * 8192) + hh * 4096;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(t_s + hh * 32, make_smem_desc(ak + ks * 32, 16, 1024), make_smem_desc(bq + ks * 32, 16, 1024), idesc_s, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(t_dp + hh * 32, make_smem_desc(av + ks * 32, 16, 1024), make_smem_desc(bd + ks * 32, 16, 1024), idesc_s, ks > 0);
+                tc_commit(&bars->s[hh]);           // also covers every product issued before (dK / dV of the chunk before)
+            };
+            mbar_wait(&bars->res, 0);
+            mbar_wait(&bars->chunk[0], 0);
+            tc_fence_after();
+            issue_s(0, 0), issue_s(0, 1);
+            bool first = true;
+            for (int i = 0; i < n_qc; ++i) {
+                if (i >= 1 && i + 2 < n_qc) {
+                    // Q/dO buffer (i - 1) % 3 was last read by the dK / dV products of chunk i - 1, which the commits
+                    // of chunk i's score products cover (full chunks only: i + 2 < n_qc)
+                    mbar_wait(&bars->s[0], i & 1);
+                    mbar_wait(&bars->s[1], i & 1);
+                    load_q(i + 2);
+                }
+                if (i + 1 < n_qc) mbar_wait(&bars->chunk[(i + 1) % 3], ((i + 1) / 3) & 1);
+                const uint32_t bq = smem_u32(sQ + (i % 3) * 8192), bd = smem_u32(sdO + (i % 3) * 8192);
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int n = half_n16(i, hh);
+                    if (n == 0) continue;
+                    mbar_wait(&bars->st[hh], i & 1);            // P^T / dS^T of the half are in tensor memory
+                    tc_fence_after();
+                    for (int ks = 0; ks < (n >> 4); ++ks)
+                        umma_bf16_ts(t_dv, t_s + hh * 32 + ks * 8, rows_b_desc(bd, 2 * hh + ks), idesc_acc, (first && ks == 0) ? 0u : 1u);
+                    for (int ks = 0; ks < (n >> 4); ++ks)
+                        umma_bf16_ts(t_dk, t_dp + hh * 32 + ks * 8, rows_b_desc(bq, 2 * hh + ks), idesc_acc, (first && ks == 0) ? 0u : 1u);
+                    first = false;
+                    if (i + 1 < n_qc) issue_s(i + 1, hh);       // behind the products that read the same columns
+                }
+            }
+            tc_commit(&bars->done);
         }
         __syncwarp();
-    }
-    mbar_wait(bar_s, n_qc & 1);
-    tc_fence_after();
-    {
-        // half 0 writes dK, half 1 dV (64 columns each, two loads of 32)
-        const uint32_t t_src = (half == 0 ? t_dk : t_dv) + t_row;
-        __nv_bfloat16* base = half == 0 ? p.dk : p.dv;
-        const int64_t ld = half == 0 ? p.lddk : p.lddv;
+    } else {
+        const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+        const int key = k0 + row;
+        const uint32_t t_row = uint32_t((warp & 3) * 32) << 16;
+        const float c1 = p.scale * kLog2e;
+        const float kbias = (p.mask_mode == 1 && key < p.lk) ? p.key_mask[(size_t)b * p.lk + key] * kLog2e : 0.f;
+        const int q_first = p.mask_mode == 2 ? (key / p.k_per_frame) * p.q_per_frame : 0;   // block-causal: visible to q >= q_first
+        const bool key_ok = key < p.lk;
+        uint32_t dkey = 0, dth = 0, lane_mask = 0, pair_stride = 0, col_pair0 = 0;
+        float inv_keep = 1.f;
+        if (DROP) {
+            if (DROP == 1) dkey = drop_key(__ldg(p.drop.seed), p.drop.salt), dth = drop_thresh(p.drop.p);
+            inv_keep = 1.f / (1.f - p.drop.p);
+            lane_mask = (key & 1) ? 0xffff0000u : 0x0000ffffu;
+            pair_stride = attn_row_pair0(0, p.heads, 0, p.lq, 1, p.lk);
+            col_pair0 = attn_row_pair0(b, p.heads, h, p.lq, 0, p.lk) + (uint32_t)(key >> 1);
+        }
+        const bool rows_live = k0 + (warp & 3) * 32 < p.lk;     // warps of key rows beyond lk: nothing to do
+        const float scale_keep = p.scale * inv_keep;
+        const int c = half * 32;
+        for (int i = 0; i < n_qc; ++i) {
+            const int n16 = half_n16(i, half);
+            if (n16 == 0) break;
+            mbar_wait(&bars->s[half], i & 1);
+            tc_fence_after();
+            uint32_t pr0[8], pr1[8], ds0[8], ds1[8];
+            const int qc0 = i * kB2Chunk + c;           // first query of this half
+            auto batch = [&](const int sb, uint32_t(&prb)[8], uint32_t(&dsb)[8]) {
+                uint32_t rs[16], rp[16];
+                tmem_ld16(t_s + t_row + c + 16 * sb, rs);
+                tmem_ld16(t_dp + t_row + c + 16 * sb, rp);
+                tmem_ld_wait();
+                const int qb = qc0 + 16 * sb;
+                // first query of this batch that sees the key; queries beyond lq carry lse = +inf -> p = 0
+                const int e_first = key_ok ? q_first - qb : 16;
+                const uint32_t pair0 = col_pair0 + (uint32_t)qb * pair_stride;
+                const uint32_t* bits_i = s_bits + (row >> 5) * kB2MaxLen + qb;
+                if (__all_sync(0xffffffffu, e_first <= 0))
+                    dkv_group_math<DROP, true, 16>(rs, rp, prb, dsb, c1, kbias, s_lse + qb, s_delta + qb, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask, bits_i, row & 31);
+                else
+                    dkv_group_math<DROP, false, 16>(rs, rp, prb, dsb, c1, kbias, s_lse + qb, s_delta + qb, e_first, scale_keep, inv_keep, dkey, pair0, pair_stride, dth, lane_mask, bits_i, row & 31);
+            };
+            if (rows_live) {
+                batch(0, pr0, ds0);
+                batch(1, pr1, ds1);
+            }
+            if (rows_live) {
+                // over the first half of the score columns this warp has just read (its lanes, its 32 columns)
+                tmem_st8(t_s + t_row + c, pr0);
+                tmem_st8(t_s + t_row + c + 8, pr1);
+                tmem_st8(t_dp + t_row + c, ds0);
+                tmem_st8(t_dp + t_row + c + 8, ds1);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(&bars->st[half]);
+        }
+        mbar_wait(&bars->done, 0);
+        tc_fence_after();
+        {
+            // half 0 writes dK, half 1 dV (64 columns each, two loads of 32)
+            const uint32_t t_src = (half == 0 ? t_dk : t_dv) + t_row;
+            __nv_bfloat16* base = half == 0 ? p.dk : p.dv;
+            const int64_t ld = half == 0 ? p.lddk : p.lddv;
 #pragma unroll
-        for (int cc = 0; cc < 64; cc += 32) {
-            uint32_t raw[32];
-            tmem_ld32(t_src + cc, raw);
-            tmem_ld_wait();
-            if (key_ok) {
-                __nv_bfloat16* dst = base + ((size_t)b * p.lk + key) * ld + h * kHeadDim + cc;
+            for (int cc = 0; cc < 64; cc += 32) {
+                uint32_t raw[32];
+                tmem_ld32(t_src + cc, raw);
+                tmem_ld_wait();
+                if (key_ok) {
+                    __nv_bfloat16* dst = base + ((size_t)b * p.lk + key) * ld + h * kHeadDim + cc;
 #pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                    uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]));
-                    u.y = pack_bf16x2(__uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
-                    u.z = pack_bf16x2(__uint_as_float(raw[e + 4]), __uint_as_float(raw[e + 5]));
-                    u.w = pack_bf16x2(__uint_as_float(raw[e + 6]), __uint_as_float(raw[e + 7]));
-                    *reinterpret_cast<uint4*>(dst + e) = u;
+                    for (int e = 0; e < 32; e += 8) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]));
+                        u.y = pack_bf16x2(__uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
+                        u.z = pack_bf16x2(__uint_as_float(raw[e + 4]), __uint_as_float(raw[e + 5]));
+                        u.w = pack_bf16x2(__uint_as_float(raw[e + 6]), __uint_as_float(raw[e + 7]));
+                        *reinterpret_cast<uint4*>(dst + e) = u;
+                    }
                 }
             }
         }
@@ -1856,14 +1909,14 @@ extern "C" int shg_attn_bwd(const shg_attn_bwd_args* a, void* stream) {
         const char* e = getenv("SHG_ATTN_BWD2");
         g_attn_bwd2 = (e && e[0] == '0') ? 0 : 1;
     }
-    if (a->o_f32 && a->lk <= 512 && g_attn_bwd2) {
+    if (a->o_f32 && a->lk <= kB2MaxLen && a->lq <= kB2MaxLen && g_attn_bwd2) {
         // several query tiles: the two-CTA-per-SM passes with TMEM-resident P / dS operands (attn_bwd2_*_kernel)
         const CUtensorMap* tk64 = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, kB2Chunk);
         const CUtensorMap* tv64 = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, kB2Chunk);
         const CUtensorMap* tq64 = head_tmap(a->q, a->ldq, a->heads, a->lq, a->batch, kB2Chunk);
         const CUtensorMap* tdo64 = head_tmap(a->d_o, a->lddo, a->heads, a->lq, a->batch, kB2Chunk);
         if (!tk64 || !tv64 || !tq64 || !tdo64) return SHG_ECUDA;
-        const size_t smem2 = kB2TileBytes + 6144 + 128 + 1024;
+        const size_t smem2 = kB2TileBytes + 12288 + sizeof(B2Bars) + 16 + 1024;
         static bool attr2 = false;
         if (!attr2) {
             cudaFuncSetAttribute(attn_bwd2_dq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);

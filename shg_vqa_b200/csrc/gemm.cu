@@ -78,11 +78,6 @@ __device__ __forceinline__ PairItem pair_item(const GemmParams& p, int it) {
     return r;
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 #define SHG_STAMP(i) do { if (p.dbg && blockIdx.x == 0) p.dbg[i] = globaltimer_ns(); } while (0)
 
 __device__ __forceinline__ float apply_act(float x, int act) {

@@ -39,7 +39,10 @@ for lq, lk in SHAPES:
     _lib.check(_lib.lib().shg_set_attn_bwd_chunked(0))
     tb_old = graph_time(fb) * 1e3
     _lib.check(_lib.lib().shg_set_attn_bwd_chunked(1))
+    _lib.check(_lib.lib().shg_set_attn_bwd_merge(0))
+    tb_nomerge = graph_time(fb) * 1e3
+    _lib.check(_lib.lib().shg_set_attn_bwd_merge(1))
     fl = 4.0 * B * 12 * lq * lk * 64
-    print("%3d x %3d  fwd whole-row %7.1f us  chunked %7.1f us (%6.1f TF/s)   bwd %7.1f us (%6.1f TF/s)  first-gen bwd %7.1f us" % (
-        lq, lk, res.get("whole-row", float("nan")), res["chunked"], fl / res["chunked"] / 1e6, tb, 2.5 * fl / tb / 1e6, tb_old),
+    print("%3d x %3d  fwd whole-row %7.1f us  chunked %7.1f us (%6.1f TF/s)   bwd %7.1f us (%6.1f TF/s)  first-gen bwd %7.1f us  merge off %7.1f us" % (
+        lq, lk, res.get("whole-row", float("nan")), res["chunked"], fl / res["chunked"] / 1e6, tb, 2.5 * fl / tb / 1e6, tb_old, tb_nomerge),
         flush=True)
