@@ -293,8 +293,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     uint8_t* sQ = smem;                 // 128 x 128 B
     uint8_t* sK = smem + 16384;         // one chunk: 128 keys x 128 B
     uint8_t* sV = smem + 32768;         // one chunk
-    uint8_t* sP = smem + 49152;         // one chunk: two [128 x 64] bf16 blocks
-    float* s_kmask = reinterpret_cast<float*>(smem + 81920);          // [448] additive key mask * log2(e)
+    float* s_kmask = reinterpret_cast<float*>(smem + 49152);          // [448] additive key mask * log2(e)
     float* s_red = s_kmask + 448;                                      // [2][128]
     Fwd2Bars* bars = reinterpret_cast<Fwd2Bars*>(s_red + 256);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
@@ -324,12 +323,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_s = tmem, t_o = tmem + kFwd2Chunk;
+    // S chunk 128 columns | O tile 64 | P chunk (bf16 pairs) 64: P goes registers -> tcgen05.st -> TMEM and is the TMEM
+    // A operand of the PV product — no swizzled shared-memory tile, no proxy fence, no A-operand shared-memory reads
+    const uint32_t t_s = tmem, t_o = tmem + kFwd2Chunk, t_p = tmem + kFwd2Chunk + 64;
 
     if (warp == 8) {
         // ---------------------------------------------------------------- TMA + MMA issuer
         if (lane == 0) {
-            const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP);
+            const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV);
             const uint32_t idesc_o = make_idesc_bf16(128, kHeadDim, 0, 1);
             mbar_expect_tx(&bars->q, 16384);
             tma_load_3d(sQ, &tma_q, &bars->q, h * kHeadDim, q0, b);
@@ -344,8 +345,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
                 mbar_wait(&bars->v, j & 1);
                 tc_fence_after();
                 for (int k = 0; k < n16; k += 16)
-                    umma_bf16(t_o, make_smem_desc(ap + (k >> 6) * 16384 + ((k & 63) >> 4) * 32, 16, 1024),
-                              make_smem_desc(av + k * 128, 8192, 1024), idesc_o, k > 0);
+                    umma_bf16_ts(t_o, t_p + (k >> 1), make_smem_desc(av + k * 128, 8192, 1024), idesc_o, k > 0);
                 tc_commit(&bars->pv);
                 mbar_wait(&bars->pv, j & 1);
                 if (j + 1 < n_ch) {
@@ -391,9 +391,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         if (!rows_live) {
             // rows past Lq are never written below; the PV product still reads them: keep them finite (zero), so that no
             // NaN is left behind in TMEM for whoever allocates these columns next
+            uint32_t z[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<uint4*>(sP + half * 16384 + row * 128 + (j << 4)) = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 16; ++j) z[j] = 0u;
+            tmem_st16(t_p + t_row + half * 32, z);
+            tmem_st16(t_p + t_row + half * 32 + 16, z);
+            tmem_st_wait();
         }
         float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
         float o_acc[32];
@@ -463,7 +466,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
             alpha_prev = alpha;
             // pass B: probabilities of my columns -> bf16 -> P block `half` (row = 128 B, 16-byte units swizzled)
             float sum = 0.f;
-            uint8_t* prow = sP + half * 16384 + row * 128;
             for (int g = 0; g < n_mine; g += 32) {
                 uint32_t raw[32];
                 tmem_ld32(tmem + t_row + col0 + g, raw);
@@ -484,6 +486,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
                     }
                 }
                 const uint32_t keep_bits = keep_w[g >> 5];
+                uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 u;
@@ -501,15 +504,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
                         u.z &= ((kb >> 4) & 1u) * 0xffffu + ((kb >> 5) & 1u) * 0xffff0000u;
                         u.w &= ((kb >> 6) & 1u) * 0xffffu + ((kb >> 7) & 1u) * 0xffff0000u;
                     }
-                    *reinterpret_cast<uint4*>(prow + ((((g >> 3) + j) ^ (row & 7)) << 4)) = u;
+                    pk[4 * j] = u.x, pk[4 * j + 1] = u.y, pk[4 * j + 2] = u.z, pk[4 * j + 3] = u.w;
                 }
+                tmem_st16(t_p + t_row + half * 32 + (g >> 1), pk);
                 if (DROP && p.drop_bits && q < p.lq)
                     p.drop_bits[(((size_t)b * p.heads + h) * p.lq + q) * (p.lk32 >> 5) + ((kc0 + col0 + g) >> 5)] = keep_bits;
             }
             l_run = fmaf(l_run, alpha, sum);
             m_run = m_new;
-            // S_c is consumed (TMEM) and P_c is in shared memory: hand both to the issuer
-            fence_proxy_async_smem();
+            // S_c is consumed and P_c is stored (both TMEM): hand both to the issuer
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -1822,7 +1826,7 @@ extern "C" int shg_attn_fwd(const shg_attn_args* a, void* stream) {
         const CUtensorMap* tk2 = head_tmap(a->k, a->ldk, a->heads, a->lk, a->batch, kFwd2Chunk);
         const CUtensorMap* tv2 = head_tmap(a->v, a->ldv, a->heads, a->lk, a->batch, kFwd2Chunk);
         if (!tk2 || !tv2) return SHG_ECUDA;
-        const size_t smem2 = 81920 + (448 + 256) * 4 + sizeof(Fwd2Bars) + 16 + 1024;
+        const size_t smem2 = 49152 + (448 + 256) * 4 + sizeof(Fwd2Bars) + 16 + 1024;
         static bool attr2 = false;
         if (!attr2) {
             cudaFuncSetAttribute(attn_fwd2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
