@@ -1386,34 +1386,36 @@ attn_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         // ------------------------------------------------------------------ issuer: TMA loads and every product
         if (lane == 0) {
             const uint32_t idesc_dq = make_idesc_bf16(128, kHeadDim, 0, 1);
-            auto issue_s = [&](int j, int hh) {   // S = Q K_j^T ; dP = dO V_j^T  for the 32 keys of half hh
-                const int n = half_n16(j, hh);
-                if (n == 0) return;
+            // S = Q K_j^T ; dP = dO V_j^T for the whole 64-key chunk in ONE set of eight products (a tcgen05.mma costs the
+            // issuing thread ~47 clk whatever its width — tools/micro/mma_issue.cu — so the halves share the score
+            // products and keep only their own accumulating products); one commit per half that has keys
+            auto issue_s = [&](int j) {
+                const int n = half_n16(j, 0) + half_n16(j, 1);
                 const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
-                const uint32_t bk = smem_u32(sK + (j % 3) * 8192) + hh * 4096, bv = smem_u32(sV + (j % 3) * 8192) + hh * 4096;
+                const uint32_t bk = smem_u32(sK + (j % 3) * 8192), bv = smem_u32(sV + (j % 3) * 8192);
                 const uint32_t idesc_s = make_idesc_bf16(128, n, 0, 0);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16(t_s + hh * 32, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(bk + ks * 32, 16, 1024), idesc_s, ks > 0);
+                    umma_bf16(t_s, make_smem_desc(aq + ks * 32, 16, 1024), make_smem_desc(bk + ks * 32, 16, 1024), idesc_s, ks > 0);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16(t_dp + hh * 32, make_smem_desc(ado + ks * 32, 16, 1024), make_smem_desc(bv + ks * 32, 16, 1024), idesc_s, ks > 0);
-                tc_commit(&bars->s[hh]);
+                    umma_bf16(t_dp, make_smem_desc(ado + ks * 32, 16, 1024), make_smem_desc(bv + ks * 32, 16, 1024), idesc_s, ks > 0);
+                tc_commit(&bars->s[0]);
+                if (half_n16(j, 1) > 0) tc_commit(&bars->s[1]);
             };
             mbar_wait(&bars->res, 0);
             mbar_wait(&bars->chunk[0], 0);
             tc_fence_after();
-            issue_s(0, 0), issue_s(0, 1);
+            issue_s(0);
             bool first = true;
             for (int j = 0; j < n_kc; ++j) {
                 if (j + 1 < n_kc) {
+                    // chunk j is full here (only the last chunk can be short): both halves read their S/dP columns
                     mbar_wait(&bars->chunk[(j + 1) % 3], ((j + 1) / 3) & 1);
-                    for (int hh = 0; hh < 2; ++hh) {
-                        if (half_n16(j, hh) == 0) continue;
-                        mbar_wait(&bars->ld[hh], j & 1);        // the half's S/dP columns have been read
-                        tc_fence_after();
-                        issue_s(j + 1, hh);
-                    }
+                    mbar_wait(&bars->ld[0], j & 1);
+                    mbar_wait(&bars->ld[1], j & 1);
+                    tc_fence_after();
+                    issue_s(j + 1);
                 }
                 if (j >= 1 && j + 2 < n_kc) {
                     // K/V buffer (j - 1) % 3 is free once both halves' dQ products of chunk j - 1 retired
