@@ -19,6 +19,8 @@ B200-first choices (vs the reference's module-by-module eager fp32):
     wgrad accumulates with split-K fp32 atomics straight into the flat gradient buffer;
   * matching + weighted CE + its gradient never leave the device.
 """
+import os
+
 import torch
 
 from . import ops
@@ -71,6 +73,7 @@ class Engine:
         # are queued on their own stream and fill the SMs the dependent chain of small launches leaves idle
         self.sw = torch.cuda.Stream(self.dev) if self.use_streams else None
         self._keep = []          # operands of in-flight wgrads stay referenced until the final join
+        self.early_lang_bwd = os.environ.get("SHG_EARLY_LANG_BWD", "1") != "0"   # see backward_lang_start
 
     def _fork(self, *streams):
         """streams start after everything queued so far on the current stream."""
@@ -858,6 +861,8 @@ class Engine:
         for s in reversed(ctx["HGX"]):
             d_xl, d_xg = self._cross_bwd(self.hgx_layer, s, d_xl, d_xg, B, nl, ng, kmask, ctx["hg_kmask"])
         ctx["d_lang_l"] = d_xl
+        if self.early_lang_bwd:
+            self.backward_lang_start(ctx)
         # hypergraph assembly backward: cls / type-token gradients and the decoder-output gradients
         st = self.st
         ops.colsum_accum(d_xg.view(B, ng * H)[:, :H], st.g("hgq_encoder.cls_token").view(-1))
@@ -913,9 +918,14 @@ class Engine:
     # The second half of the backward in steps, so that a data-parallel trainer can start the all-reduce of each
     # group of gradients the moment it is final (HotPathTrainer.train_step): begin -> relation layers nr-1 .. 0 ->
     # end.  backward_early_params() below runs them in sequence (optionally in two parts).
-    def backward_early_begin(self, ctx):
-        """Language layers + embeddings on the side stream (40 tokens per clip: they finish long before the relation
-        side); the hoisted K/V dgrad on the main stream leaves the gradient w.r.t. the relation-layer output."""
+    def backward_lang_start(self, ctx):
+        """Language layers + embeddings on side stream s1.  Their input gradient (CrossEncoder branch + LXRT answer
+        branch) is complete as soon as the CrossEncoder's backward has run, i.e. BEFORE the decoders' backward: started
+        there, the 40-token language side fills the SMs that the decoders' chains of small kernels leave idle instead
+        of competing with the relation layers' large kernels later.  Idempotent per step."""
+        if ctx.get("_lang_started"):
+            return
+        ctx["_lang_started"] = True
         B = ctx["B"]
         nl = ctx["dims"][0]
         kmask = ctx["kmask"]
@@ -934,11 +944,16 @@ class Engine:
             de = ops.layernorm_bwd(d_lang, pre, E["ln"].g, mean, rstd, E["ln"].gg, E["ln"].gb, in_drop=d_emb)
             ops.call("shg_embed_scatter_bwd", ops.ptr(de), ops.ptr(ids), ops.ptr(seg), ops.ptr(E["gword"]), 0,
                      ops.ptr(E["gpos"]), 0, ops.ptr(E["gtype"]), 0, B * nl, nl, H, ops.stream())
+        ctx["_lang_pending"] = True
+
+    def backward_early_begin(self, ctx):
+        """The language side (if backward_late_params has not started it already) and the hoisted K/V dgrad on the main
+        stream, which leaves the gradient w.r.t. the relation-layer output."""
+        self.backward_lang_start(ctx)
         if "dkv_mem" in ctx:
             ctx["d_visn_mid"] = ops.gemm(ctx["dkv_mem"], self.kv_w, b_t=True, residual=ctx.get("d_x_visn"))
         else:
             ctx["d_visn_mid"] = ctx["d_x_visn"]
-        ctx["_lang_pending"] = True
 
     def backward_r_layer(self, ctx, i, need_dvisn=False):
         B, nv = ctx["B"], ctx["dims"][1]
