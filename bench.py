@@ -411,7 +411,7 @@ def run_ours(args):
                     "hot_path_tflop_per_step_per_gpu": round(TRAIN_GFLOP_PER_CLIP * BATCH_PER_GPU / 1e3, 2)})
         if world > 1:
             cfg["collective"] = ("fp32 NCCL all-reduce of the 191 M-element live gradient span in 6 groups, each issued when its "
-                                 "gradients are final (late | r4 | r3 | r2+language+embeddings | r1 | r0+vectors), captured in the step's graph")
+                                 "gradients are final (late+language+embeddings | r4 | r3 | r2 | r1 | r0+vectors), captured in the step's graph")
         line = {
             "metric": METRIC, "value": round(clips / (ms_step * 1e-3), 2),
             "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

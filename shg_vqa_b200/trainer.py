@@ -330,7 +330,14 @@ class HotPathTrainer:
             # the path's only collective, overlapped: every group of gradients is reduced as soon as it is final
             eng, grp = self.engine, self.store.dp_groups
             eng.backward_late_params(ctx, d_hg, d_rel, d_act)
-            works = self._reduce_async(grp["late"])
+            first = list(grp["late"])
+            lang_early = bool(ctx.get("_lang_started"))
+            if lang_early:
+                # the language side was started under the decoders' backward (Engine.backward_lang_start) and has
+                # finished by now: its matrices and the embedding tables go out with the first group
+                eng.backward_lang_join(ctx)
+                first += grp["lang"] + grp["emb"]
+            works = self._reduce_async(first)
             # from here to the end of the backward an all-reduce is in flight most of the time and owns some SMs:
             # the persistent GEMM grids leave those to it (include/shgvqa.h: shg_gemm_args.max_ctas)
             with ops.gemm_cta_cap(self.dp_gemm_ctas):
@@ -340,7 +347,7 @@ class HotPathTrainer:
                     if i == 0:
                         break
                     slices = list(grp["r%d" % i])
-                    if i == min(2, eng.nr - 1):
+                    if i == min(2, eng.nr - 1) and not lang_early:
                         eng.backward_lang_join(ctx)            # the 40-token language side finished long ago
                         slices += grp["lang"] + grp["emb"]
                     works += self._reduce_async(slices)
