@@ -1281,14 +1281,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 //     warps 4-7 half 1 (thread = tile row x 32 columns), warp 8 issues every TMA load and tcgen05.mma.  A half's score
 //     products, its exponentials and its accumulating products form their own chain, linked to the issuer by two
 //     mbarriers (values loaded / operand stored) — no block-wide barrier inside the loop; while one half does its
-//     exponentials the tensor core runs the other half's (and the other CTA's) products.
+//     exponentials the tensor core runs the other half's (and the other CTA's) products.  (In the dq pass the two halves
+//     share ONE set of score products per chunk — an instruction costs the issuing thread the same whatever its width —
+//     and keep their own accumulating products.)
 //   * the dS (dq pass) and P^T / dS^T (dkv pass) operands go registers -> tcgen05.st -> TMEM and feed the accumulating
 //     products as TMEM A operands (tcgen05.mma [d], [a], b-desc): no swizzled shared-memory tile, no proxy fence.  In the
 //     dkv pass they overwrite the first half of the very score columns their warp has just read (256 TMEM columns per
 //     CTA: S^T 64 | dP^T 64 | dK 64 | dV 64); the next score products into those columns are issued behind the products
 //     that read them, on the same in-order tensor pipe.
 //   * 393 keys are 7 chunks of 64 (400 of 448 columns useful, the last chunk 16 wide) instead of 4 of 128 (400 of 512).
-//   84 KB (dq) / 92 KB (dkv) of shared memory and 256 TMEM columns per CTA, 288 threads, <= 112 registers.
+//   84 KB (dq) / 92 KB (dkv) of shared memory and 256 TMEM columns per CTA, 288 threads, <= 96 registers (a 288-thread CTA is allocated as 320 threads).
 // =====================================================================================================
 constexpr int kB2Threads = 288;
 constexpr int kB2Chunk = 64;
@@ -1473,7 +1475,7 @@ attn_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             tc_fence_after();
             uint32_t ds0[8], ds1[8];
             const int key0 = j * kB2Chunk + c;
-            // two 16-column batches keep the live registers under 112
+            // two 16-column batches keep the live registers under the 96-register cap
             auto batch = [&](const int sb, uint32_t(&dsb)[8]) {
                 uint32_t rs[16], rp[16];
                 if (rows_live) {
